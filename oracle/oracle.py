@@ -1,0 +1,612 @@
+"""CPU oracle for the DIVA/SSA velocity-solve path (numpy + oracle/ufe_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- never imported by the product package.  Only tests/,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs
+load this module, as the checker and the CPU baseline.
+
+It restates, with file:line citations into the reference
+(``src/UFEMISM/ice_dynamics/conservation_of_momentum/SSA_DIVA/*.f90`` etc.):
+operator construction, the per-Picard-iteration closures, stiffness assembly, the linear
+solve (exact sparse direct solve as ground truth; GMRES(30)+block-Jacobi/ILU(0) as the
+PETSc-defaults restatement) and the Picard drivers ``solve_DIVA`` / ``solve_SSA``.
+
+Parity pinning: see the header of ufe_oracle.c.  KSPSolve iterates: parity unpinned (the
+reference holds no known-answer test for them); everything else is pinned by
+tests/test_oracle_golden.py against the reference's own unit-test vectors.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ice_density = 910.0      # src/UPSY/basic/parameters.f90:52
+grav = 9.81              # :49
+pi = 3.141592653589793   # :44
+R_gas = 8.314            # :56
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libufe_oracle.so")
+    src = os.path.join(_HERE, "ufe_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libufe_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ct.CDLL(build())
+        _LIB.ora_calc_operators_a_b.restype = ct.c_int
+        _LIB.ora_calc_operators_b_a.restype = ct.c_int
+        _LIB.ora_calc_operators_b_b_2nd.restype = ct.c_int
+        _LIB.ora_assemble_stiffness.restype = ct.c_int
+        _LIB.ora_ksp_gmres_bjacobi_ilu0.restype = ct.c_int
+        _LIB.ora_jacobi.restype = ct.c_int
+    return _LIB
+
+
+class _OraMesh(ct.Structure):
+    _fields_ = [("nV", ct.c_int), ("nTri", ct.c_int), ("nC_mem", ct.c_int),
+                ("V", ct.c_void_p), ("Tri", ct.c_void_p), ("TriC", ct.c_void_p),
+                ("C", ct.c_void_p), ("nC", ct.c_void_p), ("iTri", ct.c_void_p),
+                ("niTri", ct.c_void_p), ("VBI", ct.c_void_p), ("TriBI", ct.c_void_p),
+                ("TriGC", ct.c_void_p),
+                ("xmin", ct.c_double), ("xmax", ct.c_double), ("ymin", ct.c_double),
+                ("ymax", ct.c_double)]
+
+
+def _p(a):
+    return a.ctypes.data_as(ct.c_void_p)
+
+
+def _cmesh(mesh):
+    return _OraMesh(mesh.nV, mesh.nTri, mesh.nC_mem, _p(mesh.V), _p(mesh.Tri), _p(mesh.TriC),
+                    _p(mesh.C), _p(mesh.nC), _p(mesh.iTri), _p(mesh.niTri), _p(mesh.VBI),
+                    _p(mesh.TriBI), _p(mesh.TriGC), mesh.xmin, mesh.xmax, mesh.ymin, mesh.ymax)
+
+
+@dataclass
+class CSR:
+    """``type_sparse_matrix_CSR_dp`` (CSR_sparse_matrix_type.f90:15-38): ptr = local 1-based
+    offsets for rows i1..i2, ind = global 1-based columns (unsorted), val."""
+    m: int
+    n: int
+    i1: int
+    i2: int
+    ptr: np.ndarray
+    ind: np.ndarray
+    val: np.ndarray
+
+    @property
+    def nnz(self):
+        return int(self.ptr[-1] - 1)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.val, self.ind.astype(np.int64) - 1,
+                              self.ptr.astype(np.int64) - 1), shape=(self.i2 - self.i1 + 1, self.n))
+
+
+def partition_list(ntot, i, n):
+    i1, i2 = ct.c_int(), ct.c_int()
+    lib().ora_partition_list(ntot, i, n, ct.byref(i1), ct.byref(i2))
+    return i1.value, i2.value
+
+
+def spmv(A: CSR, x_tot: np.ndarray, threaded=False) -> np.ndarray:
+    """multiply_CSR_matrix_with_vector_1D (CSR_matrix_vector_multiplication.f90:198-334)."""
+    x_tot = np.ascontiguousarray(x_tot, dtype=np.float64)
+    y = np.empty(A.i2 - A.i1 + 1)
+    f = lib().ora_spmv_mt if threaded else lib().ora_spmv
+    f(ct.c_int(y.size), _p(A.ptr), _p(A.ind), _p(A.val), _p(x_tot), _p(y))
+    return y
+
+
+def spmv_2D(A: CSR, X: np.ndarray, threaded=False) -> np.ndarray:
+    """multiply_CSR_matrix_with_vector_2D (:336-364): one 1-D SpMV per layer."""
+    Y = np.empty((A.i2 - A.i1 + 1, X.shape[1]), order="F")
+    for k in range(X.shape[1]):
+        Y[:, k] = spmv(A, np.ascontiguousarray(X[:, k]), threaded)
+    return Y
+
+
+# --------------------------------------------------------------------------------------
+# operator construction (mesh_disc_calc_matrix_operators_2D.f90:26-59)
+# --------------------------------------------------------------------------------------
+def calc_operator_rows(mesh, family, row1, row2):
+    """Rows row1..row2 (1-based inclusive) of one operator family.
+    family 'a_b' -> (M_map_a_b, M_ddx_a_b, M_ddy_a_b); 'b_a' likewise;
+    'b_b_2nd' -> (M2_ddx, M2_ddy, M2_d2dx2, M2_d2dxdy, M2_d2dy2)_b_b."""
+    cm = _cmesh(mesh)
+    m_loc = row2 - row1 + 1
+    cap = max(1, m_loc) * (mesh.nC_mem + 1)
+    ptr = np.zeros(m_loc + 1, dtype=np.int32)
+    ind = np.zeros(cap, dtype=np.int32)
+    nv = 5 if family == "b_b_2nd" else 3
+    vals = [np.zeros(cap) for _ in range(nv)]
+    fn = {"a_b": lib().ora_calc_operators_a_b, "b_a": lib().ora_calc_operators_b_a,
+          "b_b_2nd": lib().ora_calc_operators_b_b_2nd}[family]
+    nnz = fn(ct.byref(cm), ct.c_int(row1), ct.c_int(row2), ct.c_int(cap), _p(ptr), _p(ind),
+             *[_p(v) for v in vals])
+    if nnz < 0:
+        raise RuntimeError("operator construction overflowed its nnz estimate")
+    n = {"a_b": mesh.nV, "b_a": mesh.nTri, "b_b_2nd": mesh.nTri}[family]
+    m = {"a_b": mesh.nTri, "b_a": mesh.nV, "b_b_2nd": mesh.nTri}[family]
+    ind = ind[:nnz].copy()
+    return [CSR(m, n, row1, row2, ptr, ind, v[:nnz].copy()) for v in vals]
+
+
+def calc_all_matrix_operators_mesh(mesh):
+    ops = {}
+    a_b = calc_operator_rows(mesh, "a_b", 1, mesh.nTri)
+    ops["M_map_a_b"], ops["M_ddx_a_b"], ops["M_ddy_a_b"] = a_b
+    b_a = calc_operator_rows(mesh, "b_a", 1, mesh.nV)
+    ops["M_map_b_a"], ops["M_ddx_b_a"], ops["M_ddy_b_a"] = b_a
+    b_b = calc_operator_rows(mesh, "b_b_2nd", 1, mesh.nTri)
+    (ops["M2_ddx_b_b"], ops["M2_ddy_b_b"], ops["M2_d2dx2_b_b"], ops["M2_d2dxdy_b_b"],
+     ops["M2_d2dy2_b_b"]) = b_b
+    mesh.ops = ops
+    return ops
+
+
+# --------------------------------------------------------------------------------------
+# vertical integrals (mesh_zeta.f90:163-194, :257-283)
+# --------------------------------------------------------------------------------------
+def integrate_from_zeta_is_one_to_zeta_is_zetap(zeta, F):
+    nz = zeta.size
+    out = np.zeros_like(F)
+    for k in range(nz - 2, -1, -1):
+        out[:, k] = out[:, k + 1] - 0.5 * (F[:, k + 1] + F[:, k]) * (zeta[k + 1] - zeta[k])
+    return out
+
+
+def vertical_average(zeta, F):
+    avg = np.zeros(F.shape[0])
+    for k in range(zeta.size - 1):
+        avg = avg + 0.5 * (F[:, k + 1] + F[:, k]) * (zeta[k + 1] - zeta[k])
+    return avg
+
+
+# --------------------------------------------------------------------------------------
+# rheology and sliding
+# --------------------------------------------------------------------------------------
+def calc_ice_rheology_Glen(mesh, ice, C):
+    """constitutive_equation.f90:84-163."""
+    nV, nz = mesh.nV, mesh.nz
+    if C.choice_ice_rheology_Glen == "uniform":
+        A = np.full((nV, nz), C.uniform_Glens_flow_factor, order="F")
+    elif C.choice_ice_rheology_Glen == "Huybrechts1992":
+        Ti = ice.Ti
+        lo = 1.14e-05 * np.exp(-6.0e04 / (R_gas * Ti))
+        hi = 5.47e10 * np.exp(-13.9e04 / (R_gas * Ti))
+        A = np.asfortranarray(np.where(Ti < 263.15, lo, hi))
+    else:
+        raise ValueError('unknown choice_ice_rheology_Glen "%s"!' % C.choice_ice_rheology_Glen)
+    gr = ice.mask_grounded_ice.astype(bool)
+    fl = ice.mask_floating_ice.astype(bool)
+    if C.choice_enhancement_factor_transition == "separate":
+        f = np.where(gr, C.m_enh_sheet, np.where(fl, C.m_enh_shelf, 1.0))
+    elif C.choice_enhancement_factor_transition == "interp":
+        interp = (ice.Hi > 0.0) & (ice.Hib < ice.SL)
+        fi = ice.fraction_gr * C.m_enh_sheet + (1.0 - ice.fraction_gr) * C.m_enh_shelf
+        f = np.where(interp, fi, np.where(gr, C.m_enh_sheet, np.where(fl, C.m_enh_shelf, 1.0)))
+    else:
+        raise ValueError("unknown choice_enhancement_factor_transition")
+    return A * f[:, None]
+
+
+def Schoof2006_icestream(A, n, H, tantheta, L, m, y):
+    """Schoof_SSA_solution.f90:9-63; returns (u, tau_yield)."""
+    f = -ice_density * grav * H * tantheta
+    B = A ** (-1.0 / 3.0)
+    W = L * (m + 1.0) ** (1.0 / m)
+    tau_yield = f * np.abs(y / L) ** m
+    ua = -2.0 * f ** 3 * L ** 4 / (B ** 3 * H ** 3)
+    ub = (1.0 / 4.0) * ((y / L) ** 4.0 - (m + 1.0) ** (4.0 / m))
+    uc = (-3.0 / ((m + 1.0) * (m + 4.0))) * (np.abs(y / L) ** (m + 4.0) - (m + 1.0) ** (1.0 + (4.0 / m)))
+    ud = (3.0 / ((m + 1.0) ** 2 * (2.0 * m + 4.0))) * (np.abs(y / L) ** (2 * m + 4.0) - (m + 1.0) ** (2.0 + (4.0 / m)))
+    ue = (-1.0 / ((m + 1.0) ** 3 * (3.0 * m + 4.0))) * (np.abs(y / L) ** (3 * m + 4.0) - (m + 1.0) ** (3.0 + (4.0 / m)))
+    u = ua * (ub + uc + ud + ue)
+    u = np.where(np.abs(y) > W, 0.0, u)
+    return u, tau_yield
+
+
+def _till_yield_stress(mesh, ice, C):
+    """till_yield_stress + extend_till_yield_stress_to_neighbours (sliding_laws.f90
+    :133-137, 370-409).  do_subgrid_friction_on_A_grid = .false. path (:330-333)."""
+    if C.do_subgrid_friction_on_A_grid:
+        raise NotImplementedError("do_subgrid_friction_on_A_grid (needs Hs_slope, gl masks)")
+    tys = ice.effective_pressure * np.tan(pi / 180.0) * ice.till_friction_angle
+    out = tys.copy()
+    land = np.nonzero(ice.mask_icefree_land)[0]
+    gr = ice.mask_grounded_ice.astype(bool)
+    for vi in land:
+        found = False
+        mn = 1000.0 * ice_density * grav
+        for ci in range(mesh.nC[vi]):
+            vc = mesh.C[vi, ci] - 1
+            if gr[vc]:
+                mn = min(mn, tys[vc])
+                found = True
+        out[vi] = mn if found else C.Hi_min * ice_density * grav
+    return out
+
+
+def calc_basal_friction_coefficient(mesh, ice, C, u_b, v_b, cache=None):
+    """sliding_laws.f90:25-81 and the individual laws."""
+    ops = mesh.ops
+    u_a = spmv(ops["M_map_b_a"], u_b)
+    v_a = spmv(ops["M_map_b_a"], v_b)
+    law = C.choice_sliding_law
+    uabs = np.sqrt(C.slid_delta_v ** 2 + u_a ** 2 + v_a ** 2)
+    if law == "no_sliding":
+        beta = np.zeros(mesh.nV)
+    elif law == "idealised":
+        ch = C.choice_idealised_sliding_law
+        x, y = mesh.V[:, 0], mesh.V[:, 1]
+        if ch == "SSA_icestream":
+            _, tys = Schoof2006_icestream(C.uniform_Glens_flow_factor, C.Glens_flow_law_exponent,
+                                          C.refgeo_idealised_SSA_icestream_Hi,
+                                          C.refgeo_idealised_SSA_icestream_dhdx,
+                                          C.refgeo_idealised_SSA_icestream_L,
+                                          C.refgeo_idealised_SSA_icestream_m, y)
+            beta = tys / uabs
+        elif ch == "ISMIP-HOM_C":
+            L = C.refgeo_idealised_ISMIP_HOM_L
+            beta = 1000.0 + 1000.0 * np.sin(2.0 * pi * x / L) * np.sin(2.0 * pi * y / L)
+        elif ch == "ISMIP-HOM_D":
+            L = C.refgeo_idealised_ISMIP_HOM_L
+            beta = 1000.0 + 1000.0 * np.sin(2.0 * pi * x / L)
+        elif ch == "ISMIP-HOM_F":
+            beta = np.full(mesh.nV, (C.uniform_Glens_flow_factor * 1000.0) ** (-1.0))
+        else:
+            raise ValueError('unknown choice_idealised_sliding_law "%s"' % ch)
+    elif law == "Weertman":
+        beta = ice.beta_sq * uabs ** (1.0 / C.slid_Weertman_m - 1.0)
+    elif law in ("Coulomb", "Budd", "Zoet-Iverson"):
+        tys = _till_yield_stress(mesh, ice, C)
+        if law == "Coulomb":
+            beta = tys / uabs
+        elif law == "Budd":
+            beta = tys * uabs ** (C.slid_Budd_q_plastic - 1.0) / (C.slid_Budd_u_threshold ** C.slid_Budd_q_plastic)
+        else:
+            beta = tys * (uabs ** (1.0 / C.slid_ZI_p - 1.0)) * ((uabs + C.slid_ZI_ut) ** (-1.0 / C.slid_ZI_p))
+    elif law == "Tsai2015":
+        beta = np.minimum(ice.alpha_sq * ice.effective_pressure,
+                          ice.beta_sq * uabs ** (1.0 / C.slid_Weertman_m)) * uabs ** (-1.0)
+    elif law == "Schoof2005":
+        m = C.slid_Weertman_m
+        aN = ice.alpha_sq * ice.effective_pressure
+        beta = ((ice.beta_sq * uabs ** (1.0 / m) * aN) /
+                ((ice.beta_sq ** m * uabs + aN ** m) ** (1.0 / m))) * uabs ** (-1.0)
+    else:
+        raise ValueError('unknown choice_sliding_law "%s"' % law)
+    return np.minimum(C.slid_beta_max, beta)
+
+
+# --------------------------------------------------------------------------------------
+# linearised solve (solve_linearised_SSA_DIVA.f90:23-178)
+# --------------------------------------------------------------------------------------
+from ufemism2_0_b200.config import BC_CODES  # noqa: E402  (plain data, no product code path)
+
+
+def assemble_stiffness(mesh, C, N_b, dN_dx_b, dN_dy_b, beta_b, tau_dx_b, tau_dy_b, u_b_prev,
+                       v_b_prev, bc_mask=None, bc_u=None, bc_v=None, ti1=1, ti2=None):
+    """Assembly part of solve_SSA_DIVA_linearised (:61-153). Returns (A: CSR, bb)."""
+    if ti2 is None:
+        ti2 = mesh.nTri
+    ops = mesh.ops
+    M2 = ops["M2_ddx_b_b"]
+    nloc = ti2 - ti1 + 1
+    cap = max(4 * M2.nnz, 16) if (ti1 == 1 and ti2 == mesh.nTri) else 4 * nloc * (mesh.nC_mem + 1)
+    ptr = np.zeros(2 * nloc + 1, dtype=np.int32)
+    ind = np.zeros(cap, dtype=np.int32)
+    val = np.zeros(cap)
+    bb = np.zeros(2 * nloc)
+    if bc_mask is None:
+        bc_mask = np.zeros(mesh.nTri, dtype=np.int32)
+        bc_u = np.zeros(mesh.nTri)
+        bc_v = np.zeros(mesh.nTri)
+    codes_u = np.array([BC_CODES[C.BC_u_north], BC_CODES[C.BC_u_east], BC_CODES[C.BC_u_south],
+                        BC_CODES[C.BC_u_west]], dtype=np.int32)
+    codes_v = np.array([BC_CODES[C.BC_v_north], BC_CODES[C.BC_v_east], BC_CODES[C.BC_v_south],
+                        BC_CODES[C.BC_v_west]], dtype=np.int32)
+    cm = _cmesh(mesh)
+    c = np.ascontiguousarray
+    args = [c(a, dtype=np.float64) for a in (N_b, dN_dx_b, dN_dy_b, beta_b, tau_dx_b, tau_dy_b,
+                                             u_b_prev, v_b_prev)]
+    bc_mask = c(bc_mask, dtype=np.int32)
+    bc_u = c(bc_u, dtype=np.float64)
+    bc_v = c(bc_v, dtype=np.float64)
+    nnz = lib().ora_assemble_stiffness(
+        ct.byref(cm), ct.c_int(ti1), ct.c_int(ti2), _p(M2.ptr), _p(M2.ind), _p(M2.val),
+        _p(ops["M2_ddy_b_b"].val), _p(ops["M2_d2dx2_b_b"].val), _p(ops["M2_d2dxdy_b_b"].val),
+        _p(ops["M2_d2dy2_b_b"].val), *[_p(a) for a in args], _p(bc_mask), _p(bc_u), _p(bc_v),
+        _p(codes_u), _p(codes_v), ct.c_int(1 if C.do_include_SSADIVA_crossterms else 0),
+        ct.c_double(C.visc_it_relax), ct.c_double(C.refgeo_idealised_ISMIP_HOM_L),
+        ct.c_int(cap), _p(ptr), _p(ind), _p(val), _p(bb))
+    if nnz < 0:
+        raise RuntimeError("stiffness assembly overflowed its nnz estimate")
+    A = CSR(2 * mesh.nTri, 2 * mesh.nTri, 2 * ti1 - 1, 2 * ti2, ptr, ind[:nnz].copy(), val[:nnz].copy())
+    return A, bb
+
+
+def ksp_solve(A: CSR, b, rtol, abstol, nranks=1, maxits=10000):
+    """PETSc-defaults restatement (petsc_basic.f90:66-141): GMRES(30) + bjacobi/ILU(0)."""
+    n = A.m
+    x = np.zeros(n)
+    reason = ct.c_int()
+    rn = ct.c_double()
+    its = lib().ora_ksp_gmres_bjacobi_ilu0(ct.c_int(n), _p(A.ptr), _p(A.ind), _p(A.val),
+                                           _p(np.ascontiguousarray(b)), _p(x), ct.c_double(rtol),
+                                           ct.c_double(abstol), ct.c_int(nranks), ct.c_int(maxits),
+                                           ct.byref(reason), ct.byref(rn))
+    return x, its, reason.value, rn.value
+
+
+def direct_solve(A: CSR, b):
+    import scipy.sparse.linalg as spla
+    return spla.splu(A.to_scipy().tocsc()).solve(np.asarray(b))
+
+
+def solve_SSA_DIVA_linearised(mesh, C, u_b, v_b, N_b, dN_dx_b, dN_dy_b, beta_b, tau_dx_b, tau_dy_b,
+                              rtol, abstol, linear_solver="direct", nranks=1,
+                              bc_mask=None, bc_u=None, bc_v=None, return_system=False):
+    """solve_SSA_DIVA_linearised (:23-178). Returns (u_b, v_b, u_b_prev, v_b_prev, n_its)."""
+    u_b_prev, v_b_prev = u_b.copy(), v_b.copy()      # gather_to_all, :54-55
+    A, bb = assemble_stiffness(mesh, C, N_b, dN_dx_b, dN_dy_b, beta_b, tau_dx_b, tau_dy_b,
+                               u_b_prev, v_b_prev, bc_mask, bc_u, bc_v)
+    if linear_solver == "direct":
+        x = direct_solve(A, bb)
+        its = 0
+    else:
+        x, its, _, _ = ksp_solve(A, bb, rtol, abstol, nranks)
+    u_new, v_new = x[0::2].copy(), x[1::2].copy()     # tiuv2n de-interleave, :163-173
+    if return_system:
+        return u_new, v_new, u_b_prev, v_b_prev, its, A, bb
+    return u_new, v_new, u_b_prev, v_b_prev, its
+
+
+# --------------------------------------------------------------------------------------
+# SSA_DIVA_utilities.f90
+# --------------------------------------------------------------------------------------
+def calc_driving_stress(mesh, ice):
+    """:21-57"""
+    ops = mesh.ops
+    Hi_b = spmv(ops["M_map_a_b"], ice.Hi)
+    dHs_dx_b = spmv(ops["M_ddx_a_b"], ice.Hs)
+    dHs_dy_b = spmv(ops["M_ddy_a_b"], ice.Hs)
+    return -ice_density * grav * Hi_b * dHs_dx_b, -ice_density * grav * Hi_b * dHs_dy_b
+
+
+def apply_velocity_limits(C, u, v):
+    """:110-141"""
+    uabs = np.sqrt(u ** 2 + v ** 2)
+    over = uabs > C.vel_max
+    safe = np.where(over, uabs, 1.0)
+    return np.where(over, u * C.vel_max / safe, u), np.where(over, v * C.vel_max / safe, v)
+
+
+def relax_viscosity_iterations(u, v, up, vp, r):
+    """:84-108"""
+    return (r * u) + ((1.0 - r) * up), (r * v) + ((1.0 - r) * vp)
+
+
+def calc_L2_norm_uv(u, v, up, vp):
+    """:143-184"""
+    res1 = np.sum((u - up) ** 2) + np.sum((v - vp) ** 2)
+    res2 = np.sum((u + up) ** 2) + np.sum((v + vp) ** 2)
+    return 2.0 * res1 / max(res2, 1e-8)
+
+
+# --------------------------------------------------------------------------------------
+# solve_DIVA (DIVA_main.f90:88-262) and solve_SSA (SSA_main.f90:87-242)
+# --------------------------------------------------------------------------------------
+class PicardDiverged(RuntimeError):
+    pass
+
+
+def new_DIVA_state(mesh):
+    """allocate_DIVA_solver (DIVA_main.f90:752-804), 'zero' initial velocities."""
+    nV, nT, nz = mesh.nV, mesh.nTri, mesh.nz
+    z2 = lambda n: np.zeros((n, nz), order="F")
+    return dict(u_vav_b=np.zeros(nT), v_vav_b=np.zeros(nT), u_base_b=np.zeros(nT), v_base_b=np.zeros(nT),
+                u_3D_b=z2(nT), v_3D_b=z2(nT), tau_bx_b=np.zeros(nT), tau_by_b=np.zeros(nT),
+                eta_3D_b=z2(nT))
+
+
+def solve_DIVA(mesh, ice, C, D, linear_solver="direct", nranks=1, bc_mask=None, bc_u=None,
+               bc_v=None, trace=None):
+    """Returns (n_visc_its, n_Axb_its). D (state dict) is updated in place."""
+    ops = mesh.ops
+    zeta = mesh.zeta
+    nz = mesh.nz
+    n_exp = C.Glens_flow_law_exponent
+    if not np.any(ice.mask_grounded_ice):                                 # :123-134
+        for k in ("u_vav_b", "v_vav_b", "u_base_b", "v_base_b", "u_3D_b", "v_3D_b"):
+            D[k][...] = 0.0
+        return 0, 0
+    D["tau_dx_b"], D["tau_dy_b"] = calc_driving_stress(mesh, ice)         # :155
+    L2_uv = 1e9
+    nit_diverg_consec = 0
+    relax = C.visc_it_relax
+    eps0 = C.Glens_flow_law_epsilon_sq_0
+    n_Axb_its = 0
+    it = 0
+    Hi_sp = np.maximum(np.float64(np.float32(0.1)), ice.Hi)              # max(0.1, Hi), :468 (default-real literal)
+    Hi_dp = np.maximum(0.1, ice.Hi)                                       # max(0.1_dp, Hi), :503
+    converged = False
+    while not converged:
+        it += 1
+        u, v = D["u_vav_b"], D["v_vav_b"]
+        # calc_horizontal_strain_rates, SSA_DIVA_utilities.f90:59-82
+        D["du_dx_a"] = spmv(ops["M_ddx_b_a"], u)
+        D["du_dy_a"] = spmv(ops["M_ddy_b_a"], u)
+        D["dv_dx_a"] = spmv(ops["M_ddx_b_a"], v)
+        D["dv_dy_a"] = spmv(ops["M_ddy_b_a"], v)
+        # calc_vertical_shear_strain_rates, DIVA_main.f90:375-410
+        den = np.maximum(C.visc_eff_min, D["eta_3D_b"])
+        du_dz_b = np.asfortranarray(D["tau_bx_b"][:, None] * zeta[None, :] / den)
+        dv_dz_b = np.asfortranarray(D["tau_by_b"][:, None] * zeta[None, :] / den)
+        D["du_dz_3D_a"] = spmv_2D(ops["M_map_b_a"], du_dz_b)
+        D["dv_dz_3D_a"] = spmv_2D(ops["M_map_b_a"], dv_dz_b)
+        # calc_effective_viscosity, :412-479
+        A_min = 1e-18
+        eta_max = 0.5 * A_min ** (-1.0 / n_exp) * eps0 ** ((1.0 - n_exp) / (2.0 * n_exp))
+        if C.choice_flow_law != "Glen":
+            raise ValueError('unknown choice_flow_law "%s"!' % C.choice_flow_law)
+        A_flow = calc_ice_rheology_Glen(mesh, ice, C)
+        eps_sq = (D["du_dx_a"][:, None] ** 2 + D["dv_dy_a"][:, None] ** 2 +
+                  (D["du_dx_a"] * D["dv_dy_a"])[:, None] +
+                  0.25 * (D["du_dy_a"] + D["dv_dx_a"])[:, None] ** 2 +
+                  0.25 * (D["du_dz_3D_a"] ** 2 + D["dv_dz_3D_a"] ** 2) + eps0)
+        eta = 0.5 * A_flow ** (-1.0 / n_exp) * eps_sq ** ((1.0 - n_exp) / (2.0 * n_exp))
+        eta = np.asfortranarray(np.minimum(np.maximum(eta, C.visc_eff_min), eta_max))
+        D["eta_3D_a"] = eta
+        D["eta_3D_b"] = spmv_2D(ops["M_map_a_b"], eta)
+        D["eta_vav_a"] = vertical_average(zeta, eta)
+        D["N_a"] = D["eta_vav_a"] * Hi_sp
+        D["N_b"] = spmv(ops["M_map_a_b"], D["N_a"])
+        D["dN_dx_b"] = spmv(ops["M_ddx_a_b"], D["N_a"])
+        D["dN_dy_b"] = spmv(ops["M_ddy_a_b"], D["N_a"])
+        # calc_F_integrals, :481-520
+        F1 = -Hi_dp[:, None] * integrate_from_zeta_is_one_to_zeta_is_zetap(zeta, zeta[None, :] / eta)
+        F2 = -Hi_dp[:, None] * integrate_from_zeta_is_one_to_zeta_is_zetap(zeta, zeta[None, :] ** 2 / eta)
+        D["F1_3D_a"], D["F2_3D_a"] = np.asfortranarray(F1), np.asfortranarray(F2)
+        D["F1_3D_b"] = spmv_2D(ops["M_map_a_b"], D["F1_3D_a"])
+        D["F2_3D_b"] = spmv_2D(ops["M_map_a_b"], D["F2_3D_a"])
+        # calc_effective_basal_friction_coefficient, :522-574
+        beta_a = calc_basal_friction_coefficient(mesh, ice, C, D["u_base_b"], D["v_base_b"])
+        D["basal_friction_coefficient_a"] = beta_a
+        if C.choice_sliding_law == "no_sliding":
+            D["beta_eff_a"] = 1.0 / D["F2_3D_a"][:, 0]
+        else:
+            D["beta_eff_a"] = beta_a / (1.0 + beta_a * D["F2_3D_a"][:, 0])
+        D["basal_friction_coefficient_b"] = spmv(ops["M_map_a_b"], beta_a)
+        D["beta_eff_b"] = spmv(ops["M_map_a_b"], D["beta_eff_a"])
+        if C.do_GL_subgrid_friction:
+            D["beta_eff_b"] = D["beta_eff_b"] * ice.fraction_gr_b ** C.subgrid_friction_exponent_on_B_grid
+        # linearised solve, :189-192
+        res = solve_SSA_DIVA_linearised(mesh, C, u, v, D["N_b"], D["dN_dx_b"], D["dN_dy_b"],
+                                        D["beta_eff_b"], D["tau_dx_b"], D["tau_dy_b"],
+                                        C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol,
+                                        linear_solver, nranks, bc_mask, bc_u, bc_v)
+        u, v, up, vp, its = res
+        D["u_b_prev"], D["v_b_prev"] = up, vp
+        n_Axb_its += its
+        u, v = apply_velocity_limits(C, u, v)
+        u, v = relax_viscosity_iterations(u, v, up, vp, relax)
+        D["u_vav_b"], D["v_vav_b"] = u, v
+        # calc_basal_velocities :601-634, calc_basal_shear_stress :576-599
+        if C.choice_sliding_law == "no_sliding":
+            D["u_base_b"], D["v_base_b"] = np.zeros_like(u), np.zeros_like(v)
+        else:
+            dn = 1.0 + D["basal_friction_coefficient_b"] * D["F2_3D_b"][:, 0]
+            D["u_base_b"], D["v_base_b"] = u / dn, v / dn
+        D["tau_bx_b"], D["tau_by_b"] = u * D["beta_eff_b"], v * D["beta_eff_b"]
+        L2_prev = L2_uv
+        L2_uv = calc_L2_norm_uv(u, v, up, vp)
+        if trace is not None:
+            trace.append((it, L2_uv, its))
+        if L2_uv > L2_prev:
+            nit_diverg_consec += 1
+        else:
+            nit_diverg_consec = 0
+        if nit_diverg_consec > 2:
+            nit_diverg_consec = 0
+            relax *= 0.9
+            eps0 *= 1.2
+        if relax <= 0.05 or eps0 >= 1e-5:
+            if relax < 0.05:
+                raise PicardDiverged("viscosity iteration still diverges even with very low relaxation factor!")
+            elif eps0 > 1e-5:
+                raise PicardDiverged("viscosity iteration still diverges even with very high effective strain rate regularisation!")
+        converged = L2_uv < C.visc_it_norm_dUV_tol
+        if it > C.visc_it_nit:
+            break
+    # calc_3D_velocities, :636-676
+    if C.choice_sliding_law == "no_sliding":
+        D["u_3D_b"] = np.asfortranarray(D["tau_bx_b"][:, None] * D["F1_3D_b"])
+        D["v_3D_b"] = np.asfortranarray(D["tau_by_b"][:, None] * D["F1_3D_b"])
+    else:
+        f = 1.0 + D["basal_friction_coefficient_b"][:, None] * D["F1_3D_b"]
+        D["u_3D_b"] = np.asfortranarray(D["u_base_b"][:, None] * f)
+        D["v_3D_b"] = np.asfortranarray(D["v_base_b"][:, None] * f)
+    return it, n_Axb_its
+
+
+def solve_SSA(mesh, ice, C, S, linear_solver="direct", nranks=1, bc_mask=None, bc_u=None,
+              bc_v=None, trace=None):
+    """solve_SSA (SSA_main.f90:87-242). S = dict(u_b, v_b)."""
+    ops = mesh.ops
+    n_exp = C.Glens_flow_law_exponent
+    if not np.any(ice.mask_grounded_ice):
+        S["u_b"][...] = 0.0
+        S["v_b"][...] = 0.0
+        return 0, 0
+    S["tau_dx_b"], S["tau_dy_b"] = calc_driving_stress(mesh, ice)
+    L2_uv = 1e9
+    nit_diverg_consec = 0
+    relax = C.visc_it_relax
+    eps0 = C.Glens_flow_law_epsilon_sq_0
+    n_Axb_its = 0
+    it = 0
+    converged = False
+    while not converged:
+        it += 1
+        u, v = S["u_b"], S["v_b"]
+        du_dx = spmv(ops["M_ddx_b_a"], u)
+        du_dy = spmv(ops["M_ddy_b_a"], u)
+        dv_dx = spmv(ops["M_ddx_b_a"], v)
+        dv_dy = spmv(ops["M_ddy_b_a"], v)
+        A_min = 1e-18
+        eta_max = 0.5 * A_min ** (-1.0 / n_exp) * eps0 ** ((1.0 - n_exp) / (2.0 * n_exp))
+        A_flow = calc_ice_rheology_Glen(mesh, ice, C)
+        A_vav = vertical_average(mesh.zeta, A_flow)                       # SSA_main.f90:300-312
+        eps_sq = du_dx ** 2 + dv_dy ** 2 + du_dx * dv_dy + 0.25 * (du_dy + dv_dx) ** 2 + eps0
+        eta = 0.5 * A_vav ** (-1.0 / n_exp) * eps_sq ** ((1.0 - n_exp) / (2.0 * n_exp))
+        eta = np.minimum(np.maximum(eta, C.visc_eff_min), eta_max)
+        N_a = eta * np.maximum(0.1, ice.Hi)                               # :382, 0.1_dp
+        S["eta_a"], S["N_a"] = eta, N_a
+        N_b = spmv(ops["M_map_a_b"], N_a)
+        dN_dx_b = spmv(ops["M_ddx_a_b"], N_a)
+        dN_dy_b = spmv(ops["M_ddy_a_b"], N_a)
+        beta_a = calc_basal_friction_coefficient(mesh, ice, C, u, v)
+        beta_b = spmv(ops["M_map_a_b"], beta_a)
+        if C.do_GL_subgrid_friction:
+            beta_b = beta_b * ice.fraction_gr_b ** C.subgrid_friction_exponent_on_B_grid
+        S["N_b"], S["dN_dx_b"], S["dN_dy_b"], S["basal_friction_coefficient_b"] = N_b, dN_dx_b, dN_dy_b, beta_b
+        u, v, up, vp, its = solve_SSA_DIVA_linearised(
+            mesh, C, u, v, N_b, dN_dx_b, dN_dy_b, beta_b, S["tau_dx_b"], S["tau_dy_b"],
+            C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol, linear_solver, nranks,
+            bc_mask, bc_u, bc_v)
+        n_Axb_its += its
+        u, v = apply_velocity_limits(C, u, v)
+        u, v = relax_viscosity_iterations(u, v, up, vp, relax)
+        S["u_b"], S["v_b"], S["u_b_prev"], S["v_b_prev"] = u, v, up, vp
+        L2_prev = L2_uv
+        L2_uv = calc_L2_norm_uv(u, v, up, vp)
+        if trace is not None:
+            trace.append((it, L2_uv, its))
+        nit_diverg_consec = nit_diverg_consec + 1 if L2_uv > L2_prev else 0
+        if nit_diverg_consec > 2:
+            nit_diverg_consec = 0
+            relax *= 0.9
+            eps0 *= 1.2
+        if relax <= 0.05 or eps0 >= 1e-5:
+            if relax < 0.05:
+                raise PicardDiverged("viscosity iteration still diverges even with very low relaxation factor!")
+            elif eps0 > 1e-5:
+                raise PicardDiverged("viscosity iteration still diverges even with very high effective strain rate regularisation!")
+        converged = L2_uv < C.visc_it_norm_dUV_tol
+        if it > C.visc_it_nit:
+            break
+    return it, n_Axb_its
