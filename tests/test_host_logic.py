@@ -1,0 +1,170 @@
+"""Host-side logic and the C-ABI surface, without a GPU."""
+import ctypes as ct
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from ufemism2_0_b200 import capi, config, diva, experiments
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ufe_diva.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ufe_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    lib = capi.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(capi.EXPORTS)
+    assert lib.ufe_version() == 100
+
+
+def test_partition_list_matches_oracle(oracle):
+    for ntot in (0, 3, 16, 17, 1000, 2000003):
+        for n in (1, 2, 4, 8):
+            for i in range(n):
+                assert diva.partition_list(ntot, i, n) == oracle.partition_list(ntot, i, n)
+
+
+def test_struct_layouts_match_header():
+    # compile a tiny C program against the header and compare sizeof() with the ctypes mirrors
+    src = textwrap.dedent("""
+        #include <stdio.h>
+        #include "ufe_diva.h"
+        int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ufe_csr), sizeof(ufe_mesh),
+          sizeof(ufe_config), sizeof(ufe_ice_inputs), sizeof(ufe_diva_state), sizeof(ufe_ssa_state),
+          sizeof(ufe_solve_info), sizeof(ufe_comm)); return 0; }""")
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = list(map(int, subprocess.check_output([exe]).split()))
+    mirrors = [capi.ufe_csr, capi.ufe_mesh, capi.ufe_config, capi.ufe_ice_inputs, capi.ufe_diva_state,
+               capi.ufe_ssa_state, capi.ufe_solve_info, capi.ufe_comm]
+    assert sizes == [ct.sizeof(m) for m in mirrors]
+
+
+def test_config_namelist_parser(tmp_path):
+    p = tmp_path / "config.cfg"
+    p.write_text(textwrap.dedent("""
+        &CONFIG
+          ! comment
+          start_time_of_run_config                     = 0.0      ! ignored key
+          visc_it_norm_dUV_tol_config                  = 5E-7                             ! Stop criterion
+          visc_it_nit_config                           = 5000
+          visc_it_relax_config                         = 0.4_dp
+          stress_balance_PETSc_rtol_config             = 1E-6
+          BC_u_west_config                             = 'periodic_ISMIP-HOM'   ! Boundary conditions
+          choice_sliding_law_config                    = 'no_sliding'
+          do_GL_subgrid_friction_config                = .FALSE.
+          uniform_Glens_flow_factor_config             = 1.4280330398280316E-017
+          choice_initial_velocity_ANT_config           = 'zero'
+        /
+        """))
+    C = config.Config.from_namelist(str(p))
+    assert C.visc_it_norm_dUV_tol == 5e-7 and C.visc_it_nit == 5000 and C.visc_it_relax == 0.4
+    assert C.BC_u_west == "periodic_ISMIP-HOM" and C.BC_u_east == "infinite"
+    assert C.choice_sliding_law == "no_sliding" and C.do_GL_subgrid_friction is False
+    assert C.uniform_Glens_flow_factor == 1.4280330398280316e-17
+    # defaults of model_configuration.f90:307-313
+    D = config.Config()
+    assert (D.visc_it_norm_dUV_tol, D.visc_it_nit, D.visc_it_relax, D.stress_balance_PETSc_rtol,
+            D.stress_balance_PETSc_abstol) == (5e-5, 50, 0.2, 1e-7, 1e-5)
+
+
+def test_unknown_choices_raise_like_crash():
+    C = config.Config(choice_sliding_law="Coulombic")
+    with pytest.raises(capi.UfeError, match="unknown choice_sliding_law"):
+        diva.config_struct(C)
+    with pytest.raises(capi.UfeError, match="unknown choice_BC_u"):
+        diva.config_struct(config.Config(BC_u_west="open"))
+    with pytest.raises(capi.UfeError, match="unknown choice_flow_law"):
+        diva.config_struct(config.Config(choice_flow_law="Newton"))
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a usable sm_100 device the product path must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    mesh, C, ice = experiments.ISMIP_HOM("A", 160e3, 9)
+    with pytest.raises(capi.UfeError):
+        diva.initialise_DIVA_solver(mesh, C)
+    A = diva.CSRMatrix(2, 2, 1, 2, np.array([1, 2, 3], np.int32), np.array([1, 2], np.int32), np.ones(2))
+    with pytest.raises(capi.UfeError):
+        diva.multiply_CSR_matrix_with_vector(A, np.ones(2))
+    with pytest.raises(capi.UfeError):
+        diva.solve_matrix_equation_CSR(A, np.ones(2), np.zeros(2), 1e-8, 1e-10)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ufemism2.0_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in txt and "ufe_oracle" not in txt and "oracle/" not in txt, f
+
+
+GLOO_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["UFE_ROOT"]); sys.path.insert(0, os.path.join(os.environ["UFE_ROOT"], "oracle"))
+import ufe_pkg; ufe_pkg.load()
+from ufemism2_0_b200 import synthetic, diva
+import oracle as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# the unique-id broadcast bench.py performs before ufe_diva_create
+uid = torch.zeros(128, dtype=torch.uint8)
+if rank == 0: uid[:] = torch.arange(128, dtype=torch.uint8)
+dist.broadcast(uid, 0)
+assert uid.tolist() == list(range(128))
+mesh = synthetic.lattice_mesh(-1e5, 1e5, -1e5, 1e5, 17, 13)
+ti1, ti2 = diva.partition_list(mesh.nTri, rank, world)
+vi1, vi2 = diva.partition_list(mesh.nV, rank, world)
+# each rank builds and applies only its own rows (strip decomposition), then all-gathers
+rows = O.calc_operator_rows(mesh, "a_b", ti1, ti2)
+f = 1.0 + 3e-5 * mesh.V[:, 0] - 2e-5 * mesh.V[:, 1]
+y_loc = O.spmv(rows[0], f)
+sizes = [diva.partition_list(mesh.nTri, r, world) for r in range(world)]
+parts = [torch.zeros(b - a + 1, dtype=torch.float64) for a, b in sizes]
+dist.all_gather(parts, torch.from_numpy(y_loc))
+y = torch.cat(parts).numpy()
+full = O.calc_operator_rows(mesh, "a_b", 1, mesh.nTri)[0]
+assert np.array_equal(y, O.spmv(full, f))
+# halo range = column range touched by the owned rows (calc_j_node_range)
+lo, hi = rows[0].ind.min(), rows[0].ind.max()
+assert lo <= vi1 + 0 or vi1 > vi2
+t = torch.tensor([float(lo), float(hi)], dtype=torch.float64)
+allr = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+dist.all_gather(allr, t)
+if rank == 0:
+    assert allr[0][0] == 1 and allr[-1][1] == mesh.nV
+# Krylov-style dot product: local partial sums + all_reduce == global
+s = torch.tensor([float(np.dot(y_loc, y_loc))], dtype=torch.float64)
+dist.all_reduce(s)
+assert abs(s.item() - float(np.dot(y, y))) <= 1e-9 * abs(s.item())
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_two_rank_gloo_strip_decomposition(tmp_path, oracle):
+    w = tmp_path / "worker.py"
+    w.write_text(GLOO_WORKER)
+    env = dict(os.environ, UFE_ROOT=ROOT, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", str(w)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2

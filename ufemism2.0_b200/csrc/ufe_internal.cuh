@@ -1,0 +1,136 @@
+// Internal declarations shared by the translation units of libufe_diva.so.
+// sm_100a only; fp64 throughout (the reference is real(dp) everywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ufe_diva.h"
+
+#define UFE_NZ_MAX 32
+#define UFE_STACK_MAX 64        // local BFS stack capacity in the operator-construction kernels
+#define UFE_RED_BLOCKS 592      // 4 x 148 SMs: fixed grid for reductions (deterministic sums)
+#define UFE_RED_THREADS 256
+
+void ufe_set_error(const char *fmt, ...);
+extern thread_local int64_t g_launch_count;
+
+#define UFE_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      ufe_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                    cudaGetErrorString(e_));                                            \
+      return UFE_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define UFE_NCCL(call)                                                                  \
+  do {                                                                                  \
+    ncclResult_t r_ = (call);                                                           \
+    if (r_ != ncclSuccess) {                                                            \
+      ufe_set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, ncclGetErrorString(r_)); \
+      return UFE_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define UFE_TRY(call)                 \
+  do {                                \
+    int rc_ = (call);                 \
+    if (rc_ != UFE_OK) return rc_;    \
+  } while (0)
+
+#define UFE_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    g_launch_count++;                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ != cudaSuccess) {                                                            \
+      ufe_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,            \
+                    cudaGetErrorString(e_));                                            \
+      return UFE_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+static inline int ufe_div_up(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// One operator family on the device: rows i1..i1+m_loc-1 (1-based global), shared
+// pattern, nval value arrays.  ptr: local 1-based offsets; ind: global 1-based columns.
+struct DevFamily {
+  int m_loc = 0, m = 0, n = 0, i1 = 1, nnz = 0, nval = 0;
+  int *ptr = nullptr, *ind = nullptr;
+  double *val[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+// device mesh (full topology replicated per GPU, as the reference replicates it per rank)
+struct DevMesh {
+  int nV = 0, nTri = 0, nC_mem = 0, nz = 0;
+  double xmin = 0, xmax = 0, ymin = 0, ymax = 0;
+  double *V = nullptr, *TriGC = nullptr, *zeta = nullptr;
+  int *Tri = nullptr, *TriC = nullptr, *C = nullptr, *nC = nullptr, *iTri = nullptr, *niTri = nullptr,
+      *VBI = nullptr, *TriBI = nullptr;
+};
+
+// Krylov scalars living in device memory
+struct KrylovScalars {
+  double dots[8];       // raw (all-reduced) dot products of the current stage
+  double rho, alpha, omega, beta;
+  double bnorm, ttol, rnorm, dtol_bnorm, abstol;
+  int its, done, reason, maxits;   // reason: 2 rtol, 3 atol, -3 maxits, -4 dtol, -5 breakdown
+  int jcount, finalized, pad0, pad1; // GMRES: steps completed in the current cycle; x updated after convergence
+};
+
+struct KrylovWork {
+  int n_loc = 0;          // owned unknowns
+  double *r = nullptr, *rhat = nullptr, *p = nullptr, *v = nullptr, *s = nullptr, *t = nullptr;  // owned-length
+  double *pg = nullptr, *sg = nullptr;   // full-length, global-indexed SpMV inputs (owned part + halo valid)
+  int N = 0;
+  double *Vb = nullptr;   // GMRES basis (restart+1) x n_loc
+  double *w = nullptr;
+  double *partials = nullptr;   // UFE_RED_BLOCKS * 32
+  double *dots_local = nullptr; // 40 doubles (pre-allreduce)
+  unsigned *counter = nullptr;
+  KrylovScalars *sc = nullptr;
+  double *gm = nullptr;   // GMRES small dense state: H(31x30), cs, sn, g, y, hcol
+  KrylovScalars *sc_host = nullptr;  // pinned mirror
+};
+
+struct Comm {
+  int rank = 0, nranks = 1;
+  ncclComm_t nccl = nullptr;
+};
+
+// A distributed square CSR system on the device (rows r1..r1+m_loc-1, 1-based global).
+struct DevSystem {
+  int N = 0, m_loc = 0, r1 = 1, nnz = 0;
+  int *ptr = nullptr, *ind = nullptr;
+  double *val = nullptr;     // as assembled (reference values)
+  double *valS = nullptr;    // left-preconditioner folded in: B*A
+  double *bb = nullptr, *bS = nullptr;
+  double *x = nullptr;       // full-length (N) solution / SpMV input vector (global indexing)
+  int jmin = 1, jmax = 0;    // column range touched by the owned rows (calc_j_node_range)
+};
+
+int ufe_spmv_launch(cudaStream_t st, int m_loc, int nnz, const int *ptr, const int *ind,
+                    const double *val, const double *x, long long ldx, double *y, long long ldy,
+                    int nlayers);
+
+int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres);
+void ufe_krylov_free(KrylovWork &kw);
+// solves valS * x = bS on the owned rows; x full-length global vector (x[r1-1 ..] owned).
+// halo: callback-free -- single GPU handled inline, multi-GPU through the exchange plan.
+struct HaloPlan;
+int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm,
+                   const HaloPlan *halo, int method, double rtol, double abstol, int maxits,
+                   int guess_nonzero, int *n_its, int *flags);
+
+// halo exchange plan for a global-indexed vector partitioned into contiguous ranges
+struct HaloPlan {
+  int nranks = 1, rank = 0;
+  std::vector<int> own_lo, own_hi;     // 0-based [lo,hi) owned by each rank
+  std::vector<int> need_lo, need_hi;   // 0-based [lo,hi) each rank needs (own + halo)
+};
+int ufe_halo_exchange(cudaStream_t st, const Comm &comm, const HaloPlan &plan, double *x, long long ld,
+                      int nlayers, int mult);

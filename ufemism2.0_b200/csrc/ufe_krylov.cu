@@ -1,0 +1,562 @@
+// Hand-written Krylov solvers replacing the PETSc KSP call
+// (src/UPSY/basic/petsc_basic.f90:66-141, KSPSolve isolated at :143-168).
+//
+// The left preconditioner B (point Jacobi or 2x2 u-v block Jacobi) is folded into the
+// matrix at assembly time (valS = B*A, bS = B*b), so the Krylov loop is unpreconditioned
+// on the scaled system and its residual norm IS PETSc's default preconditioned norm:
+//     stop when ||B r|| <= max(rtol*||B b||, abstol)      (KSPConvergedDefault)
+//     diverged when ||B r|| >= dtol*||B b||, dtol = 1e5;   zero initial guess by default.
+//
+// Everything the iteration needs (dot products, alpha/omega/beta, the convergence test,
+// the iteration counter) lives in device memory; the host only enqueues batches of
+// iterations and polls a pinned copy of the scalars between batches.  After the device
+// has set `done`, the remaining kernels of a batch return immediately, so the solution
+// and the reported iteration count are exactly those of the converged iteration.
+// Dot products are reduced in a fixed order (per-block partials summed by the last block)
+// => bitwise reproducible run to run.  Multi-GPU: one ncclAllReduce per reduction stage
+// on the batched scalars, halo exchange of the SpMV input before each MatMult.
+#include "ufe_internal.cuh"
+#include "ufe_reduce.cuh"
+
+#define KGRID 1184   // 8 x 148 persistent blocks for the fused SpMV kernels
+#define GM_RESTART 30
+
+// ---------------------------------------------------------------------------------
+// scalar recurrences, run by exactly one thread after each reduction stage
+// ---------------------------------------------------------------------------------
+// gm layout: H[31*30] | cs[30] | sn[30] | g[31] | y[30] | hcol[32] | inv_hn
+#define GM_H(gm) (gm)
+#define GM_CS(gm) ((gm) + 31 * 30)
+#define GM_SN(gm) ((gm) + 31 * 30 + 30)
+#define GM_G(gm) ((gm) + 31 * 30 + 60)
+#define GM_Y(gm) ((gm) + 31 * 30 + 60 + 31)
+#define GM_HCOL(gm) ((gm) + 31 * 30 + 60 + 31 + 30)
+#define GM_INVHN(gm) ((gm) + 31 * 30 + 60 + 31 + 30 + 32)
+#define GM_SIZE (31 * 30 + 60 + 31 + 30 + 32 + 1)
+
+enum { ST_INIT = 0, ST_A = 1, ST_B = 2, ST_C = 3, ST_GM_INIT = 4, ST_GM_H = 5, ST_GM_NORM = 6 };
+
+__device__ void gmres_givens(KrylovScalars *sc, double *gm, double hn);
+
+__device__ void post_reduce(int stage, KrylovScalars *sc, double *gm, double rtol, double abstol) {
+  switch (stage) {
+    case ST_INIT: {   // dots: (r,r), (b,b)
+      sc->bnorm = sqrt(sc->dots[1]);
+      sc->ttol = fmax(rtol * sc->bnorm, abstol);
+      sc->dtol_bnorm = 1.0e5 * sc->bnorm;
+      sc->rnorm = sqrt(sc->dots[0]);
+      sc->rho = sc->dots[0];
+      sc->alpha = 1.0; sc->omega = 1.0; sc->beta = 0.0;
+      if (sc->rnorm <= sc->ttol) { sc->done = 1; sc->reason = (sc->rnorm <= abstol) ? 3 : 2; }
+      break;
+    }
+    case ST_A: {      // dots: (rhat, v)
+      const double rv = sc->dots[0];
+      if (rv == 0.0) { sc->done = 1; sc->reason = -5; break; }
+      sc->alpha = sc->rho / rv;
+      break;
+    }
+    case ST_B: {      // dots: (t,s), (t,t)
+      const double tt = sc->dots[1];
+      sc->omega = (tt == 0.0) ? 0.0 : sc->dots[0] / tt;
+      break;
+    }
+    case ST_C: {      // dots: (r,r), (rhat,r)
+      sc->rnorm = sqrt(sc->dots[0]);
+      sc->its += 1;
+      if (!(sc->rnorm == sc->rnorm)) { sc->done = 1; sc->reason = -5; break; }
+      if (sc->rnorm <= sc->ttol) { sc->done = 1; sc->reason = (sc->rnorm <= abstol) ? 3 : 2; break; }
+      if (sc->rnorm >= sc->dtol_bnorm) { sc->done = 1; sc->reason = -4; break; }
+      if (sc->its >= sc->maxits) { sc->done = 1; sc->reason = -3; break; }
+      const double rho_new = sc->dots[1];
+      if (sc->omega == 0.0 || sc->rho == 0.0 || rho_new == 0.0) { sc->done = 1; sc->reason = -5; break; }
+      sc->beta = (rho_new / sc->rho) * (sc->alpha / sc->omega);
+      sc->rho = rho_new;
+      break;
+    }
+    case ST_GM_INIT: {  // dots: (r,r)[, (b,b) on the first cycle -> dots[1] >= 0]
+      if (sc->bnorm < 0.0) {
+        sc->bnorm = sqrt(sc->dots[1]);
+        sc->ttol = fmax(rtol * sc->bnorm, abstol);
+        sc->dtol_bnorm = 1.0e5 * sc->bnorm;
+      }
+      sc->rnorm = sqrt(sc->dots[0]);
+      sc->jcount = 0;
+      for (int i = 0; i <= GM_RESTART; i++) GM_G(gm)[i] = 0.0;
+      GM_G(gm)[0] = sc->rnorm;
+      *GM_INVHN(gm) = (sc->rnorm > 0.0) ? 1.0 / sc->rnorm : 0.0;
+      if (sc->rnorm <= sc->ttol) { sc->done = 1; sc->reason = (sc->rnorm <= abstol) ? 3 : 2; sc->finalized = 1; }
+      break;
+    }
+    case ST_GM_NORM: {  // dots: (w,w)
+      gmres_givens(sc, gm, sqrt(sc->dots[0]));
+      break;
+    }
+  }
+}
+
+__device__ void gmres_givens(KrylovScalars *sc, double *gm, double hn) {
+  const int j = sc->jcount;
+  double *hcol = GM_HCOL(gm), *cs = GM_CS(gm), *sn = GM_SN(gm), *g = GM_G(gm);
+  hcol[j + 1] = hn;
+  *GM_INVHN(gm) = (hn != 0.0) ? 1.0 / hn : 0.0;
+  for (int i = 0; i < j; i++) {
+    const double a = hcol[i], c = hcol[i + 1];
+    hcol[i] = cs[i] * a + sn[i] * c;
+    hcol[i + 1] = -sn[i] * a + cs[i] * c;
+  }
+  const double a = hcol[j], c = hcol[j + 1], rr = hypot(a, c);
+  if (rr == 0.0) { cs[j] = 1.0; sn[j] = 0.0; } else { cs[j] = a / rr; sn[j] = c / rr; }
+  hcol[j] = rr; hcol[j + 1] = 0.0;
+  g[j + 1] = -sn[j] * g[j];
+  g[j] = cs[j] * g[j];
+  for (int i = 0; i <= j; i++) GM_H(gm)[i + 31 * j] = hcol[i];
+  sc->rnorm = fabs(g[j + 1]);
+  sc->its += 1;
+  sc->jcount = j + 1;
+  if (!(sc->rnorm == sc->rnorm)) { sc->done = 1; sc->reason = -5; }
+  else if (sc->rnorm <= sc->ttol) { sc->done = 1; sc->reason = (sc->rnorm <= sc->abstol) ? 3 : 2; }
+  else if (sc->rnorm >= sc->dtol_bnorm) { sc->done = 1; sc->reason = -4; }
+  else if (sc->its >= sc->maxits) { sc->done = 1; sc->reason = -3; }
+  else if (hn == 0.0) { sc->done = 1; sc->reason = 2; }
+}
+
+__global__ void k_post(int stage, KrylovScalars *sc, double *gm, const double *dots_in, int nd, double rtol,
+                       double abstol) {
+  if (sc->done) return;
+  for (int i = 0; i < nd; i++) sc->dots[i] = dots_in[i];
+  post_reduce(stage, sc, gm, rtol, abstol);
+}
+
+// copy the (all-reduced) Gram-Schmidt coefficients of step j into the Hessenberg column
+__global__ void k_gm_sethcol(const KrylovScalars *sc, double *gm, const double *dots_in, int cnt) {
+  if (sc->done) return;
+  for (int i = 0; i < cnt; i++) GM_HCOL(gm)[i] = dots_in[i];
+}
+
+// finish a reduction stage inside the producing kernel (single GPU) or leave the local
+// partial sums in dots_local for the all-reduce (multi GPU)
+template <int NV>
+__device__ __forceinline__ void finish_stage(double (&acc)[NV], int stage, double *partials, unsigned *counter,
+                                             double *dots_local, KrylovScalars *sc, double *gm, int single,
+                                             double rtol, double abstol) {
+  if (reduce_publish<NV>(acc, partials, counter, dots_local)) {
+    if (single && threadIdx.x == 0) {
+      for (int i = 0; i < NV; i++) sc->dots[i] = dots_local[i];
+      post_reduce(stage, sc, gm, rtol, abstol);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// fused SpMV (+ dot products) on the scaled matrix, T threads per row, persistent grid.
+// MODE 0: y = A xg
+// MODE 1: y = A xg ; dot0 = (z, y)                      [BiCGStab: v = A p, (rhat, v)]
+// MODE 2: y = A xg ; dot0 = (y, xg_own), dot1 = (y, y)   [BiCGStab: t = A s, (t,s), (t,t)]
+// ---------------------------------------------------------------------------------
+template <int T, int MODE>
+__global__ void __launch_bounds__(256)
+k_kspmv(int m_loc, int r0, const int *__restrict__ ptr, const int *__restrict__ ind,
+        const double *__restrict__ val, const double *__restrict__ xg, double *__restrict__ y,
+        const double *__restrict__ z, int stage, double *partials, unsigned *counter, double *dots_local,
+        KrylovScalars *sc, double *gm, int single, double rtol, double abstol) {
+  if (sc->done) return;
+  const int lane = threadIdx.x % T;
+  const int rows_per_block = 256 / T;
+  double acc[2] = {0.0, 0.0};
+  for (int base = blockIdx.x * rows_per_block; base < m_loc; base += gridDim.x * rows_per_block) {
+    const int row = base + threadIdx.x / T;
+    double s = 0.0;
+    if (row < m_loc) {
+      const int k0 = ptr[row] - 1, k1 = ptr[row + 1] - 1;
+      for (int k = k0 + lane; k < k1; k += T) s += __ldg(val + k) * __ldg(xg + (__ldg(ind + k) - 1));
+    }
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, T);
+    if (row < m_loc && lane == 0) {
+      y[row] = s;
+      if (MODE == 1) acc[0] += z[row] * s;
+      if (MODE == 2) { acc[0] += s * xg[r0 + row]; acc[1] += s * s; }
+    }
+  }
+  if (MODE == 1) { double a1[1] = {acc[0]}; finish_stage<1>(a1, stage, partials, counter, dots_local, sc, gm, single, rtol, abstol); }
+  if (MODE == 2) finish_stage<2>(acc, stage, partials, counter, dots_local, sc, gm, single, rtol, abstol);
+}
+
+template <int MODE>
+static int launch_kspmv(cudaStream_t st, const DevSystem &S, const double *xg, double *y, const double *z,
+                        int stage, KrylovWork &kw, int single, double rtol, double abstol) {
+  const double mean = S.m_loc > 0 ? (double)S.nnz / S.m_loc : 1.0;
+  int T = 1;
+  while (T < 32 && T * 4 < mean) T *= 2;
+  const int rpb = 256 / T;
+  int blocks = ufe_div_up(S.m_loc, rpb);
+  if (blocks > KGRID) blocks = KGRID;
+  if (blocks < 1) blocks = 1;
+#define KS_ARGS S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, xg, y, z, stage, kw.partials, kw.counter, kw.dots_local, kw.sc, kw.gm, single, rtol, abstol
+  switch (T) {
+    case 1: k_kspmv<1, MODE><<<blocks, 256, 0, st>>>(KS_ARGS); break;
+    case 2: k_kspmv<2, MODE><<<blocks, 256, 0, st>>>(KS_ARGS); break;
+    case 4: k_kspmv<4, MODE><<<blocks, 256, 0, st>>>(KS_ARGS); break;
+    case 8: k_kspmv<8, MODE><<<blocks, 256, 0, st>>>(KS_ARGS); break;
+    case 16: k_kspmv<16, MODE><<<blocks, 256, 0, st>>>(KS_ARGS); break;
+    default: k_kspmv<32, MODE><<<blocks, 256, 0, st>>>(KS_ARGS); break;
+  }
+#undef KS_ARGS
+  UFE_LAUNCH_CHECK();
+  return UFE_OK;
+}
+
+int ufe_kspmv_plain(cudaStream_t st, const DevSystem &S, const double *xg, double *y, KrylovWork &kw) {
+  return launch_kspmv<0>(st, S, xg, y, nullptr, 0, kw, 1, 0.0, 0.0);
+}
+
+// ---------------------------------------------------------------------------------
+// BiCGStab vector kernels (grid-stride, fixed grid => deterministic reductions)
+// ---------------------------------------------------------------------------------
+// r = b - Ax (Ax in r on entry if have_ax), rhat = r, p = r -> pg ; x unchanged.
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_bicg_init(int n, int r0, const double *__restrict__ b, double *__restrict__ r, double *__restrict__ rhat,
+            double *__restrict__ pg, double *__restrict__ xg, int have_ax, double *partials, unsigned *counter,
+            double *dots_local, KrylovScalars *sc, int single, double rtol, double abstol) {
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    double ri = bi;
+    if (have_ax) ri = bi - r[i]; else xg[r0 + i] = 0.0;
+    r[i] = ri; rhat[i] = ri; pg[r0 + i] = ri;
+    acc[0] += ri * ri; acc[1] += bi * bi;
+  }
+  finish_stage<2>(acc, ST_INIT, partials, counter, dots_local, sc, nullptr, single, rtol, abstol);
+}
+
+// p = r + beta (p - omega v)
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_bicg_p(int n, int r0, const double *__restrict__ r, const double *__restrict__ v, double *__restrict__ pg,
+         const KrylovScalars *sc) {
+  if (sc->done) return;
+  const double beta = sc->beta, omega = sc->omega;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    pg[r0 + i] = r[i] + beta * (pg[r0 + i] - omega * v[i]);
+}
+
+// s = r - alpha v
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_bicg_s(int n, int r0, const double *__restrict__ r, const double *__restrict__ v, double *__restrict__ sg,
+         const KrylovScalars *sc) {
+  if (sc->done) return;
+  const double alpha = sc->alpha;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    sg[r0 + i] = r[i] - alpha * v[i];
+}
+
+// x += alpha p + omega s ; r = s - omega t ; dots (r,r), (rhat,r)
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_bicg_xr(int n, int r0, double *__restrict__ xg, const double *__restrict__ pg, const double *__restrict__ sg,
+          const double *__restrict__ t, const double *__restrict__ rhat, double *__restrict__ r,
+          double *partials, unsigned *counter, double *dots_local, KrylovScalars *sc, int single, double rtol,
+          double abstol) {
+  if (sc->done) return;
+  const double alpha = sc->alpha, omega = sc->omega;
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double si = sg[r0 + i];
+    xg[r0 + i] += alpha * pg[r0 + i] + omega * si;
+    const double ri = si - omega * t[i];
+    r[i] = ri;
+    acc[0] += ri * ri; acc[1] += rhat[i] * ri;
+  }
+  finish_stage<2>(acc, ST_C, partials, counter, dots_local, sc, nullptr, single, rtol, abstol);
+}
+
+__global__ void k_sc_reset(KrylovScalars *sc, int maxits, double abstol) {
+  sc->abstol = abstol;
+  sc->its = 0; sc->done = 0; sc->reason = 0; sc->maxits = maxits; sc->jcount = 0; sc->finalized = 0;
+  sc->bnorm = -1.0; sc->rnorm = 0.0; sc->ttol = 0.0; sc->rho = 1.0; sc->alpha = 1.0; sc->omega = 1.0; sc->beta = 0.0;
+}
+
+// ---------------------------------------------------------------------------------
+// GMRES(30) kernels (PETSc-default twin: classical Gram-Schmidt, no refinement)
+// ---------------------------------------------------------------------------------
+// r = b - Ax (Ax in w on entry if have_ax) -> w ; dots (r,r), (b,b)
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_gm_resid(int n, int r0, const double *__restrict__ b, double *__restrict__ w, double *__restrict__ xg,
+           int have_ax, int zero_x, double *partials, unsigned *counter, double *dots_local, KrylovScalars *sc,
+           double *gm, int single, double rtol, double abstol) {
+  if (sc->done) return;
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    double ri = bi;
+    if (have_ax) ri = bi - w[i];
+    if (zero_x) xg[r0 + i] = 0.0;
+    w[i] = ri;
+    acc[0] += ri * ri; acc[1] += bi * bi;
+  }
+  finish_stage<2>(acc, ST_GM_INIT, partials, counter, dots_local, sc, gm, single, rtol, abstol);
+}
+
+// V_j = w * inv_hn -> Vb[j], pg
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_gm_scale(int n, int r0, const double *__restrict__ w, double *__restrict__ Vj, double *__restrict__ pg,
+           const KrylovScalars *sc, const double *gm, int j) {
+  if (sc->done || sc->jcount != j) return;
+  const double inv = *GM_INVHN(gm);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double vi = w[i] * inv;
+    Vj[i] = vi; pg[r0 + i] = vi;
+  }
+}
+
+// h_i = (V_i, w), i = i0 .. i0+NV-1 (<= j)
+template <int NV>
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_gm_mdot(int n, const double *__restrict__ Vb, long long ldv, const double *__restrict__ w, int i0, int cnt,
+          double *partials, unsigned *counter, double *dots_local, KrylovScalars *sc) {
+  if (sc->done) return;
+  double acc[NV];
+#pragma unroll
+  for (int q = 0; q < NV; q++) acc[q] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double wi = w[i];
+#pragma unroll
+    for (int q = 0; q < NV; q++) if (q < cnt) acc[q] += Vb[(size_t)(i0 + q) * ldv + i] * wi;
+  }
+  reduce_publish<NV>(acc, partials, counter, dots_local + i0);
+}
+
+// w -= sum_i h_i V_i ; dot (w,w)
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_gm_update(int n, const double *__restrict__ Vb, long long ldv, double *__restrict__ w, int j,
+            double *partials, unsigned *counter, double *dots_local, KrylovScalars *sc, double *gm, int single,
+            double rtol, double abstol) {
+  if (sc->done) return;
+  const double *h = GM_HCOL(gm);
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double wi = w[i];
+    for (int q = 0; q <= j; q++) wi -= h[q] * Vb[(size_t)q * ldv + i];
+    w[i] = wi;
+    acc[0] += wi * wi;
+  }
+  finish_stage<1>(acc, ST_GM_NORM, partials, counter, dots_local, sc, gm, single, rtol, abstol);
+}
+
+// back-substitution for y (one thread), then x += sum_i y_i V_i
+__global__ void k_gm_solve_y(KrylovScalars *sc, double *gm) {
+  if (sc->finalized) return;
+  const int j = sc->jcount;
+  double *y = GM_Y(gm);
+  const double *g = GM_G(gm), *H = GM_H(gm);
+  for (int i = j - 1; i >= 0; i--) {
+    double s = g[i];
+    for (int k = i + 1; k < j; k++) s -= H[i + 31 * k] * y[k];
+    y[i] = s / H[i + 31 * i];
+  }
+}
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_gm_xupdate(int n, int r0, const double *__restrict__ Vb, long long ldv, double *__restrict__ xg,
+             const KrylovScalars *sc, const double *gm) {
+  if (sc->finalized) return;
+  const int j = sc->jcount;
+  const double *y = GM_Y(gm);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double xi = xg[r0 + i];
+    for (int q = 0; q < j; q++) xi += y[q] * Vb[(size_t)q * ldv + i];
+    xg[r0 + i] = xi;
+  }
+}
+__global__ void k_gm_cycle_end(KrylovScalars *sc) {
+  if (sc->done) sc->finalized = 1;
+  sc->jcount = 0;
+}
+
+// ---------------------------------------------------------------------------------
+// halo exchange of a global-indexed vector (contiguous owned ranges per rank)
+// ---------------------------------------------------------------------------------
+int ufe_halo_exchange(cudaStream_t st, const Comm &comm, const HaloPlan &plan, double *x, long long ld,
+                      int nlayers, int mult) {
+  if (comm.nranks <= 1) return UFE_OK;
+  const int me = comm.rank;
+  UFE_NCCL(ncclGroupStart());
+  for (int q = 0; q < comm.nranks; q++) {
+    if (q == me) continue;
+    // what I need from q: intersection of my need range with q's owned range
+    int lo = plan.need_lo[me] > plan.own_lo[q] ? plan.need_lo[me] : plan.own_lo[q];
+    int hi = plan.need_hi[me] < plan.own_hi[q] ? plan.need_hi[me] : plan.own_hi[q];
+    if (hi > lo)
+      for (int l = 0; l < nlayers; l++)
+        UFE_NCCL(ncclRecv(x + l * ld + (long long)lo * mult, (size_t)(hi - lo) * mult, ncclDouble, q, comm.nccl, st));
+    // what q needs from me
+    lo = plan.need_lo[q] > plan.own_lo[me] ? plan.need_lo[q] : plan.own_lo[me];
+    hi = plan.need_hi[q] < plan.own_hi[me] ? plan.need_hi[q] : plan.own_hi[me];
+    if (hi > lo)
+      for (int l = 0; l < nlayers; l++)
+        UFE_NCCL(ncclSend(x + l * ld + (long long)lo * mult, (size_t)(hi - lo) * mult, ncclDouble, q, comm.nccl, st));
+  }
+  UFE_NCCL(ncclGroupEnd());
+  g_launch_count++;
+  return UFE_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------
+int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres) {
+  kw.n_loc = n_loc; kw.N = N;
+  size_t nb = (size_t)(n_loc > 0 ? n_loc : 1) * sizeof(double);
+  size_t Nb = (size_t)(N > 0 ? N : 1) * sizeof(double);
+  UFE_CUDA(cudaMalloc(&kw.r, nb)); UFE_CUDA(cudaMalloc(&kw.rhat, nb));
+  UFE_CUDA(cudaMalloc(&kw.v, nb)); UFE_CUDA(cudaMalloc(&kw.t, nb));
+  UFE_CUDA(cudaMalloc(&kw.w, nb));
+  UFE_CUDA(cudaMalloc(&kw.pg, Nb)); UFE_CUDA(cudaMalloc(&kw.sg, Nb));
+  UFE_CUDA(cudaMemset(kw.pg, 0, Nb)); UFE_CUDA(cudaMemset(kw.sg, 0, Nb));
+  if (gmres) UFE_CUDA(cudaMalloc(&kw.Vb, nb * (GM_RESTART + 1)));
+  UFE_CUDA(cudaMalloc(&kw.partials, sizeof(double) * KGRID * 8));
+  UFE_CUDA(cudaMalloc(&kw.dots_local, sizeof(double) * 48));
+  UFE_CUDA(cudaMalloc(&kw.counter, sizeof(unsigned)));
+  UFE_CUDA(cudaMemset(kw.counter, 0, sizeof(unsigned)));
+  UFE_CUDA(cudaMalloc(&kw.sc, sizeof(KrylovScalars)));
+  UFE_CUDA(cudaMemset(kw.sc, 0, sizeof(KrylovScalars)));
+  UFE_CUDA(cudaMalloc(&kw.gm, sizeof(double) * GM_SIZE));
+  UFE_CUDA(cudaMemset(kw.gm, 0, sizeof(double) * GM_SIZE));
+  UFE_CUDA(cudaMallocHost(&kw.sc_host, sizeof(KrylovScalars)));
+  return UFE_OK;
+}
+
+void ufe_krylov_free(KrylovWork &kw) {
+  cudaFree(kw.r); cudaFree(kw.rhat); cudaFree(kw.v); cudaFree(kw.t); cudaFree(kw.w);
+  cudaFree(kw.pg); cudaFree(kw.sg); cudaFree(kw.Vb); cudaFree(kw.partials); cudaFree(kw.dots_local);
+  cudaFree(kw.counter); cudaFree(kw.sc); cudaFree(kw.gm);
+  if (kw.sc_host) cudaFreeHost(kw.sc_host);
+  kw = KrylovWork();
+}
+
+static int allreduce_stage(cudaStream_t st, const Comm &comm, KrylovWork &kw, int stage, int nd, double rtol,
+                           double abstol) {
+  if (comm.nranks <= 1) return UFE_OK;
+  UFE_NCCL(ncclAllReduce(kw.dots_local, kw.dots_local, nd, ncclDouble, ncclSum, comm.nccl, st));
+  g_launch_count++;
+  k_post<<<1, 1, 0, st>>>(stage, kw.sc, kw.gm, kw.dots_local, nd, rtol, abstol);
+  UFE_LAUNCH_CHECK();
+  return UFE_OK;
+}
+
+static int poll(cudaStream_t st, KrylovWork &kw) {
+  UFE_CUDA(cudaMemcpyAsync(kw.sc_host, kw.sc, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, st));
+  UFE_CUDA(cudaStreamSynchronize(st));
+  return UFE_OK;
+}
+
+static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm,
+                        const HaloPlan *halo, double rtol, double abstol, int maxits, int guess_nonzero) {
+  const int n = S.m_loc, r0 = S.r1 - 1, single = comm.nranks <= 1;
+  const int G = UFE_RED_BLOCKS, B = UFE_RED_THREADS;
+  double *xg = S.x;
+  k_sc_reset<<<1, 1, 0, st>>>(kw.sc, maxits, abstol); UFE_LAUNCH_CHECK();
+  if (guess_nonzero) {
+    if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, xg, 0, 1, 2));
+    UFE_TRY(launch_kspmv<0>(st, S, xg, kw.r, nullptr, 0, kw, single, rtol, abstol));
+  }
+  k_bicg_init<<<G, B, 0, st>>>(n, r0, S.bS, kw.r, kw.rhat, kw.pg, xg, guess_nonzero, kw.partials, kw.counter,
+                               kw.dots_local, kw.sc, single, rtol, abstol);
+  UFE_LAUNCH_CHECK();
+  UFE_TRY(allreduce_stage(st, comm, kw, ST_INIT, 2, rtol, abstol));
+  int launched = 0, batch = 4;
+  while (true) {
+    for (int b = 0; b < batch; b++, launched++) {
+      if (launched > 0) { k_bicg_p<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.pg, kw.sc); UFE_LAUNCH_CHECK(); }
+      if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.pg, 0, 1, 2));
+      UFE_TRY(launch_kspmv<1>(st, S, kw.pg, kw.v, kw.rhat, ST_A, kw, single, rtol, abstol));
+      UFE_TRY(allreduce_stage(st, comm, kw, ST_A, 1, rtol, abstol));
+      k_bicg_s<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.sc); UFE_LAUNCH_CHECK();
+      if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.sg, 0, 1, 2));
+      UFE_TRY(launch_kspmv<2>(st, S, kw.sg, kw.t, nullptr, ST_B, kw, single, rtol, abstol));
+      UFE_TRY(allreduce_stage(st, comm, kw, ST_B, 2, rtol, abstol));
+      k_bicg_xr<<<G, B, 0, st>>>(n, r0, xg, kw.pg, kw.sg, kw.t, kw.rhat, kw.r, kw.partials, kw.counter,
+                                 kw.dots_local, kw.sc, single, rtol, abstol);
+      UFE_LAUNCH_CHECK();
+      UFE_TRY(allreduce_stage(st, comm, kw, ST_C, 2, rtol, abstol));
+    }
+    UFE_TRY(poll(st, kw));
+    if (kw.sc_host->done) break;
+    if (batch < 64) batch *= 2;
+  }
+  return UFE_OK;
+}
+
+static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm, const HaloPlan *halo,
+                     double rtol, double abstol, int maxits, int guess_nonzero, bool reset) {
+  const int n = S.m_loc, r0 = S.r1 - 1, single = comm.nranks <= 1;
+  const int G = UFE_RED_BLOCKS, B = UFE_RED_THREADS;
+  const long long ldv = n;
+  double *xg = S.x;
+  if (reset) { k_sc_reset<<<1, 1, 0, st>>>(kw.sc, maxits, abstol); UFE_LAUNCH_CHECK(); }
+  bool first = true;
+  while (true) {
+    const int have_ax = (!first || guess_nonzero) ? 1 : 0;
+    if (have_ax) {
+      if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, xg, 0, 1, 2));
+      UFE_TRY(launch_kspmv<0>(st, S, xg, kw.w, nullptr, 0, kw, single, rtol, abstol));
+    }
+    k_gm_resid<<<G, B, 0, st>>>(n, r0, S.bS, kw.w, xg, have_ax, (first && !guess_nonzero) ? 1 : 0, kw.partials,
+                                kw.counter, kw.dots_local, kw.sc, kw.gm, single, rtol, abstol);
+    UFE_LAUNCH_CHECK();
+    UFE_TRY(allreduce_stage(st, comm, kw, ST_GM_INIT, 2, rtol, abstol));
+    first = false;
+    for (int j = 0; j < GM_RESTART; j++) {
+      k_gm_scale<<<G, B, 0, st>>>(n, r0, kw.w, kw.Vb + (size_t)j * ldv, kw.pg, kw.sc, kw.gm, j); UFE_LAUNCH_CHECK();
+      if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.pg, 0, 1, 2));
+      UFE_TRY(launch_kspmv<0>(st, S, kw.pg, kw.w, nullptr, 0, kw, single, rtol, abstol));
+      for (int i0 = 0; i0 <= j; i0 += 8) {
+        const int cnt = (j + 1 - i0) < 8 ? (j + 1 - i0) : 8;
+        k_gm_mdot<8><<<G, B, 0, st>>>(n, kw.Vb, ldv, kw.w, i0, cnt, kw.partials, kw.counter, kw.dots_local, kw.sc);
+        UFE_LAUNCH_CHECK();
+      }
+      if (!single) {
+        UFE_NCCL(ncclAllReduce(kw.dots_local, kw.dots_local, j + 1, ncclDouble, ncclSum, comm.nccl, st));
+        g_launch_count++;
+      }
+      k_gm_sethcol<<<1, 1, 0, st>>>(kw.sc, kw.gm, kw.dots_local, j + 1);
+      UFE_LAUNCH_CHECK();
+      k_gm_update<<<G, B, 0, st>>>(n, kw.Vb, ldv, kw.w, j, kw.partials, kw.counter, kw.dots_local + 40, kw.sc,
+                                   kw.gm, single, rtol, abstol);
+      UFE_LAUNCH_CHECK();
+      if (!single) {
+        UFE_NCCL(ncclAllReduce(kw.dots_local + 40, kw.dots_local + 40, 1, ncclDouble, ncclSum, comm.nccl, st));
+        g_launch_count++;
+        k_post<<<1, 1, 0, st>>>(ST_GM_NORM, kw.sc, kw.gm, kw.dots_local + 40, 1, rtol, abstol); UFE_LAUNCH_CHECK();
+      }
+    }
+    k_gm_solve_y<<<1, 1, 0, st>>>(kw.sc, kw.gm); UFE_LAUNCH_CHECK();
+    k_gm_xupdate<<<G, B, 0, st>>>(n, r0, kw.Vb, ldv, xg, kw.sc, kw.gm); UFE_LAUNCH_CHECK();
+    k_gm_cycle_end<<<1, 1, 0, st>>>(kw.sc); UFE_LAUNCH_CHECK();
+    UFE_TRY(poll(st, kw));
+    if (kw.sc_host->done) break;
+  }
+  return UFE_OK;
+}
+
+int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm, const HaloPlan *halo,
+                   int method, double rtol, double abstol, int maxits, int guess_nonzero, int *n_its, int *flags) {
+  if (maxits <= 0) maxits = 10000;
+  int fl = 0;
+  if (method == UFE_KRYLOV_GMRES) {
+    if (!kw.Vb) { ufe_set_error("GMRES workspace not allocated"); return UFE_ERR_INVALID; }
+    UFE_TRY(run_gmres(st, S, kw, comm, halo, rtol, abstol, maxits, guess_nonzero, true));
+  } else {
+    UFE_TRY(run_bicgstab(st, S, kw, comm, halo, rtol, abstol, maxits, guess_nonzero));
+    if (kw.sc_host->reason == -5 && kw.Vb) {
+      // BiCGStab breakdown: continue from the current iterate with GMRES(30)
+      const int its0 = kw.sc_host->its;
+      UFE_TRY(run_gmres(st, S, kw, comm, halo, rtol, abstol, maxits, 1, true));
+      kw.sc_host->its += its0;
+    }
+  }
+  const int reason = kw.sc_host->reason;
+  if (reason == -3) fl |= UFE_FLAG_KRYLOV_MAXIT;
+  if (reason == -4 || reason == -5) fl |= UFE_FLAG_KRYLOV_DIVERGED;
+  if (n_its) *n_its = kw.sc_host->its;
+  if (flags) *flags = fl;
+  return UFE_OK;
+}

@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's call surface into the velocity-solver modules.
+
+Same names, argument meaning and error behaviour as the Fortran procedures, on top of
+the C ABI (include/ufe_diva.h):
+
+  initialise_DIVA_solver / solve_DIVA / solve_SSA     DIVA_main.f90:37,88 ; SSA_main.f90:87
+  solve_SSA_DIVA_linearised                           solve_linearised_SSA_DIVA.f90:23
+  solve_matrix_equation_CSR_PETSc                     src/UPSY/basic/petsc_basic.f90:32
+  multiply_CSR_matrix_with_vector_1D/_2D              CSR_matrix_vector_multiplication.f90:198,336
+  map_a_b_2D/3D, ddx_a_b_2D, ... , ddy_b_a_2D          mesh_disc_apply_operators.f90:121-431
+  partition_list                                      mpi_distributed_memory.f90:42
+
+``crash(...)`` in the reference becomes ``UfeError``; the "viscosity iteration failed to
+converge" warning becomes ``info.flags & PICARD_MAXIT``.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import UfeError, check, vp
+from .config import (BC_CODES, ENH_CODES, IDEALISED_SLIDING_CODES, RHEOLOGY_CODES, SLIDING_CODES, Config)
+from .mesh_types import Mesh
+
+PICARD_MAXIT, KRYLOV_MAXIT, KRYLOV_DIVERGED = 1, 2, 4
+KRYLOV_METHODS = {"bicgstab": 0, "gmres": 1}
+KRYLOV_PCS = {"jacobi": 0, "bjacobi2": 1}
+FAMILIES = {"a_b": (0, ("map", "ddx", "ddy")), "b_a": (1, ("map", "ddx", "ddy")),
+            "b_b": (2, ("ddx", "ddy", "d2dx2", "d2dxdy", "d2dy2"))}
+
+
+def _code(table, key, what):
+    try:
+        return table[key]
+    except KeyError:
+        raise UfeError(1, f'unknown {what} "{key}"!') from None
+
+
+def config_struct(C: Config) -> capi.ufe_config:
+    s = capi.ufe_config()
+    s.do_include_SSADIVA_crossterms = int(C.do_include_SSADIVA_crossterms)
+    for k in ("visc_it_norm_dUV_tol", "visc_it_nit", "visc_it_relax", "visc_eff_min", "vel_max",
+              "stress_balance_PETSc_rtol", "stress_balance_PETSc_abstol", "slid_Weertman_m",
+              "slid_Budd_q_plastic", "slid_Budd_u_threshold", "slid_ZI_p", "slid_ZI_ut",
+              "subgrid_friction_exponent_on_B_grid", "slid_beta_max", "slid_delta_v", "Hi_min",
+              "Glens_flow_law_exponent", "Glens_flow_law_epsilon_sq_0", "uniform_Glens_flow_factor",
+              "m_enh_sheet", "m_enh_shelf", "refgeo_idealised_SSA_icestream_Hi",
+              "refgeo_idealised_SSA_icestream_dhdx", "refgeo_idealised_SSA_icestream_L",
+              "refgeo_idealised_SSA_icestream_m", "refgeo_idealised_ISMIP_HOM_L"):
+        setattr(s, k, getattr(C, k))
+    for i, side in enumerate(("north", "east", "south", "west")):
+        s.BC_u[i] = _code(BC_CODES, getattr(C, f"BC_u_{side}"), "choice_BC_u")
+        s.BC_v[i] = _code(BC_CODES, getattr(C, f"BC_v_{side}"), "choice_BC_v")
+    s.choice_sliding_law = _code(SLIDING_CODES, C.choice_sliding_law, "choice_sliding_law")
+    s.choice_idealised_sliding_law = _code(IDEALISED_SLIDING_CODES, C.choice_idealised_sliding_law,
+                                           "choice_idealised_sliding_law")
+    s.do_GL_subgrid_friction = int(C.do_GL_subgrid_friction)
+    s.do_subgrid_friction_on_A_grid = int(C.do_subgrid_friction_on_A_grid)
+    s.choice_ice_rheology_Glen = _code(RHEOLOGY_CODES, C.choice_ice_rheology_Glen, "choice_ice_rheology_Glen")
+    s.choice_enhancement_factor_transition = _code(ENH_CODES, C.choice_enhancement_factor_transition,
+                                                   "choice_enhancement_factor_transition")
+    if C.choice_flow_law != "Glen":
+        raise UfeError(1, f'unknown choice_flow_law "{C.choice_flow_law}"!')
+    s.krylov_method = _code(KRYLOV_METHODS, C.b200_krylov_method, "b200_krylov_method")
+    s.krylov_pc = _code(KRYLOV_PCS, C.b200_krylov_pc, "b200_krylov_pc")
+    s.krylov_maxits = C.b200_krylov_maxits
+    s.krylov_guess_nonzero = int(C.b200_krylov_guess_nonzero)
+    return s
+
+
+def partition_list(ntot, i, n):
+    i1, i2 = ct.c_int32(), ct.c_int32()
+    capi.lib().ufe_partition_list(ntot, i, n, ct.byref(i1), ct.byref(i2))
+    return i1.value, i2.value
+
+
+@dataclass
+class CSRMatrix:
+    """type_sparse_matrix_CSR_dp (CSR_sparse_matrix_type.f90:15-38)."""
+    m: int
+    n: int
+    i1: int
+    i2: int
+    ptr: np.ndarray
+    ind: np.ndarray
+    val: np.ndarray
+
+
+def multiply_CSR_matrix_with_vector(A: CSRMatrix, x: np.ndarray) -> np.ndarray:
+    """1-D (x shape (n,)) or 2-D (x shape (n,nz), column-major) SpMV on the GPU."""
+    keep = []
+    s = capi.csr_struct(A.m, A.n, A.i1, A.i2, A.ptr, A.ind, A.val, keep)
+    x = np.asfortranarray(x, dtype=np.float64)
+    nl = 1 if x.ndim == 1 else x.shape[1]
+    y = np.zeros((A.i2 - A.i1 + 1,) if x.ndim == 1 else (A.i2 - A.i1 + 1, nl), order="F")
+    check(capi.lib().ufe_spmv(ct.byref(s), vp(x), vp(y), nl))
+    return y
+
+
+def solve_matrix_equation_CSR(A: CSRMatrix, bb, xx, rtol, abstol, method="bicgstab", maxits=10000,
+                              guess_nonzero=False):
+    """Replaces solve_matrix_equation_CSR_PETSc (petsc_basic.f90:32-64). Returns (x, n_its, flags)."""
+    keep = []
+    s = capi.csr_struct(A.m, A.n, A.i1, A.i2, A.ptr, A.ind, A.val, keep)
+    b = np.ascontiguousarray(bb, dtype=np.float64)
+    x = np.array(xx, dtype=np.float64, copy=True)
+    its, fl = ct.c_int32(), ct.c_int32()
+    check(capi.lib().ufe_krylov_solve(ct.byref(s), vp(b), vp(x), ct.c_double(rtol), ct.c_double(abstol),
+                                      KRYLOV_METHODS[method], maxits, int(guess_nonzero), ct.byref(its),
+                                      ct.byref(fl)))
+    return x, its.value, fl.value
+
+
+@dataclass
+class SolveInfo:
+    n_visc_its: int
+    n_Axb_its: int
+    flags: int
+    L2_uv: float
+    visc_it_relax_applied: float
+    Glens_flow_law_epsilon_sq_0_applied: float
+    ms_total: float
+    ms_closures: float
+    ms_assembly: float
+    ms_krylov: float
+    ms_h2d: float
+    ms_d2h: float
+    gpu_launches: int
+
+
+def _info(s: capi.ufe_solve_info) -> SolveInfo:
+    return SolveInfo(*[getattr(s, f[0]) for f in capi.ufe_solve_info._fields_])
+
+
+class DIVASolver:
+    """type_ice_velocity_solver_DIVA (+ _SSA) bound to one mesh; owns the device handle."""
+
+    STATE_FIELDS_B = ("u_vav_b", "v_vav_b", "tau_bx_b", "tau_by_b", "u_base_b", "v_base_b")
+
+    def __init__(self, mesh: Mesh, C: Config, comm=None, operators=None):
+        """comm: None (one GPU) or (rank, nranks, device, nccl_unique_id_bytes).
+        operators: None -> built on the GPU; or dict name -> CSRMatrix holding this rank's rows."""
+        self.mesh, self.C = mesh, C
+        self._keep = []
+        m = capi.ufe_mesh()
+        m.nV, m.nTri, m.nC_mem, m.nz = mesh.nV, mesh.nTri, mesh.nC_mem, mesh.nz
+        m.xmin, m.xmax, m.ymin, m.ymax = mesh.xmin, mesh.xmax, mesh.ymin, mesh.ymax
+        for name in ("V", "Tri", "TriC", "C", "nC", "iTri", "niTri", "VBI", "TriBI", "TriGC", "zeta"):
+            a = getattr(mesh, name)
+            a = np.asfortranarray(a)
+            self._keep.append(a)
+            setattr(m, name, vp(a))
+        if operators is not None:
+            self._csr_structs = []
+            for fam, attr in (("a_b", "M_a_b"), ("b_a", "M_b_a"), ("b_b", "M2_b_b")):
+                arr = getattr(m, attr)
+                for i, w in enumerate(FAMILIES[fam][1]):
+                    nm = ("M2_%s_b_b" % w) if fam == "b_b" else ("M_%s_%s" % (w, fam))
+                    A = operators[nm]
+                    s = capi.csr_struct(A.m, A.n, A.i1, A.i2, A.ptr, A.ind, A.val, self._keep)
+                    self._csr_structs.append(s)
+                    arr[i] = ct.pointer(s)
+        cs = config_struct(C)
+        cm = None
+        if comm is not None:
+            rank, nranks, device, uid = comm
+            self._uid = ct.create_string_buffer(uid, 128) if uid is not None else None
+            cm = capi.ufe_comm(rank, nranks, device, ct.cast(self._uid, ct.c_char_p) if self._uid else None)
+        self._h = ct.c_void_p()
+        check(capi.lib().ufe_diva_create(ct.byref(m), ct.byref(cs), ct.byref(cm) if cm else None,
+                                         ct.byref(self._h)))
+        nT, nV, nz = mesh.nTri, mesh.nV, mesh.nz
+        # allocate_DIVA_solver (DIVA_main.f90:752-804) with 'zero' initial velocities
+        z = np.zeros
+        self.u_vav_b, self.v_vav_b = z(nT), z(nT)
+        self.tau_bx_b, self.tau_by_b = z(nT), z(nT)
+        self.u_base_b, self.v_base_b = z(nT), z(nT)
+        self.eta_3D_b = z((nT, nz), order="F")
+        self.u_3D_b, self.v_3D_b = z((nT, nz), order="F"), z((nT, nz), order="F")
+        self.du_dx_a, self.du_dy_a, self.dv_dx_a, self.dv_dy_a = z(nV), z(nV), z(nV), z(nV)
+        self.du_dz_3D_a, self.dv_dz_3D_a = z((nV, nz), order="F"), z((nV, nz), order="F")
+        self.eta_3D_a = z((nV, nz), order="F")
+        self.basal_friction_coefficient_a = z(nV)
+        # SSA state
+        self.u_b, self.v_b = z(nT), z(nT)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            capi.lib().ufe_diva_destroy(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- config
+    def set_config(self, C: Config):
+        cs = config_struct(C)
+        check(capi.lib().ufe_diva_set_config(self._h, ct.byref(cs)))
+        self.C = C
+
+    def ownership(self):
+        v = [ct.c_int32() for _ in range(4)]
+        check(capi.lib().ufe_get_ownership(self._h, *[ct.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    # ---- structs
+    def _ice_struct(self, ice, bc=None):
+        s = capi.ufe_ice_inputs()
+        keep = []
+
+        def put(name, arr, dtype):
+            if arr is None:
+                return
+            a = np.asfortranarray(arr, dtype=dtype)
+            keep.append(a)
+            setattr(s, name, vp(a))
+        for n in ("Hi", "Hs", "Hib", "SL", "fraction_gr", "fraction_gr_b", "effective_pressure", "Ti",
+                  "till_friction_angle", "alpha_sq", "beta_sq"):
+            put(n, getattr(ice, n, None), np.float64)
+        for n in ("mask_grounded_ice", "mask_floating_ice", "mask_icefree_land"):
+            put(n, getattr(ice, n, None), np.int32)
+        if bc is not None:
+            put("BC_prescr_mask_b", bc[0], np.int32)
+            put("BC_prescr_u_b", bc[1], np.float64)
+            put("BC_prescr_v_b", bc[2], np.float64)
+        return s, keep
+
+    def _state_struct(self, outputs=True):
+        s = capi.ufe_diva_state()
+        names = ["u_vav_b", "v_vav_b", "tau_bx_b", "tau_by_b", "eta_3D_b", "u_base_b", "v_base_b"]
+        if outputs:
+            names += ["u_3D_b", "v_3D_b", "du_dx_a", "du_dy_a", "dv_dx_a", "dv_dy_a", "du_dz_3D_a",
+                      "dv_dz_3D_a", "eta_3D_a", "basal_friction_coefficient_a"]
+        for n in names:
+            setattr(s, n, vp(getattr(self, n)))
+        return s
+
+    # ---- L2
+    def solve_DIVA(self, ice, BC_prescr_mask_b=None, BC_prescr_u_b=None, BC_prescr_v_b=None,
+                   outputs=True) -> SolveInfo:
+        """solve_DIVA(mesh, ice, bed_roughness, DIVA, n_visc_its, n_Axb_its [, BC_prescr_*])."""
+        given = [a is not None for a in (BC_prescr_mask_b, BC_prescr_u_b, BC_prescr_v_b)]
+        if any(given) and not all(given):
+            raise UfeError(1, "need to provide prescribed u,v fields and mask!")
+        bc = (BC_prescr_mask_b, BC_prescr_u_b, BC_prescr_v_b) if all(given) else None
+        s_ice, keep = self._ice_struct(ice, bc)
+        st = self._state_struct(outputs)
+        info = capi.ufe_solve_info()
+        check(capi.lib().ufe_diva_solve(self._h, ct.byref(s_ice), ct.byref(st), ct.byref(info)))
+        return _info(info)
+
+    def solve_SSA(self, ice, BC_prescr_mask_b=None, BC_prescr_u_b=None, BC_prescr_v_b=None) -> SolveInfo:
+        given = [a is not None for a in (BC_prescr_mask_b, BC_prescr_u_b, BC_prescr_v_b)]
+        if any(given) and not all(given):
+            raise UfeError(1, "need to provide prescribed u,v fields and mask!")
+        bc = (BC_prescr_mask_b, BC_prescr_u_b, BC_prescr_v_b) if all(given) else None
+        s_ice, keep = self._ice_struct(ice, bc)
+        st = capi.ufe_ssa_state(vp(self.u_b), vp(self.v_b), vp(self.basal_friction_coefficient_a))
+        info = capi.ufe_solve_info()
+        check(capi.lib().ufe_ssa_solve(self._h, ct.byref(s_ice), ct.byref(st), ct.byref(info)))
+        return _info(info)
+
+    # ---- device-resident variants
+    def upload(self, ice=None, state=True):
+        s_ice, keep = self._ice_struct(ice) if ice is not None else (None, None)
+        st = self._state_struct(False) if state else None
+        check(capi.lib().ufe_diva_upload(self._h, ct.byref(s_ice) if s_ice else None,
+                                         ct.byref(st) if st else None))
+
+    def solve_DIVA_resident(self) -> SolveInfo:
+        info = capi.ufe_solve_info()
+        check(capi.lib().ufe_diva_solve_resident(self._h, ct.byref(info)))
+        return _info(info)
+
+    def download(self, outputs=True):
+        st = self._state_struct(outputs)
+        check(capi.lib().ufe_diva_download(self._h, ct.byref(st)))
+
+    # ---- L1
+    def solve_SSA_DIVA_linearised(self, u_b, v_b, N_b, dN_dx_b, dN_dy_b, basal_friction_coefficient_b,
+                                  tau_dx_b, tau_dy_b, PETSc_rtol, PETSc_abstol, BC_prescr_mask_b=None,
+                                  BC_prescr_u_b=None, BC_prescr_v_b=None):
+        """Returns (u_b, v_b, u_b_prev, v_b_prev, n_Axb_its)."""
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        u, v = np.array(u_b, dtype=np.float64), np.array(v_b, dtype=np.float64)
+        up, vpv = np.zeros_like(u), np.zeros_like(v)
+        args = [c(a) for a in (N_b, dN_dx_b, dN_dy_b, basal_friction_coefficient_b, tau_dx_b, tau_dy_b)]
+        its = ct.c_int32()
+        m = None if BC_prescr_mask_b is None else np.ascontiguousarray(BC_prescr_mask_b, dtype=np.int32)
+        bu = None if BC_prescr_u_b is None else c(BC_prescr_u_b)
+        bv = None if BC_prescr_v_b is None else c(BC_prescr_v_b)
+        check(capi.lib().ufe_ssa_diva_linearised(self._h, vp(u), vp(v), *[vp(a) for a in args], vp(up), vp(vpv),
+                                                 ct.c_double(PETSc_rtol), ct.c_double(PETSc_abstol),
+                                                 ct.byref(its), vp(m), vp(bu), vp(bv)))
+        return u, v, up, vpv, its.value
+
+    # ---- operators (mesh%M_*), as held on the device
+    def get_operator(self, family: str, which: str) -> CSRMatrix:
+        fid, names = FAMILIES[family]
+        w = names.index(which)
+        m_loc, nnz = ct.c_int32(), ct.c_int32()
+        check(capi.lib().ufe_mesh_get_operator(self._h, fid, w, ct.byref(m_loc), ct.byref(nnz), None, None, None))
+        ptr = np.zeros(m_loc.value + 1, dtype=np.int32)
+        ind = np.zeros(max(nnz.value, 1), dtype=np.int32)
+        val = np.zeros(max(nnz.value, 1))
+        check(capi.lib().ufe_mesh_get_operator(self._h, fid, w, ct.byref(m_loc), ct.byref(nnz), vp(ptr), vp(ind), vp(val)))
+        vi1, vi2, ti1, ti2 = self.ownership()
+        i1, i2 = (vi1, vi2) if family == "b_a" else (ti1, ti2)
+        m = self.mesh.nV if family == "b_a" else self.mesh.nTri
+        n = self.mesh.nV if family == "a_b" else self.mesh.nTri
+        return CSRMatrix(m, n, i1, i2, ptr, ind[:nnz.value], val[:nnz.value])
+
+    def _apply(self, family, which, d):
+        fid, names = FAMILIES[family]
+        x = np.asfortranarray(d, dtype=np.float64)
+        nl = 1 if x.ndim == 1 else x.shape[1]
+        m = self.mesh.nV if family == "b_a" else self.mesh.nTri
+        y = np.zeros((m,) if x.ndim == 1 else (m, nl), order="F")
+        check(capi.lib().ufe_mesh_apply_operator(self._h, fid, names.index(which), vp(x), vp(y), nl))
+        return y
+
+    # mesh_disc_apply_operators.f90:121-431
+    def map_a_b_2D(self, d): return self._apply("a_b", "map", d)
+    def map_a_b_3D(self, d): return self._apply("a_b", "map", d)
+    def ddx_a_b_2D(self, d): return self._apply("a_b", "ddx", d)
+    def ddy_a_b_2D(self, d): return self._apply("a_b", "ddy", d)
+    def map_b_a_2D(self, d): return self._apply("b_a", "map", d)
+    def map_b_a_3D(self, d): return self._apply("b_a", "map", d)
+    def ddx_b_a_2D(self, d): return self._apply("b_a", "ddx", d)
+    def ddy_b_a_2D(self, d): return self._apply("b_a", "ddy", d)
+
+    def get_stiffness_matrix(self):
+        """(A_CSR, bb) of the most recent linearised solve, reference layout."""
+        m_loc, nnz = ct.c_int32(), ct.c_int32()
+        check(capi.lib().ufe_get_stiffness_csr(self._h, ct.byref(m_loc), ct.byref(nnz), None, None, None, None))
+        ptr = np.zeros(m_loc.value + 1, dtype=np.int32)
+        ind = np.zeros(max(nnz.value, 1), dtype=np.int32)
+        val = np.zeros(max(nnz.value, 1))
+        bb = np.zeros(max(m_loc.value, 1))
+        check(capi.lib().ufe_get_stiffness_csr(self._h, ct.byref(m_loc), ct.byref(nnz), vp(ptr), vp(ind), vp(val), vp(bb)))
+        _, _, ti1, ti2 = self.ownership()
+        N = 2 * self.mesh.nTri
+        return CSRMatrix(N, N, 2 * ti1 - 1, 2 * ti2, ptr, ind[:nnz.value], val[:nnz.value]), bb[:m_loc.value]
+
+    def bench_spmv(self, reps=50, flush_l2=False):
+        ms, by = ct.c_double(), ct.c_double()
+        check(capi.lib().ufe_bench_spmv(self._h, reps, int(flush_l2), ct.byref(ms), ct.byref(by)))
+        return ms.value, by.value
+
+
+def initialise_DIVA_solver(mesh: Mesh, C: Config, comm=None, operators=None) -> DIVASolver:
+    """initialise_DIVA_solver (DIVA_main.f90:37-86): allocate + 'zero' initial velocities."""
+    if C.choice_initial_velocity != "zero":
+        raise UfeError(1, f'unknown choice_initial_velocity "{C.choice_initial_velocity}"! '
+                          "(read_from_file is NetCDF I/O, out of scope: set the state arrays instead)")
+    return DIVASolver(mesh, C, comm, operators)
