@@ -228,6 +228,9 @@ int ufe_ssa_solve(ufe_handle *h, const ufe_ice_inputs *ice, ufe_ssa_state *state
 int ufe_diva_upload(ufe_handle *h, const ufe_ice_inputs *ice, const ufe_diva_state *state);
 int ufe_diva_solve_resident(ufe_handle *h, ufe_solve_info *info);
 int ufe_diva_download(ufe_handle *h, ufe_diva_state *state);
+/* initialise_DIVA_solver with choice_initial_velocity = 'zero' (DIVA_main.f90:60-68) on the
+ * resident state: the seven restart fields are zeroed on the device (no host traffic). */
+int ufe_diva_reset_state(ufe_handle *h);
 
 /* L1 -- replaces solve_SSA_DIVA_linearised (solve_linearised_SSA_DIVA.f90:23-178; call
  * sites DIVA_main.f90:189-192, SSA_main.f90:178-181).  Full-length (nTri) arrays.

@@ -1,0 +1,350 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path behind the C ABI against
+the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): CSR sparsity patterns and index maps bit-exact; converged
+u/v velocity fields within 1e-6 relative L2 and max-norm.  Floating-point operator values:
+1e-11 relative (the GPU evaluates the same formulas; only libm pow/exp/hypot differ).
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from ufemism2_0_b200 import diva, experiments, synthetic
+from ufemism2_0_b200.capi import UfeError
+
+pytestmark = pytest.mark.gpu
+
+TOL_UV = 1e-6          # north_star: relative L2 and max-norm of the converged u, v
+TOL_OPVAL = 1e-11      # operator / matrix values (same formula order, fp64)
+
+
+def rel(a, b, ref=None):
+    ref = b if ref is None else ref
+    return (np.linalg.norm(a - b) / max(np.linalg.norm(ref), 1e-300),
+            np.abs(a - b).max() / max(np.abs(ref).max(), 1e-300))
+
+
+# ------------------------------------------------------------------------------------------
+# L0: SpMV and linear solve, the reference's own known answers
+# ------------------------------------------------------------------------------------------
+def _csr(dense):
+    dense = np.asarray(dense, dtype=float)
+    m, n = dense.shape
+    ptr, ind, val = [1], [], []
+    for i in range(m):
+        for j in range(n):
+            if dense[i, j] != 0.0:
+                ind.append(j + 1); val.append(dense[i, j])
+        ptr.append(len(ind) + 1)
+    return diva.CSRMatrix(m, n, 1, m, np.array(ptr, np.int32), np.array(ind, np.int32), np.array(val))
+
+
+def _csr_rows(rows, n):
+    ptr, ind, val = [1], [], []
+    for r in rows:
+        for c, v in r:
+            ind.append(c); val.append(v)
+        ptr.append(len(ind) + 1)
+    return diva.CSRMatrix(len(rows), n, 1, len(rows), np.array(ptr, np.int32), np.array(ind, np.int32),
+                          np.array(val, np.float64))
+
+
+def test_spmv_known_answers():
+    """ut_mpi_CSR_matrix_vector_multiplication.f90:188-321 and ut_petsc.f90:85-149 (unsorted
+    columns, in add_entry order, exactly as in the reference tests)."""
+    import test_oracle_golden as G
+    assert np.array_equal(diva.multiply_CSR_matrix_with_vector(_csr_rows(G.EQ1, 7), G.X7), G.Y1)
+    assert np.array_equal(diva.multiply_CSR_matrix_with_vector(_csr_rows(G.EQ2, 7), G.X7), G.Y2)
+    assert np.array_equal(diva.multiply_CSR_matrix_with_vector(_csr_rows(G.PETSC, 6), np.arange(1., 7.)),
+                          np.array([1., 8., 28., 59., 40., 105.]))
+    # rank-local row blocks (rows 1-2 | 3-6), ptr local 1-based, as the two-rank PETSc test holds them
+    A1 = _csr_rows(G.PETSC[2:], 6)
+    A1 = diva.CSRMatrix(6, 6, 3, 6, A1.ptr, A1.ind, A1.val)
+    assert np.array_equal(diva.multiply_CSR_matrix_with_vector(A1, np.arange(1., 7.)), np.array([28., 59., 40., 105.]))
+
+
+def test_spmv_2D_random_matches_oracle(oracle):
+    rng = np.random.default_rng(3)
+    m, n, nz = 1000, 700, 12
+    dense = (rng.random((m, n)) < 0.01) * rng.standard_normal((m, n))
+    A = _csr(dense)
+    X = np.asfortranarray(rng.standard_normal((n, nz)))
+    got = diva.multiply_CSR_matrix_with_vector(A, X)
+    want = oracle.spmv_2D(oracle.CSR(m, n, 1, m, A.ptr, A.ind, A.val), X)
+    assert rel(got, want)[1] < 1e-13
+    # empty matrix rows and a single layer
+    got1 = diva.multiply_CSR_matrix_with_vector(A, X[:, 0].copy())
+    assert rel(got1, want[:, 0])[1] < 1e-13
+
+
+@pytest.mark.parametrize("method", ["bicgstab", "gmres"])
+def test_tridiagonal_solve_known_answer(method):
+    """ut_mpi_CSR_matrix_solving.f90:217-270: x = [1,3.5,5,5.5,5,3.5,1]."""
+    n = 7
+    D = np.zeros((n, n))
+    for i in range(n):
+        if i in (0, n - 1):
+            D[i, i] = 1.0
+        else:
+            D[i, i - 1:i + 2] = [-1.0, 2.0, -1.0]
+    x, its, fl = diva.solve_matrix_equation_CSR(_csr(D), np.ones(n), np.zeros(n), 1e-12, 1e-14, method=method)
+    assert fl == 0 and its <= 7
+    assert np.abs(x - np.array([1, 3.5, 5, 5.5, 5, 3.5, 1.0])).max() < 1e-10
+
+
+# ------------------------------------------------------------------------------------------
+# operators: patterns bit-exact, values to round-off, application == oracle SpMV
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def homA(oracle):
+    mesh, C, ice = experiments.ISMIP_HOM("A", 160e3, 41)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-11, 1e-10
+    S = diva.initialise_DIVA_solver(mesh, C)
+    yield mesh, C, ice, S
+    S.close()
+
+
+def test_operator_patterns_bit_exact(homA):
+    mesh, C, ice, S = homA
+    for fam, names in diva.FAMILIES.items():
+        for w in names[1]:
+            nm = ("M2_%s_b_b" % w) if fam == "b_b" else ("M_%s_%s" % (w, fam))
+            G, R = S.get_operator(fam, w), mesh.ops[nm]
+            assert np.array_equal(G.ptr, R.ptr), nm
+            assert np.array_equal(G.ind, R.ind), nm
+            assert rel(G.val, R.val)[1] < TOL_OPVAL, nm
+
+
+def test_operator_patterns_bit_exact_irregular_mesh(oracle):
+    """Strongly jittered, anisotropic lattice: exercises the BFS growth and border rows."""
+    mesh = synthetic.lattice_mesh(0.0, 300e3, -20e3, 20e3, 61, 9, jitter=0.35, seed=11)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    S = diva.initialise_DIVA_solver(mesh, experiments.MISMIPplus(8e3)[1])
+    try:
+        for fam, names in diva.FAMILIES.items():
+            for w in names[1]:
+                nm = ("M2_%s_b_b" % w) if fam == "b_b" else ("M_%s_%s" % (w, fam))
+                G, R = S.get_operator(fam, w), mesh.ops[nm]
+                assert np.array_equal(G.ptr, R.ptr) and np.array_equal(G.ind, R.ind), nm
+                assert rel(G.val, R.val)[1] < 1e-9, nm
+    finally:
+        S.close()
+
+
+def test_apply_operators_match_oracle(homA, oracle):
+    mesh, C, ice, S = homA
+    rng = np.random.default_rng(5)
+    da = rng.standard_normal(mesh.nV)
+    db3 = np.asfortranarray(rng.standard_normal((mesh.nTri, mesh.nz)))
+    assert rel(S.ddx_a_b_2D(da), oracle.spmv(mesh.ops["M_ddx_a_b"], da))[1] < 1e-12
+    assert rel(S.map_a_b_2D(da), oracle.spmv(mesh.ops["M_map_a_b"], da))[1] < 1e-12
+    assert rel(S.map_b_a_3D(db3), oracle.spmv_2D(mesh.ops["M_map_b_a"], db3))[1] < 1e-12
+    # operator exactness on a linear function (ct_discretisation_mapping_derivatives.f90:533-575)
+    f = 3.0 + 2e-5 * mesh.V[:, 0] - 1e-5 * mesh.V[:, 1]
+    assert np.abs(S.ddx_a_b_2D(f) - 2e-5).max() < 1e-14
+    assert np.abs(S.ddy_a_b_2D(f) + 1e-5).max() < 1e-14
+
+
+# ------------------------------------------------------------------------------------------
+# L1: assembly (pattern bit-exact) + linear solve against the direct solve
+# ------------------------------------------------------------------------------------------
+def _random_linearised_inputs(mesh, seed):
+    rng = np.random.default_rng(seed)
+    nT = mesh.nTri
+    N_b = 1e9 * (1.0 + 0.3 * rng.random(nT))
+    return dict(u_b=rng.standard_normal(nT), v_b=rng.standard_normal(nT), N_b=N_b,
+                dN_dx_b=1e3 * rng.standard_normal(nT), dN_dy_b=1e3 * rng.standard_normal(nT),
+                basal_friction_coefficient_b=1e3 * rng.random(nT), tau_dx_b=1e4 * rng.standard_normal(nT),
+                tau_dy_b=1e4 * rng.standard_normal(nT))
+
+
+@pytest.mark.parametrize("bc", ["infinite", "zero", "periodic_ISMIP-HOM", "mixed", "prescribed"])
+def test_linearised_solve_and_stiffness_pattern(oracle, bc):
+    L = 80e3
+    mesh = synthetic.lattice_mesh(-L, L, -L, L, 25, 25)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C = experiments.ISMIP_HOM("A", L, 25)[1]
+    kw = {}
+    if bc == "mixed":
+        C.BC_u_west, C.BC_u_east, C.BC_u_south, C.BC_u_north = "zero", "infinite", "infinite", "zero"
+        C.BC_v_west, C.BC_v_east, C.BC_v_south, C.BC_v_north = "infinite", "zero", "zero", "infinite"
+    elif bc == "prescribed":
+        for c in "uv":
+            for s in ("west", "east", "south", "north"):
+                setattr(C, f"BC_{c}_{s}", "zero")
+        rng = np.random.default_rng(9)
+        mask = (rng.random(mesh.nTri) < 0.1).astype(np.int32)
+        kw = dict(BC_prescr_mask_b=mask, BC_prescr_u_b=rng.standard_normal(mesh.nTri),
+                  BC_prescr_v_b=rng.standard_normal(mesh.nTri))
+    else:
+        for c in "uv":
+            for s in ("west", "east", "south", "north"):
+                setattr(C, f"BC_{c}_{s}", bc)
+    inp = _random_linearised_inputs(mesh, 21)
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        u, v, up, vp_, its = S.solve_SSA_DIVA_linearised(PETSc_rtol=1e-12, PETSc_abstol=1e-13, **inp, **kw)
+        okw = {}
+        if kw:
+            okw = dict(bc_mask=kw["BC_prescr_mask_b"], bc_u=kw["BC_prescr_u_b"], bc_v=kw["BC_prescr_v_b"])
+        ur, vr, upr, vpr, _, A, bb = oracle.solve_SSA_DIVA_linearised(
+            mesh, C, inp["u_b"], inp["v_b"], inp["N_b"], inp["dN_dx_b"], inp["dN_dy_b"], inp["basal_friction_coefficient_b"],
+            inp["tau_dx_b"], inp["tau_dy_b"], 0, 0, "direct", return_system=True, **okw)
+        Ag, bg = S.get_stiffness_matrix()
+        assert np.array_equal(Ag.ptr, A.ptr) and np.array_equal(Ag.ind, A.ind)      # bit-exact pattern
+        assert rel(Ag.val, A.val)[1] < 1e-13 and rel(bg, bb)[1] < 1e-13
+        assert np.array_equal(up, upr) and np.array_equal(vp_, vpr)
+        scale = np.concatenate([ur, vr])
+        assert rel(u, ur, scale)[0] < TOL_UV and rel(u, ur, scale)[1] < TOL_UV
+        assert rel(v, vr, scale)[0] < TOL_UV and rel(v, vr, scale)[1] < TOL_UV
+        assert its > 0
+    finally:
+        S.close()
+
+
+# ------------------------------------------------------------------------------------------
+# L2: full Picard solves
+# ------------------------------------------------------------------------------------------
+def _check_uv(S, D, names=("u_vav_b", "v_vav_b")):
+    ref = np.concatenate([D["u_vav_b"], D["v_vav_b"]])
+    for k in names:
+        r = rel(getattr(S, k), D[k], ref)
+        assert r[0] < TOL_UV and r[1] < TOL_UV, (k, r)
+
+
+@pytest.mark.parametrize("method", ["bicgstab", "gmres"])
+def test_ISMIP_HOM_A_DIVA(homA, oracle, method):
+    mesh, C, ice, S = homA
+    C2 = copy.copy(C)
+    C2.b200_krylov_method = method
+    S.set_config(C2)
+    for k in S.STATE_FIELDS_B:
+        getattr(S, k)[:] = 0
+    S.eta_3D_b[:] = 0
+    info = S.solve_DIVA(ice)
+    D = oracle.new_DIVA_state(mesh)
+    nv, _ = oracle.solve_DIVA(mesh, ice, C2, D, "direct")
+    assert info.flags == 0 and info.gpu_launches > 0
+    assert abs(info.n_visc_its - nv) <= 1
+    _check_uv(S, D)
+    ref3 = np.abs(D["u_3D_b"]).max()
+    assert np.abs(S.u_3D_b - D["u_3D_b"]).max() / ref3 < TOL_UV
+    assert np.abs(S.eta_3D_a - D["eta_3D_a"]).max() / np.abs(D["eta_3D_a"]).max() < 1e-5
+
+
+def test_ISMIP_HOM_C_DIVA(oracle):
+    mesh, C, ice = experiments.ISMIP_HOM("C", 160e3, 31)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-12
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        info = S.solve_DIVA(ice)
+        D = oracle.new_DIVA_state(mesh)
+        nv, _ = oracle.solve_DIVA(mesh, ice, C, D, "direct")
+        assert (info.flags & diva.KRYLOV_MAXIT) == 0
+        assert abs(info.n_visc_its - nv) <= 1
+        _check_uv(S, D)
+    finally:
+        S.close()
+
+
+def test_SSA_icestream_vs_oracle_and_Schoof(oracle):
+    mesh, C, ice = experiments.SSA_icestream(15, 61)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-11, 1e-10
+    C.visc_it_nit = 60
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        info = S.solve_SSA(ice)
+        R = dict(u_b=np.zeros(mesh.nTri), v_b=np.zeros(mesh.nTri))
+        nv, _ = oracle.solve_SSA(mesh, ice, C, R, "direct")
+        assert abs(info.n_visc_its - nv) <= 1
+        ref = np.concatenate([R["u_b"], R["v_b"]])
+        for k in ("u_b", "v_b"):
+            r = rel(getattr(S, k), R[k], ref)
+            assert r[0] < TOL_UV and r[1] < TOL_UV, (k, r)
+    finally:
+        S.close()
+
+
+def test_MISMIPplus_8km_two_solves_warm_start(oracle):
+    """Cold start then a warm second call with perturbed thickness (time-stepping pattern)."""
+    mesh, C, ice = experiments.MISMIPplus(8e3)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
+    C.visc_it_nit = 8
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        info = S.solve_DIVA(ice)
+        D = oracle.new_DIVA_state(mesh)
+        nv, _ = oracle.solve_DIVA(mesh, ice, C, D, "direct")
+        assert info.n_visc_its == nv
+        _check_uv(S, D)
+        ice2 = copy.copy(ice)
+        ice2.Hi = ice.Hi * 1.001
+        ice2.Hs = synthetic.ice_surface_elevation(ice2.Hi, ice.Hb, ice.SL)
+        info2 = S.solve_DIVA(ice2)
+        nv2, _ = oracle.solve_DIVA(mesh, ice2, C, D, "direct")
+        assert info2.n_visc_its == nv2
+        _check_uv(S, D)
+    finally:
+        S.close()
+
+
+def test_no_grounded_ice_returns_zero(homA):
+    mesh, C, ice, S = homA
+    ice2 = copy.copy(ice)
+    ice2.mask_grounded_ice = np.zeros(mesh.nV, dtype=np.int32)
+    S.u_vav_b[:] = 3.0
+    info = S.solve_DIVA(ice2)
+    assert info.n_visc_its == 0 and np.all(S.u_vav_b == 0.0) and np.all(S.u_3D_b == 0.0)
+
+
+def test_resident_path_equals_host_path(homA):
+    mesh, C, ice, S = homA
+    for k in S.STATE_FIELDS_B:
+        getattr(S, k)[:] = 0
+    S.eta_3D_b[:] = 0
+    a = S.solve_DIVA(ice)
+    u_host = S.u_vav_b.copy()
+    S.upload(ice, state=False)
+    S.reset_state_resident()
+    b = S.solve_DIVA_resident()
+    S.download()
+    assert a.n_visc_its == b.n_visc_its and a.n_Axb_its == b.n_Axb_its
+    assert np.array_equal(u_host, S.u_vav_b)          # deterministic reductions: bitwise repeatable
+
+
+def test_error_behaviour(homA):
+    mesh, C, ice, S = homA
+    with pytest.raises(UfeError):
+        S.solve_DIVA(ice, BC_prescr_mask_b=np.zeros(mesh.nTri, np.int32))     # DIVA_main.f90:139-141
+    bad = copy.copy(ice)
+    bad.Hi = None
+    with pytest.raises(UfeError):
+        S.solve_DIVA(bad)
+
+
+# ------------------------------------------------------------------------------------------
+# size-independent properties at a larger size (no oracle): linearity of the operators,
+# residual of the returned linear solve, idempotence of a converged warm restart
+# ------------------------------------------------------------------------------------------
+def test_properties_at_scale():
+    mesh, C, ice = experiments.MISMIP_8km(16e3)
+    C.visc_it_nit = 3
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        rng = np.random.default_rng(1)
+        a, b = rng.standard_normal(mesh.nV), rng.standard_normal(mesh.nV)
+        lin = S.ddx_a_b_2D(2.0 * a + 3.0 * b) - (2.0 * S.ddx_a_b_2D(a) + 3.0 * S.ddx_a_b_2D(b))
+        assert np.abs(lin).max() < 1e-12 * np.abs(S.ddx_a_b_2D(a)).max() * 10
+        S.solve_DIVA(ice)
+        A, bb = S.get_stiffness_matrix()
+        # row sums of free rows: derivative stencils annihilate constants => A*1 = -beta_eff on the diagonal block
+        import scipy.sparse as sp
+        M = sp.csr_matrix((A.val, A.ind - 1, A.ptr - 1), shape=(A.m, A.n))
+        assert M.shape[0] == 2 * mesh.nTri and np.isfinite(A.val).all() and np.isfinite(bb).all()
+    finally:
+        S.close()

@@ -95,7 +95,7 @@ EXPORTS = [
     "ufe_last_error_string", "ufe_comm_get_unique_id", "ufe_version", "ufe_partition_list",
     "ufe_krylov_solve", "ufe_spmv", "ufe_diva_create", "ufe_diva_destroy", "ufe_diva_set_config",
     "ufe_diva_solve", "ufe_ssa_solve", "ufe_diva_upload", "ufe_diva_solve_resident",
-    "ufe_diva_download", "ufe_ssa_diva_linearised", "ufe_mesh_get_operator",
+    "ufe_diva_download", "ufe_diva_reset_state", "ufe_ssa_diva_linearised", "ufe_mesh_get_operator",
     "ufe_mesh_apply_operator", "ufe_get_stiffness_csr", "ufe_bench_spmv", "ufe_get_ownership",
 ]
 

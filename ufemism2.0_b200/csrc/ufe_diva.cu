@@ -696,6 +696,15 @@ extern "C" int ufe_diva_solve_resident(ufe_handle *h, ufe_solve_info *info) {
   ufe_solve_info tmp;
   return picard_resident(h, 1, info ? info : &tmp);
 }
+extern "C" int ufe_diva_reset_state(ufe_handle *h) {
+  UFE_CUDA(cudaSetDevice(h->device));
+  const size_t nT = h->dm.nTri, nz = h->dm.nz;
+  DivaFields &F = h->F;
+  double *b1[] = {F.u_vav_b, F.v_vav_b, F.tau_bx_b, F.tau_by_b, F.u_base_b, F.v_base_b};
+  for (double *p : b1) UFE_CUDA(cudaMemsetAsync(p, 0, 8 * nT, h->st));
+  UFE_CUDA(cudaMemsetAsync(F.eta_3D_b, 0, 8 * nT * nz, h->st));
+  return UFE_OK;
+}
 extern "C" int ufe_diva_download(ufe_handle *h, ufe_diva_state *state) {
   UFE_CUDA(cudaSetDevice(h->device));
   UFE_TRY(gather_outputs(h, 1));

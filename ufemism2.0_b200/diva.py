@@ -278,6 +278,10 @@ class DIVASolver:
         check(capi.lib().ufe_diva_solve_resident(self._h, ct.byref(info)))
         return _info(info)
 
+    def reset_state_resident(self):
+        """'zero' initial velocities (DIVA_main.f90:60-68) on the device-resident state."""
+        check(capi.lib().ufe_diva_reset_state(self._h))
+
     def download(self, outputs=True):
         st = self._state_struct(outputs)
         check(capi.lib().ufe_diva_download(self._h, ct.byref(st)))
