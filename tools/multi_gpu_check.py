@@ -1,0 +1,50 @@
+"""torchrun --nproc-per-node N tools/multi_gpu_check.py : N-rank solves (strip partition by
+partition_list, halo exchange + allreduce over NCCL) compared on rank 0 with the oracle."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import numpy as np
+import torch, torch.distributed as dist
+import ufe_pkg; ufe_pkg.load()
+from ufemism2_0_b200 import experiments, diva, capi
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+def make_comm():
+    """A fresh NCCL unique id per handle (an id can initialise one communicator only)."""
+    uid = torch.zeros(128, dtype=torch.uint8, device='cuda')
+    if rank == 0:
+        buf = (capi.ct.c_char * 128)()
+        capi.check(capi.lib().ufe_comm_get_unique_id(buf))
+        uid = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device='cuda')
+    dist.broadcast(uid, 0)
+    return (rank, world, local, bytes(uid.cpu().tolist()))
+
+def rel(a, b, ref):
+    return np.linalg.norm(a - b) / np.linalg.norm(ref), np.abs(a - b).max() / np.abs(ref).max()
+
+ok = True
+for name, (mesh, C, ice) in (('ISMIP-HOM A', experiments.ISMIP_HOM('A', 160e3, 41)), ('ISMIP-HOM C', experiments.ISMIP_HOM('C', 160e3, 31)),
+                             ('MISMIP+ 8km', experiments.MISMIPplus(8e3))):
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
+    if name.startswith('MISMIP'): C.visc_it_nit = 8
+    S = diva.initialise_DIVA_solver(mesh, C, make_comm())
+    t = time.time(); info = S.solve_DIVA(ice); wall = time.time() - t
+    own = S.ownership()
+    if rank == 0:
+        import oracle as O
+        O.build(); O.calc_all_matrix_operators_mesh(mesh)
+        D = O.new_DIVA_state(mesh); nv, _ = O.solve_DIVA(mesh, ice, C, D, 'direct')
+        ref = np.concatenate([D['u_vav_b'], D['v_vav_b']])
+        ru, rv = rel(S.u_vav_b, D['u_vav_b'], ref), rel(S.v_vav_b, D['v_vav_b'], ref)
+        r3 = np.abs(S.u_3D_b - D['u_3D_b']).max() / np.abs(D['u_3D_b']).max()
+        good = max(ru + rv) < 1e-6 and abs(info.n_visc_its - nv) <= 1 and r3 < 1e-6
+        ok &= good
+        print(f'{name}: ranks {world} own {own} Picard {info.n_visc_its} (oracle {nv}) Krylov {info.n_Axb_its} flags {info.flags} '
+              f'u {ru} v {rv} u3D {r3:.2e} wall {wall:.3f}s {"OK" if good else "MISMATCH"}', flush=True)
+    S.close()
+dist.barrier()
+if rank == 0:
+    print('MULTI_GPU_CHECK', 'PASS' if ok else 'FAIL', flush=True)
+dist.destroy_process_group()

@@ -113,6 +113,55 @@ int ufe_colrange(cudaStream_t st, int nnz, const int *ind, int *jmin, int *jmax)
   return UFE_OK;
 }
 
+// ---- blocked sliced-ELL copy for the Krylov loop (layout: DevSystem in ufe_internal.cuh) ----
+__device__ __forceinline__ int bell_row_width(int tl, int ti, int nTri, const int *__restrict__ rowkind,
+                                              const DevFamilyView &M2, const int *__restrict__ TriC) {
+  const int ku = rowkind[2 * tl], kv = rowkind[2 * tl + 1];
+  if (ku == RK_FREE) return M2.ptr[tl + 1] - M2.ptr[tl];
+  if (ku == RK_INFINITE || kv == RK_INFINITE) {
+    int nn = 0;
+    for (int n = 0; n < 3; n++) if (TriC[(size_t)n * nTri + ti] != 0) nn++;
+    return nn + 1;
+  }
+  return 1;
+}
+
+__global__ void k_bell_slice_width(int t0, int nt, int nTri, DevFamilyView M2, const int *__restrict__ TriC,
+                                   const int *__restrict__ rowkind, int *__restrict__ slice_w) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= (nt + 31) / 32) return;
+  const int tl = s * 32 + lane;
+  int w = tl < nt ? bell_row_width(tl, t0 + tl, nTri, rowkind, M2, TriC) : 0;
+  for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+  if (lane == 0) slice_w[s] = w;
+}
+
+__global__ void k_bell_fill_cols(int t0, int nt, int nTri, DevFamilyView M2, const int *__restrict__ TriC,
+                                 const int *__restrict__ rowkind, const int *__restrict__ bell_off,
+                                 int *__restrict__ bell_col) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= (nt + 31) / 32) return;
+  const int tl = s * 32 + lane;
+  const int off = bell_off[s] - 1, w = bell_off[s + 1] - 1 - off;
+  const int ti = tl < nt ? t0 + tl : t0;
+  int e = 0;
+  if (tl < nt) {
+    const int ku = rowkind[2 * tl], kv = rowkind[2 * tl + 1];
+    if (ku == RK_FREE) {
+      for (int j = M2.ptr[tl] - 1; j < M2.ptr[tl + 1] - 1; j++, e++) bell_col[(size_t)(off + e) * 32 + lane] = M2.ind[j] - 1;
+    } else {
+      if (ku == RK_INFINITE || kv == RK_INFINITE)
+        for (int n = 0; n < 3; n++) {
+          const int tj = TriC[(size_t)n * nTri + ti];
+          if (tj == 0) continue;
+          bell_col[(size_t)(off + e) * 32 + lane] = tj - 1; e++;
+        }
+      bell_col[(size_t)(off + e) * 32 + lane] = ti; e++;
+    }
+  }
+  for (; e < w; e++) bell_col[(size_t)(off + e) * 32 + lane] = ti;     // padding: own triangle, zero values
+}
+
 // Builds S.ptr / S.ind for rows 2*t0 .. 2*(t0+nt)-1 (0-based) and allocates val / valS /
 // bb / bS (S.x is allocated by the caller).  *rowkind_io is (re)allocated.
 int ufe_build_stiffness_pattern(cudaStream_t st, int t0, int nt, int nTri, const AssemblyParams &A,
@@ -121,8 +170,10 @@ int ufe_build_stiffness_pattern(cudaStream_t st, int t0, int nt, int nTri, const
   const int m_loc = 2 * nt;
   int *counts = nullptr;
   cudaFree(S.ptr); cudaFree(S.ind); cudaFree(S.val); cudaFree(S.valS); cudaFree(S.bb); cudaFree(S.bS);
+  cudaFree(S.bell_off); cudaFree(S.bell_col); cudaFree(S.bell_val);
   cudaFree(*rowkind_io);
   S.ptr = S.ind = nullptr; S.val = S.valS = S.bb = S.bS = nullptr; *rowkind_io = nullptr;
+  S.bell_off = S.bell_col = nullptr; S.bell_val = nullptr; S.nslices = 0; S.bell_entries = 0;
   UFE_CUDA(cudaMalloc(&counts, sizeof(int) * (m_loc > 0 ? m_loc : 1)));
   UFE_CUDA(cudaMalloc(rowkind_io, sizeof(int) * (m_loc > 0 ? m_loc : 1)));
   UFE_CUDA(cudaMalloc(&S.ptr, sizeof(int) * (m_loc + 1)));
@@ -134,7 +185,6 @@ int ufe_build_stiffness_pattern(cudaStream_t st, int t0, int nt, int nTri, const
   const size_t nz = S.nnz > 0 ? S.nnz : 1, mb = m_loc > 0 ? m_loc : 1;
   UFE_CUDA(cudaMalloc(&S.ind, sizeof(int) * nz));
   UFE_CUDA(cudaMalloc(&S.val, sizeof(double) * nz));
-  UFE_CUDA(cudaMalloc(&S.valS, sizeof(double) * nz));
   UFE_CUDA(cudaMalloc(&S.bb, sizeof(double) * mb));
   UFE_CUDA(cudaMalloc(&S.bS, sizeof(double) * mb));
   if (nt > 0) {
@@ -144,6 +194,23 @@ int ufe_build_stiffness_pattern(cudaStream_t st, int t0, int nt, int nTri, const
   S.N = 2 * nTri; S.m_loc = m_loc; S.r1 = 2 * t0 + 1;
   UFE_TRY(ufe_colrange(st, S.nnz, S.ind, &S.jmin, &S.jmax));
   cudaFree(counts);
+  // blocked sliced-ELL pattern for the Krylov loop (values are written by k_assemble)
+  if (nt > 0) {
+    const int nsl = (nt + 31) / 32;
+    int *slice_w = nullptr, total = 0;
+    UFE_CUDA(cudaMalloc(&slice_w, sizeof(int) * nsl));
+    UFE_CUDA(cudaMalloc(&S.bell_off, sizeof(int) * (nsl + 1)));
+    k_bell_slice_width<<<ufe_div_up((long long)nsl * 32, 256), 256, 0, st>>>(t0, nt, nTri, M2, TriC, *rowkind_io, slice_w);
+    UFE_LAUNCH_CHECK();
+    UFE_TRY(ufe_counts_to_ptr(st, nsl, slice_w, S.bell_off, &total));     // 1-based offsets, in entries
+    cudaFree(slice_w);
+    S.nslices = nsl; S.bell_entries = total;
+    UFE_CUDA(cudaMalloc(&S.bell_col, sizeof(int) * (size_t)(total > 0 ? total : 1) * 32));
+    UFE_CUDA(cudaMalloc(&S.bell_val, sizeof(double) * (size_t)(total > 0 ? total : 1) * 128));
+    UFE_CUDA(cudaMemsetAsync(S.bell_val, 0, sizeof(double) * (size_t)(total > 0 ? total : 1) * 128, st));
+    k_bell_fill_cols<<<ufe_div_up((long long)nsl * 32, 256), 256, 0, st>>>(t0, nt, nTri, M2, TriC, *rowkind_io, S.bell_off, S.bell_col);
+    UFE_LAUNCH_CHECK();
+  }
   return UFE_OK;
 }
 
@@ -152,11 +219,14 @@ __global__ void __launch_bounds__(128)
 k_assemble(int t0, int nt, int nTri, AssemblyParams A, DevFamilyView M2, const int *__restrict__ TriC,
            const int *__restrict__ rowkind, BCTables T, const int *__restrict__ bc_mask,
            const double *__restrict__ bc_u, const double *__restrict__ bc_v, DivaFields F,
-           const int *__restrict__ ptrA, double *__restrict__ val, double *__restrict__ valS,
-           double *__restrict__ bb, double *__restrict__ bS, double *__restrict__ xg, int write_x) {
+           const int *__restrict__ ptrA, double *__restrict__ val, const int *__restrict__ bell_off,
+           double *__restrict__ bval, double *__restrict__ bb, double *__restrict__ bS,
+           double *__restrict__ xg, int write_x) {
   const int tl = blockIdx.x * blockDim.x + threadIdx.x;
   if (tl >= nt) return;
   const int ti = t0 + tl;
+  // this block row's first entry in the blocked sliced-ELL value array (stride 128 per entry)
+  double *const brow = bval + (size_t)(bell_off[tl >> 5] - 1) * 128 + (tl & 31);
   if (write_x) {                  // uv_buv interleave (:74-84): initial guess for the Krylov solve
     xg[2 * (size_t)ti] = F.u_vav_b[ti];
     xg[2 * (size_t)ti + 1] = F.v_vav_b[ti];
@@ -205,8 +275,9 @@ k_assemble(int t0, int nt, int nTri, AssemblyParams A, DevFamilyView M2, const i
         const int o = 2 * (j - j0);
         val[ku + o] = Au_u; val[ku + o + 1] = Av_u;
         val[kv + o] = Au_v; val[kv + o + 1] = Av_v;
-        valS[ku + o] = B00 * Au_u + B01 * Au_v; valS[ku + o + 1] = B00 * Av_u + B01 * Av_v;
-        valS[kv + o] = B10 * Au_u + B11 * Au_v; valS[kv + o + 1] = B10 * Av_u + B11 * Av_v;
+        double *const be = brow + (size_t)(j - j0) * 128;
+        be[0] = B00 * Au_u + B01 * Au_v; be[32] = B00 * Av_u + B01 * Av_v;
+        be[64] = B10 * Au_u + B11 * Au_v; be[96] = B10 * Av_u + B11 * Av_v;
       }
       if (pass == 1) {
         bb[2 * tl] = b_u; bb[2 * tl + 1] = b_v;
@@ -215,25 +286,35 @@ k_assemble(int t0, int nt, int nTri, AssemblyParams A, DevFamilyView M2, const i
     }
     return;
   }
+  // boundary / prescribed rows.  Blocked copy: neighbours first (if either row is 'infinite'), then
+  // the diagonal block; every scaled diagonal is 1.
+  int nn = 0;
+  for (int n = 0; n < 3; n++) if (TriC[(size_t)n * nTri + ti] != 0) nn++;
+  const double dinf = -1.0 * (double)nn;
+  int e = 0;
+  if (kind_u == RK_INFINITE || kind_v == RK_INFINITE)
+    for (; e < nn; e++) {
+      double *const be = brow + (size_t)e * 128;
+      be[0] = kind_u == RK_INFINITE ? 1.0 / dinf : 0.0; be[32] = 0.0; be[64] = 0.0;
+      be[96] = kind_v == RK_INFINITE ? 1.0 / dinf : 0.0;
+    }
+  { double *const be = brow + (size_t)e * 128; be[0] = 1.0; be[32] = 0.0; be[64] = 0.0; be[96] = 1.0; }
   for (int uv = 0; uv < 2; uv++) {
     const int kind = uv == 0 ? kind_u : kind_v;
     int k = ptrA[2 * tl + uv] - 1;
     const int r = 2 * tl + uv;
     if (kind == RK_PRESCR) {
-      val[k] = 1.0; valS[k] = 1.0;
+      val[k] = 1.0;
       const double b = uv == 0 ? bc_u[ti] : bc_v[ti];
       bb[r] = b; bS[r] = b;
     } else if (kind == RK_INFINITE) {
-      int nn = 0;
-      for (int n = 0; n < 3; n++) if (TriC[(size_t)n * nTri + ti] != 0) nn++;
-      const double d = -1.0 * (double)nn;
-      for (int n = 0; n < nn; n++) { val[k] = 1.0; valS[k] = 1.0 / d; k++; }
-      val[k] = d; valS[k] = 1.0;
+      for (int n = 0; n < nn; n++) { val[k] = 1.0; k++; }
+      val[k] = dinf;
       bb[r] = 0.0; bS[r] = 0.0;
     } else if (kind == RK_ZERO) {
-      val[k] = 1.0; valS[k] = 1.0; bb[r] = 0.0; bS[r] = 0.0;
+      val[k] = 1.0; bb[r] = 0.0; bS[r] = 0.0;
     } else {   // RK_COPY: periodic_ISMIP-HOM / infinite_SSA_icestream (:555-600)
-      val[k] = 1.0; valS[k] = 1.0;
+      val[k] = 1.0;
       const double *prev = uv == 0 ? F.u_b_prev : F.v_b_prev;
       const int slot = T.slot[ti];
       double fixed = 0.0;
@@ -254,7 +335,7 @@ int ufe_launch_assemble(cudaStream_t st, int t0, int nt, int nTri, const Assembl
                         int write_x) {
   if (nt <= 0) return UFE_OK;
   k_assemble<<<ufe_div_up(nt, 128), 128, 0, st>>>(t0, nt, nTri, A, M2, TriC, rowkind, T, bc_mask, bc_u, bc_v, F,
-                                                  S.ptr, S.val, S.valS, S.bb, S.bS, S.x, write_x);
+                                                  S.ptr, S.val, S.bell_off, S.bell_val, S.bb, S.bS, S.x, write_x);
   UFE_LAUNCH_CHECK();
   return UFE_OK;
 }

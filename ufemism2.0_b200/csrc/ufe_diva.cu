@@ -14,6 +14,7 @@ int ufe_build_operators(cudaStream_t st, const DevMesh &dm, int vi1, int vi2, in
                         DevFamily fam[3]);
 int ufe_colrange(cudaStream_t st, int nnz, const int *ind, int *jmin, int *jmax);
 int ufe_kspmv_plain(cudaStream_t st, const DevSystem &S, const double *xg, double *y, KrylovWork &kw);
+int ufe_kspmv_only(cudaStream_t st, const DevSystem &S, const double *xg, double *y, KrylovWork &kw);
 
 // ------------------------------------------------------------------------------------
 // errors, counters
@@ -319,10 +320,11 @@ extern "C" int ufe_diva_destroy(ufe_handle *h) {
   for (double *p : h->owned_ptrs) cudaFree(p);
   double *dl[] = {h->Hi, h->Hs, h->Hib, h->SL, h->fraction_gr, h->fraction_gr_b, h->Neff, h->Ti, h->phi, h->alpha_sq,
                   h->beta_sq, h->tys, h->bc_u, h->bc_v, h->bc_copy_w, h->red_partials, h->red_out, h->dm.V, h->dm.TriGC,
-                  h->dm.zeta, h->S.val, h->S.valS, h->S.bb, h->S.bS, h->S.x};
+                  h->dm.zeta, h->S.val, h->S.valS, h->S.bb, h->S.bS, h->S.x, h->S.bell_val};
   for (double *p : dl) cudaFree(p);
   int *il[] = {h->mask_gr, h->mask_fl, h->mask_land, h->bc_mask, h->bc_slot, h->bc_copy_ti, h->rowkind, h->dm.Tri,
-               h->dm.TriC, h->dm.C, h->dm.nC, h->dm.iTri, h->dm.niTri, h->dm.VBI, h->dm.TriBI, h->S.ptr, h->S.ind};
+               h->dm.TriC, h->dm.C, h->dm.nC, h->dm.iTri, h->dm.niTri, h->dm.VBI, h->dm.TriBI, h->S.ptr, h->S.ind,
+               h->S.bell_off, h->S.bell_col};
   for (int *p : il) cudaFree(p);
   for (int f = 0; f < 3; f++) {
     cudaFree(h->fam[f].ptr); cudaFree(h->fam[f].ind);
@@ -843,7 +845,7 @@ extern "C" int ufe_bench_spmv(ufe_handle *h, int32_t reps, int32_t flush_l2, dou
   for (int r = 0; r < reps; r++) {
     if (flush_l2) UFE_CUDA(cudaMemsetAsync(h->flush_buf, r & 0xff, h->flush_bytes, h->st));
     cudaEventRecord(h->ev[2], h->st);
-    UFE_TRY(ufe_kspmv_plain(h->st, S, h->kw.pg, h->kw.t, h->kw));
+    UFE_TRY(ufe_kspmv_only(h->st, S, h->kw.pg, h->kw.t, h->kw));
     cudaEventRecord(h->ev[3], h->st);
     UFE_CUDA(cudaEventSynchronize(h->ev[3]));
     float ms = 0;

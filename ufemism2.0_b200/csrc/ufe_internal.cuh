@@ -111,6 +111,16 @@ struct DevSystem {
   double *bb = nullptr, *bS = nullptr;
   double *x = nullptr;       // full-length (N) solution / SpMV input vector (global indexing)
   int jmin = 1, jmax = 0;    // column range touched by the owned rows (calc_j_node_range)
+  // Krylov-loop copy of B*A for the DIVA/SSA stiffness matrix: 2x2 (u,v) blocks per triangle
+  // pair in sliced ELL (slice = 32 block rows = one warp).  Entry e of block row s*32+l:
+  //   bell_col[(off_s+e)*32 + l]            0-based global triangle index of the block column
+  //   bell_val[(off_s+e)*128 + c*32 + l]    c = 0..3 -> a_uu, a_uv, a_vu, a_vv
+  // off_s = bell_off[s] (entries), slice width = bell_off[s+1]-bell_off[s]; padding entries
+  // point at the row's own triangle with zero values.  nullptr => CSR valS is used instead.
+  int nslices = 0;
+  long long bell_entries = 0;
+  int *bell_off = nullptr, *bell_col = nullptr;
+  double *bell_val = nullptr;
 };
 
 int ufe_spmv_launch(cudaStream_t st, int m_loc, int nnz, const int *ptr, const int *ind,
