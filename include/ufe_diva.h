@@ -94,7 +94,9 @@ enum { UFE_IDEAL_NONE = 0, UFE_IDEAL_SSA_ICESTREAM = 1, UFE_IDEAL_ISMIP_HOM_C = 
 enum { UFE_RHEO_UNIFORM = 0, UFE_RHEO_HUYBRECHTS1992 = 1 };
 enum { UFE_ENH_SEPARATE = 0, UFE_ENH_INTERP = 1 };
 enum { UFE_KRYLOV_BICGSTAB = 0, UFE_KRYLOV_GMRES = 1 };
-enum { UFE_PC_JACOBI = 0, UFE_PC_BJACOBI2 = 1 };
+/* UFE_PC_BJACOBI_LU: block Jacobi over contiguous row ranges (like PETSc's per-rank blocks) with an
+ * exact block-tridiagonal LU solve inside each block (the reference uses ILU(0) there). */
+enum { UFE_PC_JACOBI = 0, UFE_PC_BJACOBI2 = 1, UFE_PC_BJACOBI_LU = 2 };
 
 typedef struct ufe_config {
   int32_t do_include_SSADIVA_crossterms;           /* :276 */
@@ -128,6 +130,7 @@ typedef struct ufe_config {
   int32_t krylov_pc;            /* UFE_PC_*     ; reference: block-Jacobi / ILU(0)   */
   int32_t krylov_maxits;        /* PETSc default 10000 */
   int32_t krylov_guess_nonzero; /* 0 = KSP default (x0 = 0, petsc_basic.f90:99-128) */
+  int32_t krylov_pc_lu_segments;/* UFE_PC_BJACOBI_LU: blocks per GPU; 0 = automatic, 1 = exact solve */
 } ufe_config;
 
 /* ---- inputs read from type_ice_model / type_bed_roughness_model ------------------

@@ -110,6 +110,7 @@ struct ufe_handle {
   int *rowkind = nullptr;
   bool pattern_valid = false;
   KrylovWork kw;
+  PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
   // reductions for the Picard residual
   double *red_partials = nullptr, *red_out = nullptr;
   unsigned *red_counter = nullptr;
@@ -146,7 +147,7 @@ static ClosureParams make_params(const ufe_handle *h, double eps_sq_0_applied) {
 static AssemblyParams make_asm_params(const ufe_handle *h) {
   AssemblyParams A;
   A.crossterms = h->cfg.do_include_SSADIVA_crossterms;
-  A.pc = h->cfg.krylov_pc;
+  A.pc = h->cfg.krylov_pc == UFE_PC_BJACOBI_LU ? UFE_PC_BJACOBI2 : h->cfg.krylov_pc;   // scaling folded into the matrix
   for (int s = 0; s < 4; s++) { A.bc_u[s] = h->cfg.BC_u[s]; A.bc_v[s] = h->cfg.BC_v[s]; }
   A.visc_it_relax = h->cfg.visc_it_relax;
   return A;
@@ -166,7 +167,7 @@ static int validate_config(const ufe_config *c) {
   if (c->choice_ice_rheology_Glen < 0 || c->choice_ice_rheology_Glen > 1) { ufe_set_error("unknown choice_ice_rheology_Glen (code %d)!", c->choice_ice_rheology_Glen); return UFE_ERR_INVALID; }
   if (c->choice_enhancement_factor_transition < 0 || c->choice_enhancement_factor_transition > 1) { ufe_set_error("unknown choice_enhancement_factor_transition!"); return UFE_ERR_INVALID; }
   if (c->do_subgrid_friction_on_A_grid) { ufe_set_error("do_subgrid_friction_on_A_grid = .true. is not supported (needs Hs_slope and grounding-line masks)"); return UFE_ERR_INVALID; }
-  if (c->krylov_method < 0 || c->krylov_method > 1 || c->krylov_pc < 0 || c->krylov_pc > 1) { ufe_set_error("unknown krylov method / preconditioner"); return UFE_ERR_INVALID; }
+  if (c->krylov_method < 0 || c->krylov_method > 1 || c->krylov_pc < 0 || c->krylov_pc > 2) { ufe_set_error("unknown krylov method / preconditioner"); return UFE_ERR_INVALID; }
   if (c->choice_sliding_law == UFE_SLID_IDEALISED && c->choice_idealised_sliding_law == UFE_IDEAL_SSA_ICESTREAM &&
       c->Glens_flow_law_exponent != 3.0) { ufe_set_error("Schoof only derived a solution for the case of n=3!"); return UFE_ERR_INVALID; }
   return UFE_OK;
@@ -333,6 +334,7 @@ extern "C" int ufe_diva_destroy(ufe_handle *h) {
   cudaFree(h->red_counter); cudaFree(h->flush_buf);
   if (h->red_host) cudaFreeHost(h->red_host);
   ufe_krylov_free(h->kw);
+  ufe_pclu_free(h->pclu);
   for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->comm.nccl) ncclCommDestroy(h->comm.nccl);
   if (h->st) cudaStreamDestroy(h->st);
@@ -345,6 +347,7 @@ extern "C" int ufe_diva_set_config(ufe_handle *h, const ufe_config *cfg) {
   bool bc_changed = false;
   for (int s = 0; s < 4; s++) if (cfg->BC_u[s] != h->cfg.BC_u[s] || cfg->BC_v[s] != h->cfg.BC_v[s]) bc_changed = true;
   if (cfg->refgeo_idealised_ISMIP_HOM_L != h->cfg.refgeo_idealised_ISMIP_HOM_L) bc_changed = true;
+  if (cfg->krylov_pc_lu_segments != h->cfg.krylov_pc_lu_segments) { ufe_pclu_free(h->pclu); h->pclu = nullptr; }
   h->cfg = *cfg;
   h->pattern_valid = false;
   if (bc_changed) {
@@ -519,6 +522,7 @@ static VertexInputs vertex_inputs(const ufe_handle *h) {
 
 static int ensure_pattern(ufe_handle *h) {
   if (h->pattern_valid) return UFE_OK;
+  ufe_pclu_free(h->pclu); h->pclu = nullptr;
   const int nt = h->ti2 - h->ti1 + 1;
   double *x_keep = h->S.x;
   UFE_TRY(ufe_build_stiffness_pattern(h->st, h->ti1 - 1, nt, h->dm.nTri, make_asm_params(h), view_of(h->fam[2]),
@@ -554,9 +558,15 @@ static int linearised_resident(ufe_handle *h, double rtol, double abstol, int *n
   UFE_TRY(ufe_launch_assemble(h->st, h->ti1 - 1, nt, h->dm.nTri, make_asm_params(h), view_of(h->fam[2]), h->dm.TriC,
                               h->rowkind, T, h->bc_mask, h->bc_u, h->bc_v, h->F, h->S, 1));
   cudaEventRecord(h->ev[3], h->st);
+  PcLU *pc = nullptr;
+  if (h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) {       // PCSetUp: factorise the strip blocks of this iteration's matrix
+    if (!h->pclu) UFE_TRY(ufe_pclu_setup(h->st, h->S, h->cfg.krylov_pc_lu_segments, (size_t)60 << 30, &h->pclu));
+    UFE_TRY(ufe_pclu_factor(h->st, h->S, h->pclu));
+    pc = h->pclu;
+  }
   UFE_TRY(ufe_krylov_run(h->st, h->S, h->kw, h->comm, h->comm.nranks > 1 ? &h->plan_b_for_b : nullptr,
                          h->cfg.krylov_method, rtol, abstol, h->cfg.krylov_maxits, h->cfg.krylov_guess_nonzero,
-                         n_its, flags));
+                         n_its, flags, pc));
   cudaEventRecord(h->ev[4], h->st);
   UFE_CUDA(cudaEventSynchronize(h->ev[4]));
   if (ms_asm) cudaEventElapsedTime(ms_asm, h->ev[2], h->ev[3]);

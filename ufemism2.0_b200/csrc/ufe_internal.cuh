@@ -95,6 +95,7 @@ struct KrylovWork {
   KrylovScalars *sc = nullptr;
   double *gm = nullptr;   // GMRES small dense state: H(31x30), cs, sn, g, y, hcol
   KrylovScalars *sc_host = nullptr;  // pinned mirror
+  double *pctmp = nullptr, *bP = nullptr;   // explicit-preconditioner work vectors (owned length)
 };
 
 struct Comm {
@@ -132,9 +133,14 @@ void ufe_krylov_free(KrylovWork &kw);
 // solves valS * x = bS on the owned rows; x full-length global vector (x[r1-1 ..] owned).
 // halo: callback-free -- single GPU handled inline, multi-GPU through the exchange plan.
 struct HaloPlan;
+struct PcLU;     // block-Jacobi / block-tridiagonal LU preconditioner (ufe_pclu.cu); nullptr = none
+int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int segments, size_t max_bytes, PcLU **out);
+int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc);
+int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z);
+void ufe_pclu_free(PcLU *pc);
 int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm,
                    const HaloPlan *halo, int method, double rtol, double abstol, int maxits,
-                   int guess_nonzero, int *n_its, int *flags);
+                   int guess_nonzero, int *n_its, int *flags, PcLU *pc = nullptr);
 
 // halo exchange plan for a global-indexed vector partitioned into contiguous ranges
 struct HaloPlan {

@@ -286,6 +286,41 @@ int ufe_kspmv_only(cudaStream_t st, const DevSystem &S, const double *xg, double
 }
 
 // ---------------------------------------------------------------------------------
+// Explicit left preconditioner (block-Jacobi / LU, ufe_pclu.cu): the operator of the Krylov
+// loop becomes y = M^-1 (A x); the dot products the fused SpMV modes would have produced
+// are taken afterwards by k_stage_dots.
+// ---------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_stage_dots(int n, int r0, const double *__restrict__ y, const double *__restrict__ z, const double *__restrict__ xg,
+             int stage, double *partials, unsigned *counter, double *dots_local, KrylovScalars *sc, double *gm,
+             int single, double rtol, double abstol) {
+  if (sc->done) return;
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double yi = y[i];
+    if (MODE == 1) acc[0] += z[i] * yi;
+    if (MODE == 2) { acc[0] += yi * xg[r0 + i]; acc[1] += yi * yi; }
+  }
+  if (MODE == 1) { double a1[1] = {acc[0]}; finish_stage<1>(a1, stage, partials, counter, dots_local, sc, gm, single, rtol, abstol); }
+  if (MODE == 2) finish_stage<2>(acc, stage, partials, counter, dots_local, sc, gm, single, rtol, abstol);
+}
+
+template <int MODE>
+static int apply_op(cudaStream_t st, const DevSystem &S, PcLU *pc, const double *xg, double *y, const double *z,
+                    int stage, KrylovWork &kw, int single, double rtol, double abstol) {
+  if (!pc) return launch_kspmv<MODE>(st, S, xg, y, z, stage, kw, single, rtol, abstol);
+  UFE_TRY(launch_kspmv<0>(st, S, xg, kw.pctmp, nullptr, 0, kw, single, rtol, abstol));
+  UFE_TRY(ufe_pclu_apply(st, pc, kw.pctmp, y));
+  if (MODE != 0) {
+    k_stage_dots<MODE><<<UFE_RED_BLOCKS, UFE_RED_THREADS, 0, st>>>(S.m_loc, S.r1 - 1, y, z, xg, stage, kw.partials, kw.counter,
+                                                                 kw.dots_local, kw.sc, kw.gm, single, rtol, abstol);
+    UFE_LAUNCH_CHECK();
+  }
+  return UFE_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // BiCGStab vector kernels (grid-stride, fixed grid => deterministic reductions)
 // ---------------------------------------------------------------------------------
 // r = b - Ax (Ax in r on entry if have_ax), rhat = r, p = r -> pg ; x unchanged.
@@ -483,6 +518,7 @@ int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres) {
   UFE_CUDA(cudaMalloc(&kw.r, nb)); UFE_CUDA(cudaMalloc(&kw.rhat, nb));
   UFE_CUDA(cudaMalloc(&kw.v, nb)); UFE_CUDA(cudaMalloc(&kw.t, nb));
   UFE_CUDA(cudaMalloc(&kw.w, nb));
+  UFE_CUDA(cudaMalloc(&kw.pctmp, nb)); UFE_CUDA(cudaMalloc(&kw.bP, nb));
   UFE_CUDA(cudaMalloc(&kw.pg, Nb)); UFE_CUDA(cudaMalloc(&kw.sg, Nb));
   UFE_CUDA(cudaMemset(kw.pg, 0, Nb)); UFE_CUDA(cudaMemset(kw.sg, 0, Nb));
   if (gmres) UFE_CUDA(cudaMalloc(&kw.Vb, nb * (GM_RESTART + 1)));
@@ -501,7 +537,7 @@ int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres) {
 void ufe_krylov_free(KrylovWork &kw) {
   cudaFree(kw.r); cudaFree(kw.rhat); cudaFree(kw.v); cudaFree(kw.t); cudaFree(kw.w);
   cudaFree(kw.pg); cudaFree(kw.sg); cudaFree(kw.Vb); cudaFree(kw.partials); cudaFree(kw.dots_local);
-  cudaFree(kw.counter); cudaFree(kw.sc); cudaFree(kw.gm);
+  cudaFree(kw.counter); cudaFree(kw.sc); cudaFree(kw.gm); cudaFree(kw.pctmp); cudaFree(kw.bP);
   if (kw.sc_host) cudaFreeHost(kw.sc_host);
   kw = KrylovWork();
 }
@@ -523,16 +559,18 @@ static int poll(cudaStream_t st, KrylovWork &kw) {
 }
 
 static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm,
-                        const HaloPlan *halo, double rtol, double abstol, int maxits, int guess_nonzero) {
+                        const HaloPlan *halo, double rtol, double abstol, int maxits, int guess_nonzero, PcLU *pc) {
   const int n = S.m_loc, r0 = S.r1 - 1, single = comm.nranks <= 1;
   const int G = UFE_RED_BLOCKS, B = UFE_RED_THREADS;
   double *xg = S.x;
   k_sc_reset<<<1, 1, 0, st>>>(kw.sc, maxits, abstol); UFE_LAUNCH_CHECK();
   if (guess_nonzero) {
     if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, xg, 0, 1, 2));
-    UFE_TRY(launch_kspmv<0>(st, S, xg, kw.r, nullptr, 0, kw, single, rtol, abstol));
+    UFE_TRY(apply_op<0>(st, S, pc, xg, kw.r, nullptr, 0, kw, single, rtol, abstol));
   }
-  k_bicg_init<<<G, B, 0, st>>>(n, r0, S.bS, kw.r, kw.rhat, kw.pg, xg, guess_nonzero, kw.partials, kw.counter,
+  const double *bS = S.bS;
+  if (pc) { UFE_TRY(ufe_pclu_apply(st, pc, S.bS, kw.bP)); bS = kw.bP; }
+  k_bicg_init<<<G, B, 0, st>>>(n, r0, bS, kw.r, kw.rhat, kw.pg, xg, guess_nonzero, kw.partials, kw.counter,
                                kw.dots_local, kw.sc, single, rtol, abstol);
   UFE_LAUNCH_CHECK();
   UFE_TRY(allreduce_stage(st, comm, kw, ST_INIT, 2, rtol, abstol));
@@ -541,11 +579,11 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
     for (int b = 0; b < batch; b++, launched++) {
       if (launched > 0) { k_bicg_p<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.pg, kw.sc); UFE_LAUNCH_CHECK(); }
       if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.pg, 0, 1, 2));
-      UFE_TRY(launch_kspmv<1>(st, S, kw.pg, kw.v, kw.rhat, ST_A, kw, single, rtol, abstol));
+      UFE_TRY(apply_op<1>(st, S, pc, kw.pg, kw.v, kw.rhat, ST_A, kw, single, rtol, abstol));
       UFE_TRY(allreduce_stage(st, comm, kw, ST_A, 1, rtol, abstol));
       k_bicg_s<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.sc); UFE_LAUNCH_CHECK();
       if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.sg, 0, 1, 2));
-      UFE_TRY(launch_kspmv<2>(st, S, kw.sg, kw.t, nullptr, ST_B, kw, single, rtol, abstol));
+      UFE_TRY(apply_op<2>(st, S, pc, kw.sg, kw.t, nullptr, ST_B, kw, single, rtol, abstol));
       UFE_TRY(allreduce_stage(st, comm, kw, ST_B, 2, rtol, abstol));
       k_bicg_xr<<<G, B, 0, st>>>(n, r0, xg, kw.pg, kw.sg, kw.t, kw.rhat, kw.r, kw.partials, kw.counter,
                                  kw.dots_local, kw.sc, single, rtol, abstol);
@@ -560,20 +598,22 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
 }
 
 static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm, const HaloPlan *halo,
-                     double rtol, double abstol, int maxits, int guess_nonzero, bool reset) {
+                     double rtol, double abstol, int maxits, int guess_nonzero, bool reset, PcLU *pc) {
   const int n = S.m_loc, r0 = S.r1 - 1, single = comm.nranks <= 1;
   const int G = UFE_RED_BLOCKS, B = UFE_RED_THREADS;
   const long long ldv = n;
   double *xg = S.x;
   if (reset) { k_sc_reset<<<1, 1, 0, st>>>(kw.sc, maxits, abstol); UFE_LAUNCH_CHECK(); }
+  const double *bS = S.bS;
+  if (pc) { UFE_TRY(ufe_pclu_apply(st, pc, S.bS, kw.bP)); bS = kw.bP; }
   bool first = true;
   while (true) {
     const int have_ax = (!first || guess_nonzero) ? 1 : 0;
     if (have_ax) {
       if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, xg, 0, 1, 2));
-      UFE_TRY(launch_kspmv<0>(st, S, xg, kw.w, nullptr, 0, kw, single, rtol, abstol));
+      UFE_TRY(apply_op<0>(st, S, pc, xg, kw.w, nullptr, 0, kw, single, rtol, abstol));
     }
-    k_gm_resid<<<G, B, 0, st>>>(n, r0, S.bS, kw.w, xg, have_ax, (first && !guess_nonzero) ? 1 : 0, kw.partials,
+    k_gm_resid<<<G, B, 0, st>>>(n, r0, bS, kw.w, xg, have_ax, (first && !guess_nonzero) ? 1 : 0, kw.partials,
                                 kw.counter, kw.dots_local, kw.sc, kw.gm, single, rtol, abstol);
     UFE_LAUNCH_CHECK();
     UFE_TRY(allreduce_stage(st, comm, kw, ST_GM_INIT, 2, rtol, abstol));
@@ -581,7 +621,7 @@ static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const 
     for (int j = 0; j < GM_RESTART; j++) {
       k_gm_scale<<<G, B, 0, st>>>(n, r0, kw.w, kw.Vb + (size_t)j * ldv, kw.pg, kw.sc, kw.gm, j); UFE_LAUNCH_CHECK();
       if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.pg, 0, 1, 2));
-      UFE_TRY(launch_kspmv<0>(st, S, kw.pg, kw.w, nullptr, 0, kw, single, rtol, abstol));
+      UFE_TRY(apply_op<0>(st, S, pc, kw.pg, kw.w, nullptr, 0, kw, single, rtol, abstol));
       for (int i0 = 0; i0 <= j; i0 += 8) {
         const int cnt = (j + 1 - i0) < 8 ? (j + 1 - i0) : 8;
         k_gm_mdot<8><<<G, B, 0, st>>>(n, kw.Vb, ldv, kw.w, i0, cnt, kw.partials, kw.counter, kw.dots_local, kw.sc);
@@ -612,18 +652,19 @@ static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const 
 }
 
 int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm, const HaloPlan *halo,
-                   int method, double rtol, double abstol, int maxits, int guess_nonzero, int *n_its, int *flags) {
+                   int method, double rtol, double abstol, int maxits, int guess_nonzero, int *n_its, int *flags,
+                   PcLU *pc) {
   if (maxits <= 0) maxits = 10000;
   int fl = 0;
   if (method == UFE_KRYLOV_GMRES) {
     if (!kw.Vb) { ufe_set_error("GMRES workspace not allocated"); return UFE_ERR_INVALID; }
-    UFE_TRY(run_gmres(st, S, kw, comm, halo, rtol, abstol, maxits, guess_nonzero, true));
+    UFE_TRY(run_gmres(st, S, kw, comm, halo, rtol, abstol, maxits, guess_nonzero, true, pc));
   } else {
-    UFE_TRY(run_bicgstab(st, S, kw, comm, halo, rtol, abstol, maxits, guess_nonzero));
+    UFE_TRY(run_bicgstab(st, S, kw, comm, halo, rtol, abstol, maxits, guess_nonzero, pc));
     if (kw.sc_host->reason == -5 && kw.Vb) {
       // BiCGStab breakdown: continue from the current iterate with GMRES(30)
       const int its0 = kw.sc_host->its;
-      UFE_TRY(run_gmres(st, S, kw, comm, halo, rtol, abstol, maxits, 1, true));
+      UFE_TRY(run_gmres(st, S, kw, comm, halo, rtol, abstol, maxits, 1, true, pc));
       kw.sc_host->its += its0;
     }
   }

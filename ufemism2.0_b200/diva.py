@@ -27,7 +27,7 @@ from .mesh_types import Mesh
 
 PICARD_MAXIT, KRYLOV_MAXIT, KRYLOV_DIVERGED = 1, 2, 4
 KRYLOV_METHODS = {"bicgstab": 0, "gmres": 1}
-KRYLOV_PCS = {"jacobi": 0, "bjacobi2": 1}
+KRYLOV_PCS = {"jacobi": 0, "bjacobi2": 1, "bjacobi_lu": 2}
 FAMILIES = {"a_b": (0, ("map", "ddx", "ddy")), "b_a": (1, ("map", "ddx", "ddy")),
             "b_b": (2, ("ddx", "ddy", "d2dx2", "d2dxdy", "d2dy2"))}
 
@@ -68,6 +68,7 @@ def config_struct(C: Config) -> capi.ufe_config:
     s.krylov_pc = _code(KRYLOV_PCS, C.b200_krylov_pc, "b200_krylov_pc")
     s.krylov_maxits = C.b200_krylov_maxits
     s.krylov_guess_nonzero = int(C.b200_krylov_guess_nonzero)
+    s.krylov_pc_lu_segments = int(C.b200_krylov_pc_lu_segments)
     return s
 
 
