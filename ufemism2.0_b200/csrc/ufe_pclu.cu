@@ -1,37 +1,60 @@
-// Block-Jacobi preconditioner with exact (block-tridiagonal LU) sub-domain solves.
+// Block-Jacobi preconditioner with exact sub-domain solves (block cyclic reduction).
 //
-// The reference preconditions its KSP with PETSc's default block-Jacobi -- one block per
-// MPI rank = one contiguous row range = one vertical strip of the x-sorted mesh -- with
-// ILU(0) inside each block (src/UPSY/basic/petsc_basic.f90:106-119, no options set).  Here
-// the blocks are contiguous row ranges as well ("segments"), but each is solved exactly:
-// because the mesh is x-sorted, the (already Jacobi-scaled) matrix is banded, so with a dense
-// block size g >= bandwidth every segment is block tridiagonal,
-//        [ D_1 U_1           ]
-//        [ L_2 D_2 U_2       ]         S_1 = D_1,  S_k = D_k - L_k W_{k-1},
-//        [     L_3 D_3 ...   ]         W_k = S_k^-1 U_k,  G_k = S_k^-1 L_k,
-// and is factorised by block Thomas elimination with explicit inverses, so that applying the
-// preconditioner is GEMV only:
-//        c_k = S_k^-1 r_k - G_k c_{k-1}   (forward),   z_k = c_k - W_k z_{k+1}   (backward).
-// Couplings between segments are dropped (that is the block-Jacobi approximation; with one
-// segment the preconditioner is the exact inverse).  Segments are independent and are
-// processed concurrently (blockIdx.z); the chain inside a segment is sequential.
-// Inverses: in-place Gauss-Jordan without row exchanges, one launch per pivot, with static
-// pivot perturbation (the outer Krylov iteration absorbs the perturbation).
+// The reference preconditions its KSP with PETSc's default block-Jacobi -- one block per MPI
+// rank = one contiguous row range = one vertical strip of the x-sorted mesh -- with ILU(0)
+// inside each block (src/UPSY/basic/petsc_basic.f90:106-119, no options set).  Here the block
+// of a GPU is its own row range as well, but it is solved exactly.  Because the mesh is
+// x-sorted, the (already Jacobi-scaled) matrix is banded; with a dense block size
+// g >= bandwidth the local matrix is block tridiagonal with K = n_loc/g blocks,
+//        L_i x_{i-1} + D_i x_i + U_i x_{i+1} = r_i ,
+// and is factorised by block cyclic reduction: at level l the active nodes are
+// i_q = (q+1) 2^l - 1; the even positions q are eliminated, the odd ones kept,
+//   eliminated j :  Dinv_j = D_j^-1,  P_j = Dinv_j L_j,  Q_j = Dinv_j U_j
+//   kept i (a = i - 2^l, b = i + 2^l):
+//        A_i = L_i Dinv_a,  B_i = U_i Dinv_b            (kept for the solve, one slot per level)
+//        D_i <- D_i - L_i Q_a - U_i P_b,  L_i <- -L_i P_a,  U_i <- -U_i Q_b
+// so every level is a handful of batched dense launches over all its nodes (log2 K levels in
+// all), and applying the preconditioner is 2 log2 K batched GEMV launches:
+//   down:  r_i <- r_i - A_i r_a - B_i r_b        up:  x_j = Dinv_j r_j - P_j x_{j-s} - Q_j x_{j+s}.
+// With one GPU the preconditioner is the exact inverse (the Krylov loop then converges in one or
+// two steps and acts as iterative refinement); with several GPUs it is block Jacobi over the
+// ranks' strips (couplings to other ranks' columns are dropped).
+// Inverses: blocked in-place Gauss-Jordan (32-wide panels, partial pivoting inside the 32 x 32
+// pivot block, static perturbation of vanishing pivots; the Krylov iteration absorbs it).
+#include <stdlib.h>
+
 #include "ufe_internal.cuh"
 
 #define GT 64          // GEMM tile
 #define GK 16
+#define NB 32          // Gauss-Jordan panel width
+
+struct PcLevel { int s, n, nE, nK, slot0; };
 
 struct PcLU {
-  int n_loc = 0, g = 0, K = 0, P = 0, m = 0;   // rows, dense block size, blocks, segments, blocks per segment
-  double *D = nullptr, *L = nullptr, *U = nullptr, *W = nullptr, *G = nullptr;   // K * g*g each, row-major
-  double *prow = nullptr, *pcol = nullptr;      // [2][P][g] pivot row / column snapshots
-  double *c = nullptr;                          // K*g work vector
+  int n_loc = 0, g = 0, K = 0;
+  std::vector<PcLevel> lev;
+  double *D = nullptr;                       // K blocks: D_i, overwritten by Dinv_i when i is eliminated
+  double *Lc[2] = {nullptr, nullptr}, *Uc[2] = {nullptr, nullptr};   // couplings of the current level (ping-pong)
+  double *Pm = nullptr, *Qm = nullptr;       // K blocks, per eliminated node
+  double *AL = nullptr, *BL = nullptr;       // one block per kept node per level (<= K slots)
+  double *ipp = nullptr, *colbuf = nullptr;  // Gauss-Jordan scratch: [items][32*32], [items][g][32]
+  double *c = nullptr;                       // 2*K*g work vectors (rhs -> solution, staging)
   size_t bytes = 0;
 };
 
+// operand addressing for the batched kernels: item z of a level works on node
+//   node(z) = (2z + 1 + kept) * s - 1 ;   operand block = node + off   (mode 0)
+//                                                        = off + z      (mode 1, slot arrays)
+struct Opnd { const double *p; int mode, off; };
+__device__ __forceinline__ long long opnd_block(const Opnd &o, int node, int z, int K) {
+  if (o.mode == 1) return o.off + z;
+  const int b = node + o.off;
+  return (b < 0 || b >= K) ? -1 : b;
+}
+
 // ------------------------------------------------------------------------------------
-// bandwidth of the local part of the blocked sliced-ELL matrix
+// matrix -> dense block-tridiagonal storage
 // ------------------------------------------------------------------------------------
 __global__ void k_bell_bandwidth(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off,
                                  const int *__restrict__ bcol, int *bw) {
@@ -43,7 +66,7 @@ __global__ void k_bell_bandwidth(int nt_loc, int t0, int nslices, const int *__r
   if (r < nt_loc)
     for (int e = 0; e < w; e++) {
       const int c = bcol[(size_t)(off + e) * 32 + lane] - t0;
-      if (c < 0 || c >= nt_loc) continue;        // halo column: dropped by block Jacobi
+      if (c < 0 || c >= nt_loc) continue;        // another rank's column: dropped by block Jacobi
       const int d = c > r ? c - r : r - c;
       b = max(b, 2 * d + 1);
     }
@@ -51,9 +74,8 @@ __global__ void k_bell_bandwidth(int nt_loc, int t0, int nslices, const int *__r
   if (lane == 0) atomicMax(bw, b);
 }
 
-// scatter the scaled matrix into the dense block-tridiagonal storage (zeroed beforehand)
 __global__ void k_bell_to_blocks(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off,
-                                 const int *__restrict__ bcol, const double *__restrict__ bval, int g, int m, int K,
+                                 const int *__restrict__ bcol, const double *__restrict__ bval, int g,
                                  double *__restrict__ D, double *__restrict__ L, double *__restrict__ U) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= nslices) return;
@@ -67,23 +89,20 @@ __global__ void k_bell_to_blocks(int nt_loc, int t0, int nslices, const int *__r
     const double *p = bval + (size_t)(off + e) * 128 + lane;
     const double a[4] = {p[0], p[32], p[64], p[96]};
     for (int q = 0; q < 4; q++) {
-      if (a[q] == 0.0) continue;
+      if (a[q] == 0.0) continue;                 // also skips the zero padding entries of the slice
       const int r = 2 * t + (q >> 1), c = 2 * ct + (q & 1);
       const int kr = r / g, kc = c / g;
-      if (kr / m != kc / m) continue;            // different segments: dropped
       const size_t o = (size_t)kr * gg + (size_t)(r - kr * g) * g + (c - kc * g);
-      // atomicAdd: padding entries of a row point at the row's own triangle and carry zeros
-      // (skipped above); duplicate columns do not occur, so this is a plain store in effect
-      if (kc == kr) atomicAdd(D + o, a[q]);
-      else if (kc == kr - 1) atomicAdd(L + o, a[q]);
-      else if (kc == kr + 1) atomicAdd(U + o, a[q]);
+      if (kc == kr) D[o] = a[q];
+      else if (kc == kr - 1) L[o] = a[q];
+      else if (kc == kr + 1) U[o] = a[q];
     }
   }
 }
 
-// the same from a scaled CSR matrix (generic L0 path)
+// the same from a scaled CSR matrix (generic L0 path); D == nullptr: bandwidth only
 __global__ void k_csr_to_blocks(int m_loc, int r0, const int *__restrict__ ptr, const int *__restrict__ ind,
-                                const double *__restrict__ val, int g, int m, double *__restrict__ D,
+                                const double *__restrict__ val, int g, double *__restrict__ D,
                                 double *__restrict__ L, double *__restrict__ U, int *bw) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m_loc) return;
@@ -95,7 +114,6 @@ __global__ void k_csr_to_blocks(int m_loc, int r0, const int *__restrict__ ptr, 
     b = max(b, c > r ? c - r : r - c);
     if (!D) continue;
     const int kr = r / g, kc = c / g;
-    if (kr / m != kc / m) continue;
     const size_t o = (size_t)kr * gg + (size_t)(r - kr * g) * g + (c - kc * g);
     if (kc == kr) atomicAdd(D + o, val[k]);
     else if (kc == kr - 1) atomicAdd(L + o, val[k]);
@@ -104,7 +122,6 @@ __global__ void k_csr_to_blocks(int m_loc, int r0, const int *__restrict__ ptr, 
   if (bw) atomicMax(bw, b);
 }
 
-// identity on the padding rows of the last block
 __global__ void k_pad_identity(int n_loc, int g, int K, double *__restrict__ D) {
   const int i = n_loc + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * g) return;
@@ -113,27 +130,27 @@ __global__ void k_pad_identity(int n_loc, int g, int K, double *__restrict__ D) 
 }
 
 // ------------------------------------------------------------------------------------
-// batched dense GEMM on g x g row-major blocks: C = beta*C + alpha*A*B, one (A,B,C) triple
-// per segment (blockIdx.z); block index inside the arrays = seg*m + step (+ offsets).
-// 64x64 tile, 256 threads, 4x4 register micro-tile.  g is a multiple of 64.
+// batched dense GEMM on g x g row-major blocks: C = beta*C + alpha*A*B for every item of a
+// level (blockIdx.z).  64x64 tile, 256 threads, 4x4 register micro-tile; g multiple of 64.
+// Items whose A or B operand does not exist (no neighbour on that side) are skipped.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_block_gemm(int g, int m, int K, int step, int offA, int offB, int offC, const double *__restrict__ A,
-             const double *__restrict__ B, double *__restrict__ C, double alpha, double beta) {
-  const int seg = blockIdx.z, kb = seg * m + step;
-  if (kb >= K || kb + offA < 0 || kb + offB < 0) return;
+k_bgemm(int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha, double beta) {
+  const int z = blockIdx.z, node = (2 * z + 1 + kept) * s - 1;
+  const long long ia = opnd_block(A, node, z, K), ib = opnd_block(B, node, z, K), ic = opnd_block(C, node, z, K);
+  if (ia < 0 || ib < 0 || ic < 0) return;
   const size_t gg = (size_t)g * g;
-  const double *Ab = A + (size_t)(kb + offA) * gg, *Bb = B + (size_t)(kb + offB) * gg;
-  double *Cb = C + (size_t)(kb + offC) * gg;
+  const double *Ab = A.p + ia * gg, *Bb = B.p + ib * gg;
+  double *Cb = const_cast<double *>(C.p) + ic * gg;
   __shared__ double sA[GK][GT + 1], sB[GK][GT + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
   double acc[4][4] = {};
   for (int k0 = 0; k0 < g; k0 += GK) {
     for (int q = threadIdx.x; q < GT * GK; q += 256) {
-      const int ii = q / GK, kk = q % GK;                 // A tile: rows i0.., cols k0..
+      const int ii = q / GK, kk = q % GK;
       sA[kk][ii] = Ab[(size_t)(i0 + ii) * g + k0 + kk];
-      const int k2 = q / GT, jj = q % GT;                 // B tile: rows k0.., cols j0..
+      const int k2 = q / GT, jj = q % GT;
       sB[k2][jj] = Bb[(size_t)(k0 + k2) * g + j0 + jj];
     }
     __syncthreads();
@@ -158,70 +175,185 @@ k_block_gemm(int g, int m, int K, int step, int offA, int offB, int offC, const 
     }
 }
 
-// ------------------------------------------------------------------------------------
-// in-place Gauss-Jordan inversion of the diagonal block of chain step `step` in every segment
-// ------------------------------------------------------------------------------------
-__global__ void k_gj_init(int g, int m, int K, int step, const double *__restrict__ D, double *__restrict__ prow,
-                          double *__restrict__ pcol) {
-  const int seg = blockIdx.z, kb = seg * m + step;
-  if (kb >= K) return;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g) return;
-  const double *Db = D + (size_t)kb * g * g;
-  prow[(size_t)seg * g + j] = Db[j];                      // parity 0
-  pcol[(size_t)seg * g + j] = Db[(size_t)j * g];
-}
-
-__global__ void __launch_bounds__(256)
-k_gj_step(int g, int m, int K, int P, int step, int p, double *__restrict__ D, double *__restrict__ prow,
-          double *__restrict__ pcol) {
-  const int seg = blockIdx.z, kb = seg * m + step;
-  if (kb >= K) return;
-  const int j = blockIdx.x * 32 + (threadIdx.x & 31), i = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int par = p & 1;
-  const double *pr = prow + ((size_t)par * P + seg) * g, *pc = pcol + ((size_t)par * P + seg) * g;
-  double *npr = prow + ((size_t)(par ^ 1) * P + seg) * g, *npc = pcol + ((size_t)(par ^ 1) * P + seg) * g;
-  double piv = pr[p];
-  // static pivoting: the scaled matrix has entries of order one
-  if (fabs(piv) < 1e-10) piv = piv < 0.0 ? -1e-10 : 1e-10;
-  const double d = 1.0 / piv;
-  double *a = D + (size_t)kb * g * g + (size_t)i * g + j;
-  double v;
-  if (i == p) v = (j == p) ? d : pr[j] * d;
-  else if (j == p) v = -pc[i] * d;
-  else v = *a - pc[i] * (pr[j] * d);
-  *a = v;
-  if (i == p + 1) npr[j] = v;
-  if (j == p + 1) npc[i] = v;
+// zero the blocks of a level's items (for outputs whose producing GEMM may be skipped)
+__global__ void k_bzero(int g, int K, int s, int kept, Opnd C) {
+  const int z = blockIdx.z, node = (2 * z + 1 + kept) * s - 1;
+  const long long ic = opnd_block(C, node, z, K);
+  if (ic < 0) return;
+  double *Cb = const_cast<double *>(C.p) + ic * (size_t)g * g;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)g * g; i += (size_t)gridDim.x * blockDim.x) Cb[i] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------
-// apply: c_k = Sinv_k r_k (all blocks at once), then the two chains
+// Blocked in-place Gauss-Jordan inversion of D_j for all eliminated nodes of a level.
+// For pivot block P:  Ipp = inv(A_PP);  A_PJ <- Ipp A_PJ (J != P);  A_IJ <- A_IJ - A_IP A_PJ
+// (I,J != P);  A_IP <- -A_IP Ipp;  A_PP <- Ipp.
 // ------------------------------------------------------------------------------------
-// y_k (+)= sign * M_k x_{k+xoff}; one warp per row; blocks addressed as seg*m+step or, if
-// step < 0, every block (blockIdx.z = block).
+__global__ void __launch_bounds__(1024)
+k_gjb_pivot(int g, int s, int b, const double *__restrict__ D, double *__restrict__ ipp) {
+  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
+  __shared__ double S[NB][NB + 1], I2[NB][NB + 1];
+  __shared__ int piv_row;
+  const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
+  const double *A = D + (size_t)node * g * g + (size_t)(b * NB) * g + b * NB;
+  S[i][j] = A[(size_t)i * g + j];
+  I2[i][j] = (i == j) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int p = 0; p < NB; p++) {
+    if (i == 0) {                       // warp 0: arg max |S[r][p]|, r >= p
+      double v = (j >= p) ? fabs(S[j][p]) : -1.0;
+      int r = j;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int r2 = __shfl_xor_sync(0xffffffffu, r, o);
+        if (v2 > v || (v2 == v && r2 < r)) { v = v2; r = r2; }
+      }
+      if (j == 0) piv_row = r;
+    }
+    __syncthreads();
+    const int pr = piv_row;
+    const bool sw = pr != p && (i == p || i == pr);  // swap rows p <-> pr: read, barrier, write
+    double a = 0.0, c = 0.0;
+    if (sw) { const int other = (i == p) ? pr : p; a = S[other][j]; c = I2[other][j]; }
+    __syncthreads();
+    if (sw) { S[i][j] = a; I2[i][j] = c; }
+    __syncthreads();
+    double piv = S[p][p];
+    if (fabs(piv) < 1e-13) piv = piv < 0.0 ? -1e-13 : 1e-13;      // static perturbation
+    const double d = 1.0 / piv;
+    const double f = S[i][p];
+    const double sp = S[p][j] * d, ip = I2[p][j] * d;
+    __syncthreads();
+    if (i == p) { S[i][j] = sp; I2[i][j] = ip; }
+    else { S[i][j] -= f * sp; I2[i][j] -= f * ip; }
+    __syncthreads();
+  }
+  ipp[(size_t)z * NB * NB + i * NB + j] = I2[i][j];
+}
+
+// y = 0: row panel tiles (J = blockIdx.x);  y = 1: column panel tiles (I = blockIdx.x)
+__global__ void __launch_bounds__(1024)
+k_gjb_panel(int g, int s, int b, double *__restrict__ D, const double *__restrict__ ipp, double *__restrict__ colbuf) {
+  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
+  __shared__ double X[NB][NB + 1], Ip[NB][NB + 1];
+  const int j = threadIdx.x & 31, i = threadIdx.x >> 5, q = blockIdx.x;
+  double *A = D + (size_t)node * g * g;
+  Ip[i][j] = ipp[(size_t)z * NB * NB + i * NB + j];
+  if (blockIdx.y == 0) {
+    double *T = A + (size_t)(b * NB) * g + q * NB;             // tile (P, J=q)
+    if (q == b) { T[(size_t)i * g + j] = Ip[i][j]; return; }
+    X[i][j] = T[(size_t)i * g + j];
+    __syncthreads();
+    double sum = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < NB; k++) sum += Ip[i][k] * X[k][j];
+    T[(size_t)i * g + j] = sum;
+  } else {
+    if (q == b) return;
+    double *T = A + (size_t)(q * NB) * g + b * NB;             // tile (I=q, P)
+    X[i][j] = T[(size_t)i * g + j];
+    colbuf[((size_t)z * g + q * NB + i) * NB + j] = X[i][j];   // old A_IP for the trailing update
+    __syncthreads();
+    double sum = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < NB; k++) sum += X[i][k] * Ip[k][j];
+    T[(size_t)i * g + j] = -sum;
+  }
+}
+
+// trailing update, 64 x 64 tile per CTA (256 threads, 4 x 4 micro-tile), inner dimension 32
 __global__ void __launch_bounds__(256)
-k_block_gemv(int g, int m, int K, int step, int xoff, const double *__restrict__ M, const double *__restrict__ x,
-             int x_len, double *__restrict__ y, int accumulate) {
-  const int kb = step < 0 ? blockIdx.z : blockIdx.z * m + step;
-  if (kb >= K || kb + xoff < 0 || kb + xoff >= K || (step >= 0 && (kb + xoff) / m != kb / m)) return;
+k_gjb_update(int g, int s, int b, double *__restrict__ D, const double *__restrict__ colbuf) {
+  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
+  __shared__ double Cb[GT][NB + 1], R[NB][GT + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+  double *A = D + (size_t)node * g * g;
+  for (int q = threadIdx.x; q < GT * NB; q += 256) {
+    const int ii = q / NB, kk = q % NB;
+    Cb[ii][kk] = ((i0 + ii) / NB == b) ? 0.0 : colbuf[((size_t)z * g + i0 + ii) * NB + kk];
+    const int k2 = q / GT, jj = q % GT;
+    R[k2][jj] = A[(size_t)(b * NB + k2) * g + j0 + jj];
+  }
+  __syncthreads();
+  double acc[4][4] = {};
+#pragma unroll
+  for (int kk = 0; kk < NB; kk++) {
+    double a[4], r[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { a[q] = Cb[ty * 4 + q][kk]; r[q] = R[kk][tx * 4 + q]; }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[p][q] += a[p] * r[q];
+  }
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int i = i0 + ty * 4 + p;
+    if (i / NB == b) continue;                 // pivot rows were handled by the panel kernel
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int j = j0 + tx * 4 + q;
+      if (j / NB == b) continue;               // pivot columns likewise
+      A[(size_t)i * g + j] -= acc[p][q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// solve kernels: one warp per row of a g x g block
+// ------------------------------------------------------------------------------------
+// down sweep, kept nodes:  r_i <- r_i - A_i r_{i-s} - B_i r_{i+s}
+__global__ void __launch_bounds__(256)
+k_bcr_down(int g, int K, int s, int slot0, const double *__restrict__ AL, const double *__restrict__ BL,
+           double *__restrict__ c) {
+  const int z = blockIdx.z, node = (2 * z + 2) * s - 1;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= g) return;
-  const double *Mr = M + (size_t)kb * g * g + (size_t)row * g;
-  const size_t xb = (size_t)(kb + xoff) * g;
-  double s = 0.0;
+  const size_t mo = (size_t)(slot0 + z) * g * g + (size_t)row * g;
+  const double *xa = c + (size_t)(node - s) * g;
+  const bool hasb = node + s < K;
+  const double *xb = c + (size_t)(hasb ? node + s : node) * g;
+  double sum = 0.0;
   for (int j = lane; j < g; j += 32) {
-    const size_t xi = xb + j;
-    s += Mr[j] * (xi < (size_t)x_len ? x[xi] : 0.0);
+    sum += AL[mo + j] * xa[j];
+    if (hasb) sum += BL[mo + j] * xb[j];
   }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0) {
-    double *yo = y + (size_t)kb * g + row;
-    *yo = accumulate ? *yo - s : s;
-  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+  if (lane == 0) c[(size_t)node * g + row] -= sum;
 }
 
-__global__ void k_copy_out(int n, const double *__restrict__ c, double *__restrict__ z) {
+// up sweep, eliminated nodes:  x_j = Dinv_j r_j - P_j x_{j-s} - Q_j x_{j+s}   (out of place: xo)
+__global__ void __launch_bounds__(256)
+k_bcr_up(int g, int K, int s, const double *__restrict__ D, const double *__restrict__ Pm,
+         const double *__restrict__ Qm, const double *__restrict__ c, double *__restrict__ xo) {
+  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= g) return;
+  const size_t mo = (size_t)node * g * g + (size_t)row * g;
+  const bool hasa = node - s >= 0, hasb = node + s < K;
+  const double *r = c + (size_t)node * g, *xa = c + (size_t)(hasa ? node - s : node) * g,
+               *xb = c + (size_t)(hasb ? node + s : node) * g;
+  double sum = 0.0;
+  for (int j = lane; j < g; j += 32) {
+    sum += D[mo + j] * r[j];
+    if (hasa) sum -= Pm[mo + j] * xa[j];
+    if (hasb) sum -= Qm[mo + j] * xb[j];
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+  if (lane == 0) xo[(size_t)node * g + row] = sum;
+}
+
+__global__ void k_vec_in(int n, int total, const double *__restrict__ r, double *__restrict__ c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) c[i] = i < n ? r[i] : 0.0;
+}
+__global__ void k_vec_level(int g, int s, const double *__restrict__ src, double *__restrict__ dst) {
+  const int node = (2 * blockIdx.z + 1) * s - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g) dst[(size_t)node * g + i] = src[(size_t)node * g + i];
+}
+__global__ void k_vec_out(int n, const double *__restrict__ c, double *__restrict__ z) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) z[i] = c[i];
 }
@@ -231,22 +363,21 @@ __global__ void k_copy_out(int n, const double *__restrict__ c, double *__restri
 // ------------------------------------------------------------------------------------
 void ufe_pclu_free(PcLU *pc) {
   if (!pc) return;
-  cudaFree(pc->D); cudaFree(pc->L); cudaFree(pc->U); cudaFree(pc->W); cudaFree(pc->G);
-  cudaFree(pc->prow); cudaFree(pc->pcol); cudaFree(pc->c);
+  cudaFree(pc->D); cudaFree(pc->Lc[0]); cudaFree(pc->Lc[1]); cudaFree(pc->Uc[0]); cudaFree(pc->Uc[1]);
+  cudaFree(pc->Pm); cudaFree(pc->Qm); cudaFree(pc->AL); cudaFree(pc->BL);
+  cudaFree(pc->ipp); cudaFree(pc->colbuf); cudaFree(pc->c);
   delete pc;
 }
 
-// segments: requested number of independent segments (0 = automatic); max_bytes: memory budget
-int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int segments, size_t max_bytes, PcLU **out) {
+int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int /*segments: reserved*/, size_t max_bytes, PcLU **out) {
   *out = nullptr;
   int *d_bw = nullptr, bw = 0;
   UFE_CUDA(cudaMalloc(&d_bw, sizeof(int)));
   UFE_CUDA(cudaMemsetAsync(d_bw, 0, sizeof(int), st));
-  if (S.bell_val) {
+  if (S.bell_val)
     k_bell_bandwidth<<<ufe_div_up((long long)S.nslices * 32, 256), 256, 0, st>>>(S.m_loc / 2, (S.r1 - 1) / 2, S.nslices, S.bell_off, S.bell_col, d_bw);
-  } else {
-    k_csr_to_blocks<<<ufe_div_up(S.m_loc, 256), 256, 0, st>>>(S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, 1, 1, nullptr, nullptr, nullptr, d_bw);
-  }
+  else
+    k_csr_to_blocks<<<ufe_div_up(S.m_loc, 256), 256, 0, st>>>(S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, 1, nullptr, nullptr, nullptr, d_bw);
   UFE_LAUNCH_CHECK();
   UFE_CUDA(cudaMemcpyAsync(&bw, d_bw, sizeof(int), cudaMemcpyDeviceToHost, st));
   UFE_CUDA(cudaStreamSynchronize(st));
@@ -259,75 +390,106 @@ int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int segments, size_t max
   pc->g = g;
   pc->K = (S.m_loc + g - 1) / g;
   if (pc->K < 1) pc->K = 1;
-  int P = segments;
-  if (P <= 0) P = pc->K <= 16 ? 1 : (pc->K + 15) / 16;       // automatic: chains of <= 16 blocks
-  if (P > pc->K) P = pc->K;
-  pc->m = (pc->K + P - 1) / P;
-  pc->P = (pc->K + pc->m - 1) / pc->m;
+  int slots = 0, maxE = 0;
+  for (int s = 1;; s *= 2) {
+    PcLevel lv;
+    lv.s = s; lv.n = pc->K / s; lv.nE = (lv.n + 1) / 2; lv.nK = lv.n / 2; lv.slot0 = slots;
+    if (lv.n < 1) break;
+    slots += lv.nK;
+    if (lv.nE > maxE) maxE = lv.nE;
+    pc->lev.push_back(lv);
+    if (lv.n == 1) break;
+  }
   const size_t gg = (size_t)g * g, blk = gg * pc->K * sizeof(double);
-  pc->bytes = 5 * blk;
+  const size_t slot_bytes = gg * (slots > 0 ? slots : 1) * sizeof(double);
+  pc->bytes = 7 * blk + 2 * slot_bytes;
   if (pc->bytes > max_bytes) {
     ufe_set_error("bjacobi_lu preconditioner needs %.1f GB (bandwidth %d -> dense block %d, %d blocks) which exceeds the %.1f GB budget; "
                   "use 'bjacobi2' or 'jacobi' for this mesh", pc->bytes / 1e9, bw, g, pc->K, max_bytes / 1e9);
     delete pc;
     return UFE_ERR_INVALID;
   }
-  UFE_CUDA(cudaMalloc(&pc->D, blk)); UFE_CUDA(cudaMalloc(&pc->L, blk)); UFE_CUDA(cudaMalloc(&pc->U, blk));
-  UFE_CUDA(cudaMalloc(&pc->W, blk)); UFE_CUDA(cudaMalloc(&pc->G, blk));
-  UFE_CUDA(cudaMalloc(&pc->prow, sizeof(double) * 2 * pc->P * g));
-  UFE_CUDA(cudaMalloc(&pc->pcol, sizeof(double) * 2 * pc->P * g));
-  UFE_CUDA(cudaMalloc(&pc->c, sizeof(double) * (size_t)pc->K * g));
+  UFE_CUDA(cudaMalloc(&pc->D, blk));
+  for (int q = 0; q < 2; q++) { UFE_CUDA(cudaMalloc(&pc->Lc[q], blk)); UFE_CUDA(cudaMalloc(&pc->Uc[q], blk)); }
+  UFE_CUDA(cudaMalloc(&pc->Pm, blk)); UFE_CUDA(cudaMalloc(&pc->Qm, blk));
+  UFE_CUDA(cudaMalloc(&pc->AL, slot_bytes));
+  UFE_CUDA(cudaMalloc(&pc->BL, slot_bytes));
+  UFE_CUDA(cudaMalloc(&pc->ipp, sizeof(double) * (size_t)maxE * NB * NB));
+  UFE_CUDA(cudaMalloc(&pc->colbuf, sizeof(double) * (size_t)maxE * g * NB));
+  UFE_CUDA(cudaMalloc(&pc->c, sizeof(double) * (size_t)pc->K * g * 2));
   *out = pc;
   return UFE_OK;
 }
 
 int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
-  const int g = pc->g, m = pc->m, K = pc->K, P = pc->P;
+  const int g = pc->g, K = pc->K;
   const size_t blk = (size_t)g * g * K * sizeof(double);
   UFE_CUDA(cudaMemsetAsync(pc->D, 0, blk, st));
-  UFE_CUDA(cudaMemsetAsync(pc->L, 0, blk, st));
-  UFE_CUDA(cudaMemsetAsync(pc->U, 0, blk, st));
-  if (S.bell_val) {
+  UFE_CUDA(cudaMemsetAsync(pc->Lc[0], 0, blk, st));
+  UFE_CUDA(cudaMemsetAsync(pc->Uc[0], 0, blk, st));
+  if (S.bell_val)
     k_bell_to_blocks<<<ufe_div_up((long long)S.nslices * 32, 256), 256, 0, st>>>(S.m_loc / 2, (S.r1 - 1) / 2, S.nslices, S.bell_off, S.bell_col,
-                                                                                 S.bell_val, g, m, K, pc->D, pc->L, pc->U);
-  } else {
-    k_csr_to_blocks<<<ufe_div_up(S.m_loc, 256), 256, 0, st>>>(S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, g, m, pc->D, pc->L, pc->U, nullptr);
-  }
+                                                                                 S.bell_val, g, pc->D, pc->Lc[0], pc->Uc[0]);
+  else
+    k_csr_to_blocks<<<ufe_div_up(S.m_loc, 256), 256, 0, st>>>(S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, g, pc->D, pc->Lc[0], pc->Uc[0], nullptr);
   UFE_LAUNCH_CHECK();
   if (K * g > pc->n_loc) { k_pad_identity<<<ufe_div_up(K * g - pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, g, K, pc->D); UFE_LAUNCH_CHECK(); }
-  const dim3 ggrid(g / GT, g / GT, P), jgrid(g / 32, g / 8, P);
-  for (int step = 0; step < m; step++) {
-    if (step > 0) {     // S_k = D_k - L_k W_{k-1}
-      k_block_gemm<<<ggrid, 256, 0, st>>>(g, m, K, step, 0, -1, 0, pc->L, pc->W, pc->D, -1.0, 1.0);
-      UFE_LAUNCH_CHECK();
+  const int nbk = g / NB, nt = g / GT;
+  int cur = 0;
+  for (const PcLevel &lv : pc->lev) {
+    const int s = lv.s;
+    double *L = pc->Lc[cur], *U = pc->Uc[cur], *L2 = pc->Lc[cur ^ 1], *U2 = pc->Uc[cur ^ 1];
+    // eliminated nodes: Dinv (in place), P = Dinv L, Q = Dinv U
+    for (int b = 0; b < nbk; b++) {
+      k_gjb_pivot<<<dim3(1, 1, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp);
+      k_gjb_panel<<<dim3(nbk, 2, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp, pc->colbuf);
+      k_gjb_update<<<dim3(nt, nt, lv.nE), 256, 0, st>>>(g, s, b, pc->D, pc->colbuf);
     }
-    k_gj_init<<<dim3(ufe_div_up(g, 256), 1, P), 256, 0, st>>>(g, m, K, step, pc->D, pc->prow, pc->pcol);
-    UFE_LAUNCH_CHECK();
-    for (int p = 0; p < g; p++) k_gj_step<<<jgrid, 256, 0, st>>>(g, m, K, P, step, p, pc->D, pc->prow, pc->pcol);
-    g_launch_count += g;
-    if (cudaGetLastError() != cudaSuccess) { ufe_set_error("Gauss-Jordan launch failed"); return UFE_ERR_CUDA; }
-    // W_k = Sinv_k U_k ; G_k = Sinv_k L_k
-    k_block_gemm<<<ggrid, 256, 0, st>>>(g, m, K, step, 0, 0, 0, pc->D, pc->U, pc->W, 1.0, 0.0);
-    UFE_LAUNCH_CHECK();
-    if (step > 0) { k_block_gemm<<<ggrid, 256, 0, st>>>(g, m, K, step, 0, 0, 0, pc->D, pc->L, pc->G, 1.0, 0.0); UFE_LAUNCH_CHECK(); }
+    g_launch_count += 3 * nbk;
+    const dim3 gE(nt, nt, lv.nE), gK(nt, nt, lv.nK > 0 ? lv.nK : 1);
+    const Opnd Dn{pc->D, 0, 0}, Ln{L, 0, 0}, Un{U, 0, 0}, Pn{pc->Pm, 0, 0}, Qn{pc->Qm, 0, 0};
+    k_bgemm<<<gE, 256, 0, st>>>(g, K, s, 0, Dn, Ln, Pn, 1.0, 0.0);
+    k_bgemm<<<gE, 256, 0, st>>>(g, K, s, 0, Dn, Un, Qn, 1.0, 0.0);
+    g_launch_count += 2;
+    if (lv.nK > 0) {
+      const Opnd Da{pc->D, 0, -s}, Db{pc->D, 0, s}, Pa{pc->Pm, 0, -s}, Pb{pc->Pm, 0, s}, Qa{pc->Qm, 0, -s}, Qb{pc->Qm, 0, s};
+      const Opnd As{pc->AL, 1, lv.slot0}, Bs{pc->BL, 1, lv.slot0}, L2n{L2, 0, 0}, U2n{U2, 0, 0};
+      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Ln, Da, As, 1.0, 0.0);        // A_i = L_i Dinv_a
+      k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, Bs);          // right neighbour may not exist
+      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Un, Db, Bs, 1.0, 0.0);        // B_i = U_i Dinv_b
+      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Ln, Qa, Dn, -1.0, 1.0);       // D_i -= L_i Q_a
+      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Un, Pb, Dn, -1.0, 1.0);       // D_i -= U_i P_b
+      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Ln, Pa, L2n, -1.0, 0.0);      // L_i' = -L_i P_a
+      k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, U2n);
+      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Un, Qb, U2n, -1.0, 0.0);      // U_i' = -U_i Q_b
+      g_launch_count += 8;
+    }
+    if (cudaGetLastError() != cudaSuccess) { ufe_set_error("bjacobi_lu factorisation launch failed"); return UFE_ERR_CUDA; }
+    cur ^= 1;
   }
   return UFE_OK;
 }
 
 // z = M^-1 r  (r, z owned-length vectors; may alias)
 int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z) {
-  const int g = pc->g, m = pc->m, K = pc->K, P = pc->P;
-  k_block_gemv<<<dim3(g / 8, 1, K), 256, 0, st>>>(g, m, K, -1, 0, pc->D, r, pc->n_loc, pc->c, 0);
+  const int g = pc->g, K = pc->K, total = K * g;
+  double *c = pc->c, *x = pc->c + total;
+  k_vec_in<<<ufe_div_up(total, 256), 256, 0, st>>>(pc->n_loc, total, r, c);
   UFE_LAUNCH_CHECK();
-  for (int step = 1; step < m; step++) {       // c_k -= G_k c_{k-1}
-    k_block_gemv<<<dim3(g / 8, 1, P), 256, 0, st>>>(g, m, K, step, -1, pc->G, pc->c, K * g, pc->c, 1);
+  for (const PcLevel &lv : pc->lev) {
+    if (lv.nK == 0) continue;
+    k_bcr_down<<<dim3(g / 8, 1, lv.nK), 256, 0, st>>>(g, K, lv.s, lv.slot0, pc->AL, pc->BL, c);
     UFE_LAUNCH_CHECK();
   }
-  for (int step = m - 2; step >= 0; step--) {  // z_k = c_k - W_k z_{k+1}
-    k_block_gemv<<<dim3(g / 8, 1, P), 256, 0, st>>>(g, m, K, step, 1, pc->W, pc->c, K * g, pc->c, 1);
-    UFE_LAUNCH_CHECK();
+  for (int l = (int)pc->lev.size() - 1; l >= 0; l--) {
+    const PcLevel &lv = pc->lev[l];
+    // x_j from r_j and the already solved neighbours (c is overwritten level by level)
+    k_bcr_up<<<dim3(g / 8, 1, lv.nE), 256, 0, st>>>(g, K, lv.s, pc->D, pc->Pm, pc->Qm, c, x);
+    k_vec_level<<<dim3(ufe_div_up(g, 256), 1, lv.nE), 256, 0, st>>>(g, lv.s, x, c);
+    g_launch_count += 2;
   }
-  k_copy_out<<<ufe_div_up(pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, pc->c, z);
+  if (cudaGetLastError() != cudaSuccess) { ufe_set_error("bjacobi_lu apply launch failed"); return UFE_ERR_CUDA; }
+  k_vec_out<<<ufe_div_up(pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, c, z);
   UFE_LAUNCH_CHECK();
   return UFE_OK;
 }
