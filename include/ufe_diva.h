@@ -96,7 +96,8 @@ enum { UFE_ENH_SEPARATE = 0, UFE_ENH_INTERP = 1 };
 enum { UFE_KRYLOV_BICGSTAB = 0, UFE_KRYLOV_GMRES = 1 };
 /* UFE_PC_BJACOBI_LU: block Jacobi over contiguous row ranges (like PETSc's per-rank blocks) with an
  * exact block-tridiagonal LU solve inside each block (the reference uses ILU(0) there). */
-enum { UFE_PC_JACOBI = 0, UFE_PC_BJACOBI2 = 1, UFE_PC_BJACOBI_LU = 2 };
+enum { UFE_PC_JACOBI = 0, UFE_PC_BJACOBI2 = 1, UFE_PC_BJACOBI_LU = 2,
+       UFE_PC_AUTO = 3 /* BJACOBI_LU when its dense blocks fit the memory budget, else BJACOBI2 */ };
 
 typedef struct ufe_config {
   int32_t do_include_SSADIVA_crossterms;           /* :276 */
@@ -130,7 +131,7 @@ typedef struct ufe_config {
   int32_t krylov_pc;            /* UFE_PC_*     ; reference: block-Jacobi / ILU(0)   */
   int32_t krylov_maxits;        /* PETSc default 10000 */
   int32_t krylov_guess_nonzero; /* 0 = KSP default (x0 = 0, petsc_basic.f90:99-128) */
-  int32_t krylov_pc_lu_segments;/* UFE_PC_BJACOBI_LU: blocks per GPU; 0 = automatic, 1 = exact solve */
+  int32_t krylov_pc_lu_segments;/* reserved (UFE_PC_BJACOBI_LU uses one block per GPU, solved exactly) */
 } ufe_config;
 
 /* ---- inputs read from type_ice_model / type_bed_roughness_model ------------------
@@ -178,6 +179,8 @@ typedef struct ufe_solve_info {
   /* device-time split, milliseconds (CUDA events) */
   double ms_total, ms_closures, ms_assembly, ms_krylov, ms_h2d, ms_d2h;
   int64_t gpu_launches;            /* kernels launched by this library during the call */
+  int32_t krylov_pc_used;          /* UFE_PC_* actually applied (resolves UFE_PC_AUTO) */
+  int32_t reserved;
 } ufe_solve_info;
 
 /* multi-GPU communicator description: one process per GPU, NCCL underneath.

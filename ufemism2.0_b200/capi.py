@@ -84,7 +84,8 @@ class ufe_solve_info(ct.Structure):
     _fields_ = [("n_visc_its", c_i32), ("n_Axb_its", c_i32), ("flags", c_i32), ("L2_uv", c_f64),
                 ("visc_it_relax_applied", c_f64), ("Glens_flow_law_epsilon_sq_0_applied", c_f64),
                 ("ms_total", c_f64), ("ms_closures", c_f64), ("ms_assembly", c_f64),
-                ("ms_krylov", c_f64), ("ms_h2d", c_f64), ("ms_d2h", c_f64), ("gpu_launches", ct.c_int64)]
+                ("ms_krylov", c_f64), ("ms_h2d", c_f64), ("ms_d2h", c_f64), ("gpu_launches", ct.c_int64),
+                ("krylov_pc_used", c_i32), ("reserved", c_i32)]
 
 
 class ufe_comm(ct.Structure):

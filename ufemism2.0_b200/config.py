@@ -73,8 +73,10 @@ class Config:
     # reference's behaviour).  The PETSc options database is the reference's only other
     # knob and is unused there.
     b200_krylov_method: str = "bicgstab"      # 'bicgstab' | 'gmres'
-    b200_krylov_pc: str = "bjacobi2"          # 'jacobi' | 'bjacobi2' (2x2 u-v blocks) | 'bjacobi_lu' (strip blocks, exact LU)
-    b200_krylov_pc_lu_segments: int = 0       # 'bjacobi_lu': blocks per GPU (0 = automatic, 1 = exact solve)
+    # 'jacobi' | 'bjacobi2' (2x2 u-v blocks) | 'bjacobi_lu' (one block per GPU, solved exactly by block
+    # cyclic reduction; needs a banded = x-sorted, narrow mesh) | 'auto' (bjacobi_lu when it fits, else bjacobi2)
+    b200_krylov_pc: str = "auto"
+    b200_krylov_pc_lu_segments: int = 0       # reserved
     b200_krylov_maxits: int = 10000           # PETSc default maxits
     b200_krylov_guess_nonzero: bool = False   # False = KSP default (zero initial guess)
 

@@ -111,6 +111,7 @@ struct ufe_handle {
   bool pattern_valid = false;
   KrylovWork kw;
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
+  int pc_used = -1;                            // resolved preconditioner for the cached pattern (-1 = undecided)
   // reductions for the Picard residual
   double *red_partials = nullptr, *red_out = nullptr;
   unsigned *red_counter = nullptr;
@@ -147,7 +148,7 @@ static ClosureParams make_params(const ufe_handle *h, double eps_sq_0_applied) {
 static AssemblyParams make_asm_params(const ufe_handle *h) {
   AssemblyParams A;
   A.crossterms = h->cfg.do_include_SSADIVA_crossterms;
-  A.pc = h->cfg.krylov_pc == UFE_PC_BJACOBI_LU ? UFE_PC_BJACOBI2 : h->cfg.krylov_pc;   // scaling folded into the matrix
+  A.pc = h->cfg.krylov_pc >= UFE_PC_BJACOBI_LU ? UFE_PC_BJACOBI2 : h->cfg.krylov_pc;   // scaling folded into the matrix
   for (int s = 0; s < 4; s++) { A.bc_u[s] = h->cfg.BC_u[s]; A.bc_v[s] = h->cfg.BC_v[s]; }
   A.visc_it_relax = h->cfg.visc_it_relax;
   return A;
@@ -167,7 +168,7 @@ static int validate_config(const ufe_config *c) {
   if (c->choice_ice_rheology_Glen < 0 || c->choice_ice_rheology_Glen > 1) { ufe_set_error("unknown choice_ice_rheology_Glen (code %d)!", c->choice_ice_rheology_Glen); return UFE_ERR_INVALID; }
   if (c->choice_enhancement_factor_transition < 0 || c->choice_enhancement_factor_transition > 1) { ufe_set_error("unknown choice_enhancement_factor_transition!"); return UFE_ERR_INVALID; }
   if (c->do_subgrid_friction_on_A_grid) { ufe_set_error("do_subgrid_friction_on_A_grid = .true. is not supported (needs Hs_slope and grounding-line masks)"); return UFE_ERR_INVALID; }
-  if (c->krylov_method < 0 || c->krylov_method > 1 || c->krylov_pc < 0 || c->krylov_pc > 2) { ufe_set_error("unknown krylov method / preconditioner"); return UFE_ERR_INVALID; }
+  if (c->krylov_method < 0 || c->krylov_method > 1 || c->krylov_pc < 0 || c->krylov_pc > 3) { ufe_set_error("unknown krylov method / preconditioner"); return UFE_ERR_INVALID; }
   if (c->choice_sliding_law == UFE_SLID_IDEALISED && c->choice_idealised_sliding_law == UFE_IDEAL_SSA_ICESTREAM &&
       c->Glens_flow_law_exponent != 3.0) { ufe_set_error("Schoof only derived a solution for the case of n=3!"); return UFE_ERR_INVALID; }
   return UFE_OK;
@@ -347,7 +348,6 @@ extern "C" int ufe_diva_set_config(ufe_handle *h, const ufe_config *cfg) {
   bool bc_changed = false;
   for (int s = 0; s < 4; s++) if (cfg->BC_u[s] != h->cfg.BC_u[s] || cfg->BC_v[s] != h->cfg.BC_v[s]) bc_changed = true;
   if (cfg->refgeo_idealised_ISMIP_HOM_L != h->cfg.refgeo_idealised_ISMIP_HOM_L) bc_changed = true;
-  if (cfg->krylov_pc_lu_segments != h->cfg.krylov_pc_lu_segments) { ufe_pclu_free(h->pclu); h->pclu = nullptr; }
   h->cfg = *cfg;
   h->pattern_valid = false;
   if (bc_changed) {
@@ -522,7 +522,7 @@ static VertexInputs vertex_inputs(const ufe_handle *h) {
 
 static int ensure_pattern(ufe_handle *h) {
   if (h->pattern_valid) return UFE_OK;
-  ufe_pclu_free(h->pclu); h->pclu = nullptr;
+  ufe_pclu_free(h->pclu); h->pclu = nullptr; h->pc_used = -1;
   const int nt = h->ti2 - h->ti1 + 1;
   double *x_keep = h->S.x;
   UFE_TRY(ufe_build_stiffness_pattern(h->st, h->ti1 - 1, nt, h->dm.nTri, make_asm_params(h), view_of(h->fam[2]),
@@ -559,8 +559,16 @@ static int linearised_resident(ufe_handle *h, double rtol, double abstol, int *n
                               h->rowkind, T, h->bc_mask, h->bc_u, h->bc_v, h->F, h->S, 1));
   cudaEventRecord(h->ev[3], h->st);
   PcLU *pc = nullptr;
-  if (h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) {       // PCSetUp: factorise the strip blocks of this iteration's matrix
-    if (!h->pclu) UFE_TRY(ufe_pclu_setup(h->st, h->S, h->cfg.krylov_pc_lu_segments, (size_t)60 << 30, &h->pclu));
+  if (h->pc_used < 0) {                               // once per cached pattern
+    h->pc_used = h->cfg.krylov_pc;
+    if (h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) UFE_TRY(ufe_pclu_setup(h->st, h->S, 0, (size_t)100 << 30, &h->pclu));
+    if (h->cfg.krylov_pc == UFE_PC_AUTO) {
+      const int rc = ufe_pclu_setup(h->st, h->S, 0, (size_t)24 << 30, &h->pclu);
+      if (rc == UFE_ERR_CUDA) return rc;
+      h->pc_used = rc == UFE_OK ? UFE_PC_BJACOBI_LU : UFE_PC_BJACOBI2;
+    }
+  }
+  if (h->pc_used == UFE_PC_BJACOBI_LU) {              // PCSetUp: factorise this iteration's matrix
     UFE_TRY(ufe_pclu_factor(h->st, h->S, h->pclu));
     pc = h->pclu;
   }
@@ -672,6 +680,7 @@ static int picard_resident(ufe_handle *h, int is_diva, ufe_solve_info *info) {
   info->visc_it_relax_applied = relax; info->Glens_flow_law_epsilon_sq_0_applied = eps0;
   info->ms_total = tot; info->ms_closures = ms_clo; info->ms_assembly = ms_asm; info->ms_krylov = ms_kry;
   info->gpu_launches = g_launch_count - launches0;
+  info->krylov_pc_used = h->pc_used;
   return UFE_OK;
 }
 

@@ -27,7 +27,7 @@ from .mesh_types import Mesh
 
 PICARD_MAXIT, KRYLOV_MAXIT, KRYLOV_DIVERGED = 1, 2, 4
 KRYLOV_METHODS = {"bicgstab": 0, "gmres": 1}
-KRYLOV_PCS = {"jacobi": 0, "bjacobi2": 1, "bjacobi_lu": 2}
+KRYLOV_PCS = {"jacobi": 0, "bjacobi2": 1, "bjacobi_lu": 2, "auto": 3}
 FAMILIES = {"a_b": (0, ("map", "ddx", "ddy")), "b_a": (1, ("map", "ddx", "ddy")),
             "b_b": (2, ("ddx", "ddy", "d2dx2", "d2dxdy", "d2dy2"))}
 
@@ -130,6 +130,8 @@ class SolveInfo:
     ms_h2d: float
     ms_d2h: float
     gpu_launches: int
+    krylov_pc_used: int = 0
+    reserved: int = 0
 
 
 def _info(s: capi.ufe_solve_info) -> SolveInfo:
