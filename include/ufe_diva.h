@@ -131,7 +131,8 @@ typedef struct ufe_config {
   int32_t krylov_pc;            /* UFE_PC_*     ; reference: block-Jacobi / ILU(0)   */
   int32_t krylov_maxits;        /* PETSc default 10000 */
   int32_t krylov_guess_nonzero; /* 0 = KSP default (x0 = 0, petsc_basic.f90:99-128) */
-  int32_t krylov_pc_lu_segments;/* reserved (UFE_PC_BJACOBI_LU uses one block per GPU, solved exactly) */
+  int32_t krylov_pc_lag;        /* UFE_PC_BJACOBI_LU: reuse a factorisation across Picard iterations until a solve
+                                 * needs more than this many Krylov iterations; 0 = factorise every iteration */
 } ufe_config;
 
 /* ---- inputs read from type_ice_model / type_bed_roughness_model ------------------

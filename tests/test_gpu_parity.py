@@ -250,7 +250,8 @@ def test_ISMIP_HOM_C_DIVA(oracle):
         S.close()
 
 
-def test_SSA_icestream_vs_oracle(oracle, segments=0):
+@pytest.mark.parametrize("lag", [0, 20])
+def test_SSA_icestream_vs_oracle(oracle, lag):
     """SSA solve with the 'infinite_SSA_icestream' copy BC.  A = 1e-18 makes these systems far
     too stiff for point Jacobi (10 000-iteration cap), so this runs with the strip-LU block-Jacobi
     preconditioner (one GPU: the block is the whole matrix, solved exactly by block cyclic reduction).
@@ -260,14 +261,15 @@ def test_SSA_icestream_vs_oracle(oracle, segments=0):
     oracle.calc_all_matrix_operators_mesh(mesh)
     C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-12
     C.visc_it_nit = 4
-    C.b200_krylov_pc, C.b200_krylov_pc_lu_segments = "bjacobi_lu", segments
+    C.b200_krylov_pc, C.b200_krylov_pc_lag = "bjacobi_lu", lag
     S = diva.initialise_DIVA_solver(mesh, C)
     try:
         info = S.solve_SSA(ice)
         R = dict(u_b=np.zeros(mesh.nTri), v_b=np.zeros(mesh.nTri))
         nv, _ = oracle.solve_SSA(mesh, ice, C, R, "direct")
         assert info.n_visc_its == nv and (info.flags & (diva.KRYLOV_MAXIT | diva.KRYLOV_DIVERGED)) == 0
-        assert info.n_Axb_its <= 2 * nv              # exact preconditioner: one or two Krylov steps per solve
+        if lag == 0:
+            assert info.n_Axb_its <= 2 * nv          # exact preconditioner: one or two Krylov steps per solve
         ref = np.concatenate([R["u_b"], R["v_b"]])
         for k in ("u_b", "v_b"):
             r = rel(getattr(S, k), R[k], ref)
@@ -277,12 +279,12 @@ def test_SSA_icestream_vs_oracle(oracle, segments=0):
 
 
 @pytest.mark.parametrize("method", ["bicgstab", "gmres"])
-def test_MISMIPplus_bjacobi_lu(oracle, method, segments=0):
+def test_MISMIPplus_bjacobi_lu(oracle, method, lag=20):
     mesh, C, ice = experiments.MISMIPplus(8e3)
     oracle.calc_all_matrix_operators_mesh(mesh)
     C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
     C.visc_it_nit = 6
-    C.b200_krylov_pc, C.b200_krylov_pc_lu_segments, C.b200_krylov_method = "bjacobi_lu", segments, method
+    C.b200_krylov_pc, C.b200_krylov_pc_lag, C.b200_krylov_method = "bjacobi_lu", lag, method
     S = diva.initialise_DIVA_solver(mesh, C)
     try:
         info = S.solve_DIVA(ice)

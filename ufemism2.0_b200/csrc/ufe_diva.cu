@@ -112,6 +112,8 @@ struct ufe_handle {
   KrylovWork kw;
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
   int pc_used = -1;                            // resolved preconditioner for the cached pattern (-1 = undecided)
+  int pc_age = -1, pc_last_its = 0;            // bjacobi_lu reuse: solves since the last factorisation (-1 = never), its of the last solve
+  int64_t pc_factorisations = 0;
   // reductions for the Picard residual
   double *red_partials = nullptr, *red_out = nullptr;
   unsigned *red_counter = nullptr;
@@ -522,7 +524,7 @@ static VertexInputs vertex_inputs(const ufe_handle *h) {
 
 static int ensure_pattern(ufe_handle *h) {
   if (h->pattern_valid) return UFE_OK;
-  ufe_pclu_free(h->pclu); h->pclu = nullptr; h->pc_used = -1;
+  ufe_pclu_free(h->pclu); h->pclu = nullptr; h->pc_used = -1; h->pc_age = -1;
   const int nt = h->ti2 - h->ti1 + 1;
   double *x_keep = h->S.x;
   UFE_TRY(ufe_build_stiffness_pattern(h->st, h->ti1 - 1, nt, h->dm.nTri, make_asm_params(h), view_of(h->fam[2]),
@@ -568,13 +570,40 @@ static int linearised_resident(ufe_handle *h, double rtol, double abstol, int *n
       h->pc_used = rc == UFE_OK ? UFE_PC_BJACOBI_LU : UFE_PC_BJACOBI2;
     }
   }
-  if (h->pc_used == UFE_PC_BJACOBI_LU) {              // PCSetUp: factorise this iteration's matrix
-    UFE_TRY(ufe_pclu_factor(h->st, h->S, h->pclu));
+  if (h->pc_used == UFE_PC_BJACOBI_LU) {
+    // PCSetUp.  The factorisation of an earlier Picard iteration's matrix is still a good
+    // preconditioner while the viscosity changes slowly, so it is reused (krylov_pc_lag > 0) until
+    // the Krylov count shows it has aged: refactorise when the previous solve needed more than
+    // krylov_pc_lag iterations.  A solve that fails with a reused factorisation is repeated with a
+    // fresh one, so the result always satisfies the same stopping rule.
+    const int lag = h->cfg.krylov_pc_lag;
+    bool fresh = false;
+    if (h->pc_age < 0 || lag <= 0 || h->pc_last_its > lag) {
+      UFE_TRY(ufe_pclu_factor(h->st, h->S, h->pclu));
+      h->pc_age = 0; h->pc_factorisations++; fresh = true;
+    } else h->pc_age++;
     pc = h->pclu;
+    int its1 = 0, fl1 = 0;
+    const int cap = fresh ? h->cfg.krylov_maxits : std::max(4 * lag, 8);
+    UFE_TRY(ufe_krylov_run(h->st, h->S, h->kw, h->comm, h->comm.nranks > 1 ? &h->plan_b_for_b : nullptr,
+                           h->cfg.krylov_method, rtol, abstol, cap, h->cfg.krylov_guess_nonzero, &its1, &fl1, pc));
+    if (!fresh && fl1 != 0) {
+      int its2 = 0;
+      UFE_TRY(ufe_pclu_factor(h->st, h->S, h->pclu));
+      h->pc_age = 0; h->pc_factorisations++;
+      UFE_TRY(ufe_krylov_run(h->st, h->S, h->kw, h->comm, h->comm.nranks > 1 ? &h->plan_b_for_b : nullptr,
+                             h->cfg.krylov_method, rtol, abstol, h->cfg.krylov_maxits, h->cfg.krylov_guess_nonzero,
+                             &its2, &fl1, pc));
+      h->pc_last_its = its2;
+      its1 += its2;
+    } else h->pc_last_its = its1;
+    if (n_its) *n_its = its1;
+    if (flags) *flags = fl1;
+  } else {
+    UFE_TRY(ufe_krylov_run(h->st, h->S, h->kw, h->comm, h->comm.nranks > 1 ? &h->plan_b_for_b : nullptr,
+                           h->cfg.krylov_method, rtol, abstol, h->cfg.krylov_maxits, h->cfg.krylov_guess_nonzero,
+                           n_its, flags, nullptr));
   }
-  UFE_TRY(ufe_krylov_run(h->st, h->S, h->kw, h->comm, h->comm.nranks > 1 ? &h->plan_b_for_b : nullptr,
-                         h->cfg.krylov_method, rtol, abstol, h->cfg.krylov_maxits, h->cfg.krylov_guess_nonzero,
-                         n_its, flags, pc));
   cudaEventRecord(h->ev[4], h->st);
   UFE_CUDA(cudaEventSynchronize(h->ev[4]));
   if (ms_asm) cudaEventElapsedTime(ms_asm, h->ev[2], h->ev[3]);

@@ -68,7 +68,7 @@ def config_struct(C: Config) -> capi.ufe_config:
     s.krylov_pc = _code(KRYLOV_PCS, C.b200_krylov_pc, "b200_krylov_pc")
     s.krylov_maxits = C.b200_krylov_maxits
     s.krylov_guess_nonzero = int(C.b200_krylov_guess_nonzero)
-    s.krylov_pc_lu_segments = int(C.b200_krylov_pc_lu_segments)
+    s.krylov_pc_lag = int(C.b200_krylov_pc_lag)
     return s
 
 

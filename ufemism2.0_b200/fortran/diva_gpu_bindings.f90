@@ -1,0 +1,198 @@
+module diva_gpu_bindings
+
+  ! ISO_C_BINDING interfaces to libufe_diva.so (include/ufe_diva.h): the B200-native replacement of
+  ! the DIVA / SSA velocity solve.  Intended location in the reference tree:
+  !   src/UFEMISM/ice_dynamics/conservation_of_momentum/SSA_DIVA/diva_gpu_bindings.f90
+  ! Call sites it serves (INTEGRATION.md):
+  !   L0  solve_linearised_SSA_DIVA.f90:159      call solve_matrix_equation_CSR_PETSc( ...)
+  !   L1  DIVA_main.f90:189-192, SSA_main.f90:178 call solve_SSA_DIVA_linearised( ...)
+  !   L2  conservation_of_momentum_main.f90:142   call solve_DIVA( ...)
+  ! NOTE: the build image of this repository has no Fortran compiler; this file is compile-checked
+  ! only where gfortran exists (gfortran -c diva_gpu_bindings.f90).
+
+  use, intrinsic :: iso_c_binding
+
+  implicit none
+
+  integer(c_int), parameter :: UFE_OK = 0
+  integer(c_int), parameter :: UFE_FLAG_PICARD_MAXIT = 1, UFE_FLAG_KRYLOV_MAXIT = 2, UFE_FLAG_KRYLOV_DIVERGED = 4
+  integer(c_int), parameter :: UFE_BC_INFINITE = 1, UFE_BC_ZERO = 2, UFE_BC_PERIODIC_ISMIP_HOM = 3, UFE_BC_INFINITE_SSA_ICESTREAM = 4
+  integer(c_int), parameter :: UFE_KRYLOV_BICGSTAB = 0, UFE_KRYLOV_GMRES = 1
+  integer(c_int), parameter :: UFE_PC_JACOBI = 0, UFE_PC_BJACOBI2 = 1, UFE_PC_BJACOBI_LU = 2, UFE_PC_AUTO = 3
+
+  type, bind(C) :: ufe_csr
+    integer(c_int32_t) :: m, n, m_loc, n_loc, i1, i2, j1, j2, nnz
+    type(c_ptr)        :: ptr, ind, val
+  end type ufe_csr
+
+  type, bind(C) :: ufe_mesh
+    integer(c_int32_t) :: nV, nTri, nC_mem, nz
+    real(c_double)     :: xmin, xmax, ymin, ymax
+    type(c_ptr)        :: V, Tri, TriC, C, nC, iTri, niTri, VBI, TriBI, TriGC, zeta
+    type(c_ptr)        :: M_a_b(3), M_b_a(3), M2_b_b(5)
+  end type ufe_mesh
+
+  type, bind(C) :: ufe_config
+    integer(c_int32_t) :: do_include_SSADIVA_crossterms
+    real(c_double)     :: visc_it_norm_dUV_tol
+    integer(c_int32_t) :: visc_it_nit
+    real(c_double)     :: visc_it_relax, visc_eff_min, vel_max, stress_balance_PETSc_rtol, stress_balance_PETSc_abstol
+    integer(c_int32_t) :: BC_u(4), BC_v(4)
+    integer(c_int32_t) :: choice_sliding_law, choice_idealised_sliding_law
+    real(c_double)     :: slid_Weertman_m, slid_Budd_q_plastic, slid_Budd_u_threshold, slid_ZI_p, slid_ZI_ut
+    integer(c_int32_t) :: do_GL_subgrid_friction, do_subgrid_friction_on_A_grid
+    real(c_double)     :: subgrid_friction_exponent_on_B_grid, slid_beta_max, slid_delta_v, Hi_min
+    real(c_double)     :: Glens_flow_law_exponent, Glens_flow_law_epsilon_sq_0
+    integer(c_int32_t) :: choice_ice_rheology_Glen
+    real(c_double)     :: uniform_Glens_flow_factor
+    integer(c_int32_t) :: choice_enhancement_factor_transition
+    real(c_double)     :: m_enh_sheet, m_enh_shelf
+    real(c_double)     :: refgeo_idealised_SSA_icestream_Hi, refgeo_idealised_SSA_icestream_dhdx
+    real(c_double)     :: refgeo_idealised_SSA_icestream_L, refgeo_idealised_SSA_icestream_m
+    real(c_double)     :: refgeo_idealised_ISMIP_HOM_L
+    integer(c_int32_t) :: krylov_method, krylov_pc, krylov_maxits, krylov_guess_nonzero, krylov_pc_lag
+  end type ufe_config
+
+  type, bind(C) :: ufe_ice_inputs
+    type(c_ptr) :: Hi, Hs, Hib, SL, fraction_gr, fraction_gr_b, effective_pressure
+    type(c_ptr) :: mask_grounded_ice, mask_floating_ice, mask_icefree_land
+    type(c_ptr) :: Ti, till_friction_angle, alpha_sq, beta_sq
+    type(c_ptr) :: BC_prescr_mask_b, BC_prescr_u_b, BC_prescr_v_b
+  end type ufe_ice_inputs
+
+  type, bind(C) :: ufe_diva_state
+    type(c_ptr) :: u_vav_b, v_vav_b, tau_bx_b, tau_by_b, eta_3D_b, u_base_b, v_base_b
+    type(c_ptr) :: u_3D_b, v_3D_b, du_dx_a, du_dy_a, dv_dx_a, dv_dy_a, du_dz_3D_a, dv_dz_3D_a, eta_3D_a
+    type(c_ptr) :: basal_friction_coefficient_a
+  end type ufe_diva_state
+
+  type, bind(C) :: ufe_ssa_state
+    type(c_ptr) :: u_b, v_b, basal_friction_coefficient_a
+  end type ufe_ssa_state
+
+  type, bind(C) :: ufe_solve_info
+    integer(c_int32_t) :: n_visc_its, n_Axb_its, flags
+    real(c_double)     :: L2_uv, visc_it_relax_applied, Glens_flow_law_epsilon_sq_0_applied
+    real(c_double)     :: ms_total, ms_closures, ms_assembly, ms_krylov, ms_h2d, ms_d2h
+    integer(c_int64_t) :: gpu_launches
+    integer(c_int32_t) :: krylov_pc_used, reserved
+  end type ufe_solve_info
+
+  type, bind(C) :: ufe_comm
+    integer(c_int32_t) :: rank, nranks, device
+    type(c_ptr)        :: nccl_unique_id
+  end type ufe_comm
+
+  interface
+
+    function ufe_last_error_string() bind(C, name='ufe_last_error_string') result(s)
+      import :: c_ptr
+      type(c_ptr) :: s
+    end function ufe_last_error_string
+
+    integer(c_int) function ufe_comm_get_unique_id( id_out) bind(C, name='ufe_comm_get_unique_id')
+      import :: c_int, c_char
+      character(kind=c_char), intent(out) :: id_out(128)
+    end function ufe_comm_get_unique_id
+
+    subroutine ufe_partition_list( ntot, i, n, i1, i2) bind(C, name='ufe_partition_list')
+      import :: c_int32_t
+      integer(c_int32_t), value       :: ntot, i, n
+      integer(c_int32_t), intent(out) :: i1, i2
+    end subroutine ufe_partition_list
+
+    ! L0: replaces solve_matrix_equation_CSR_PETSc (src/UPSY/basic/petsc_basic.f90:32-64)
+    integer(c_int) function ufe_krylov_solve( A, b, x, rtol, abstol, method, maxits, guess_nonzero, n_its, flags) &
+        bind(C, name='ufe_krylov_solve')
+      import :: c_int, c_int32_t, c_double, ufe_csr
+      type(ufe_csr),      intent(in)    :: A
+      real(c_double),     intent(in)    :: b(*)
+      real(c_double),     intent(inout) :: x(*)
+      real(c_double),     value         :: rtol, abstol
+      integer(c_int32_t), value         :: method, maxits, guess_nonzero
+      integer(c_int32_t), intent(out)   :: n_its, flags
+    end function ufe_krylov_solve
+
+    ! multiply_CSR_matrix_with_vector_1D / _2D (CSR_matrix_vector_multiplication.f90:198,336)
+    integer(c_int) function ufe_spmv( A, x, y, nlayers) bind(C, name='ufe_spmv')
+      import :: c_int, c_int32_t, c_double, ufe_csr
+      type(ufe_csr),      intent(in)  :: A
+      real(c_double),     intent(in)  :: x(*)
+      real(c_double),     intent(out) :: y(*)
+      integer(c_int32_t), value       :: nlayers
+    end function ufe_spmv
+
+    ! lifecycle: initialise_DIVA_solver / allocate_DIVA_solver (DIVA_main.f90:37,752)
+    integer(c_int) function ufe_diva_create( mesh, cfg, comm, handle) bind(C, name='ufe_diva_create')
+      import :: c_int, c_ptr, ufe_mesh, ufe_config
+      type(ufe_mesh),   intent(in)  :: mesh
+      type(ufe_config), intent(in)  :: cfg
+      type(c_ptr),      value       :: comm        ! c_loc( ufe_comm) or c_null_ptr (one rank)
+      type(c_ptr),      intent(out) :: handle
+    end function ufe_diva_create
+
+    integer(c_int) function ufe_diva_destroy( handle) bind(C, name='ufe_diva_destroy')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+    end function ufe_diva_destroy
+
+    integer(c_int) function ufe_diva_set_config( handle, cfg) bind(C, name='ufe_diva_set_config')
+      import :: c_int, c_ptr, ufe_config
+      type(c_ptr),      value      :: handle
+      type(ufe_config), intent(in) :: cfg
+    end function ufe_diva_set_config
+
+    ! L2: replaces solve_DIVA (DIVA_main.f90:88-262) and solve_SSA (SSA_main.f90:87-242)
+    integer(c_int) function ufe_diva_solve( handle, ice, state, info) bind(C, name='ufe_diva_solve')
+      import :: c_int, c_ptr, ufe_ice_inputs, ufe_diva_state, ufe_solve_info
+      type(c_ptr),          value         :: handle
+      type(ufe_ice_inputs), intent(in)    :: ice
+      type(ufe_diva_state), intent(inout) :: state
+      type(ufe_solve_info), intent(out)   :: info
+    end function ufe_diva_solve
+
+    integer(c_int) function ufe_ssa_solve( handle, ice, state, info) bind(C, name='ufe_ssa_solve')
+      import :: c_int, c_ptr, ufe_ice_inputs, ufe_ssa_state, ufe_solve_info
+      type(c_ptr),          value         :: handle
+      type(ufe_ice_inputs), intent(in)    :: ice
+      type(ufe_ssa_state),  intent(inout) :: state
+      type(ufe_solve_info), intent(out)   :: info
+    end function ufe_ssa_solve
+
+    ! L1: replaces solve_SSA_DIVA_linearised (solve_linearised_SSA_DIVA.f90:23-178)
+    integer(c_int) function ufe_ssa_diva_linearised( handle, u_b, v_b, N_b, dN_dx_b, dN_dy_b, basal_friction_coefficient_b, &
+        tau_dx_b, tau_dy_b, u_b_prev, v_b_prev, PETSc_rtol, PETSc_abstol, n_Axb_its, BC_prescr_mask_b, BC_prescr_u_b, BC_prescr_v_b) &
+        bind(C, name='ufe_ssa_diva_linearised')
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr),        value         :: handle
+      real(c_double),     intent(inout) :: u_b(*), v_b(*)
+      real(c_double),     intent(in)    :: N_b(*), dN_dx_b(*), dN_dy_b(*), basal_friction_coefficient_b(*), tau_dx_b(*), tau_dy_b(*)
+      real(c_double),     intent(out)   :: u_b_prev(*), v_b_prev(*)
+      real(c_double),     value         :: PETSc_rtol, PETSc_abstol
+      integer(c_int32_t), intent(out)   :: n_Axb_its
+      type(c_ptr),        value         :: BC_prescr_mask_b, BC_prescr_u_b, BC_prescr_v_b   ! c_null_ptr when absent
+    end function ufe_ssa_diva_linearised
+
+  end interface
+
+contains
+
+  subroutine ufe_check( ierr, routine_name)
+    ! Maps a non-zero status to the reference's crash() (control_resources_and_error_messaging.f90:377)
+    integer(c_int),   intent(in) :: ierr
+    character(len=*), intent(in) :: routine_name
+    character(kind=c_char), pointer :: cmsg(:)
+    character(len=1024) :: msg
+    integer :: i
+    if (ierr == UFE_OK) return
+    call c_f_pointer( ufe_last_error_string(), cmsg, [1024])
+    msg = ''
+    do i = 1, 1024
+      if (cmsg( i) == c_null_char) exit
+      msg( i:i) = cmsg( i)
+    end do
+    ! call crash( trim( routine_name) // ': ' // trim( msg))
+    error stop trim( routine_name) // ': ' // trim( msg)
+  end subroutine ufe_check
+
+end module diva_gpu_bindings
