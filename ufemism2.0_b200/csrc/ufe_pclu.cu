@@ -158,7 +158,7 @@ k_bgemm(int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha, dou
     for (int kk = 0; kk < GK; kk++) {
       double a[4], b[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++) { a[q] = sA[kk][ty * 4 + q]; b[q] = sB[kk][tx * 4 + q]; }
+      for (int q = 0; q < 4; q++) { a[q] = sA[kk][ty + 16 * q]; b[q] = sB[kk][tx + 16 * q]; }   // conflict-free, rows broadcast
 #pragma unroll
       for (int p = 0; p < 4; p++)
 #pragma unroll
@@ -170,7 +170,7 @@ k_bgemm(int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha, dou
   for (int p = 0; p < 4; p++)
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const size_t o = (size_t)(i0 + ty * 4 + p) * g + j0 + tx * 4 + q;
+      const size_t o = (size_t)(i0 + ty + 16 * p) * g + j0 + tx + 16 * q;
       Cb[o] = (beta == 0.0 ? 0.0 : beta * Cb[o]) + alpha * acc[p][q];
     }
 }
@@ -281,7 +281,7 @@ k_gjb_update(int g, int s, int b, double *__restrict__ D, const double *__restri
   for (int kk = 0; kk < NB; kk++) {
     double a[4], r[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) { a[q] = Cb[ty * 4 + q][kk]; r[q] = R[kk][tx * 4 + q]; }
+    for (int q = 0; q < 4; q++) { a[q] = Cb[ty + 16 * q][kk]; r[q] = R[kk][tx + 16 * q]; }
 #pragma unroll
     for (int p = 0; p < 4; p++)
 #pragma unroll
@@ -289,11 +289,11 @@ k_gjb_update(int g, int s, int b, double *__restrict__ D, const double *__restri
   }
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    const int i = i0 + ty * 4 + p;
+    const int i = i0 + ty + 16 * p;
     if (i / NB == b) continue;                 // pivot rows were handled by the panel kernel
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const int j = j0 + tx * 4 + q;
+      const int j = j0 + tx + 16 * q;
       if (j / NB == b) continue;               // pivot columns likewise
       A[(size_t)i * g + j] -= acc[p][q];
     }
