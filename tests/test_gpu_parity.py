@@ -378,3 +378,35 @@ def test_properties_at_scale():
         assert M.shape[0] == 2 * mesh.nTri and np.isfinite(A.val).all() and np.isfinite(bb).all()
     finally:
         S.close()
+
+
+# ------------------------------------------------------------------------------------------
+# committed golden fixture (tests/golden/oracle_lattice_9x7.npz): no oracle code at test time
+# ------------------------------------------------------------------------------------------
+def test_against_committed_golden_fixture():
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_lattice_9x7.npz"))
+    L = float(G["L"])
+    mesh = synthetic.lattice_mesh(-L, L, -L, L, 9, 7, jitter=0.25, seed=424242)
+    assert np.array_equal(mesh.V, G["V"]) and np.array_equal(mesh.Tri, G["Tri"])
+    _, C, _ = experiments.ISMIP_HOM("C", L, 9)
+    ice = synthetic.geometry_ISMIP_HOM_C(mesh, L)
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-12
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        for fam, names in diva.FAMILIES.items():
+            for w in names[1]:
+                nm = ("M2_%s_b_b" % w) if fam == "b_b" else ("M_%s_%s" % (w, fam))
+                A = S.get_operator(fam, w)
+                assert np.array_equal(A.ptr, G[nm + "_ptr"]) and np.array_equal(A.ind, G[nm + "_ind"]), nm
+                assert rel(A.val, G[nm + "_val"])[1] < TOL_OPVAL, nm
+        info = S.solve_DIVA(ice)
+        assert info.n_visc_its == int(G["n_visc_its"])
+        ref = np.concatenate([G["u_vav_b"], G["v_vav_b"]])
+        for k in ("u_vav_b", "v_vav_b"):
+            r = rel(getattr(S, k), G[k], ref)
+            assert r[0] < TOL_UV and r[1] < TOL_UV, (k, r)
+        A, bb = S.get_stiffness_matrix()
+        assert np.array_equal(A.ptr, G["A_ptr"]) and np.array_equal(A.ind, G["A_ind"])
+    finally:
+        S.close()

@@ -225,3 +225,39 @@ def test_bc_copy_tables(oracle, mesh41):
         py = gy - L / 2 if gy > 0 else gy + L / 2
         d = np.hypot(m.TriGC[tc[nz] - 1, 0] - px, m.TriGC[tc[nz] - 1, 1] - py)
         assert d.max() < 3 * 20e3
+
+
+# ------------------------------------------------------------------------------------------
+# committed fixtures (tests/golden/, generated by tests/golden/make_golden.py)
+# ------------------------------------------------------------------------------------------
+def _golden_dir():
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_oracle_against_committed_known_answers(oracle):
+    import json, os
+    K = json.load(open(os.path.join(_golden_dir(), "reference_known_answers.json")))
+    for name, case in K.items():
+        rows = [[(int(c), float(v)) for c, v in r] for r in case["rows"]]
+        A = _csr(oracle, rows, case["n"])
+        if "y" in case:
+            assert np.array_equal(oracle.spmv(A, np.array(case["x"], float)), np.array(case["y"], float)), name
+        else:
+            x = oracle.direct_solve(A, np.array(case["b"], float))
+            assert np.abs(x - np.array(case["x"])).max() < case["tol"], name
+
+
+def test_oracle_reproduces_committed_lattice_fixture(oracle):
+    """The npz was produced by the oracle; re-deriving it guards the fixture against silent drift
+    of either the oracle or the synthetic-mesh generator."""
+    import os
+    from ufemism2_0_b200 import experiments
+    G = np.load(os.path.join(_golden_dir(), "oracle_lattice_9x7.npz"))
+    L = float(G["L"])
+    mesh = synthetic.lattice_mesh(-L, L, -L, L, 9, 7, jitter=0.25, seed=424242)
+    assert np.array_equal(mesh.V, G["V"]) and np.array_equal(mesh.Tri, G["Tri"])
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    for nm, A in mesh.ops.items():
+        assert np.array_equal(A.ptr, G[nm + "_ptr"]) and np.array_equal(A.ind, G[nm + "_ind"]), nm
+        assert np.allclose(A.val, G[nm + "_val"], rtol=1e-12, atol=0), nm
