@@ -131,48 +131,65 @@ __global__ void k_pad_identity(int n_loc, int g, int K, double *__restrict__ D) 
 
 // ------------------------------------------------------------------------------------
 // batched dense GEMM on g x g row-major blocks: C = beta*C + alpha*A*B for every item of a
-// level (blockIdx.z).  64x64 tile, 256 threads, 4x4 register micro-tile; g multiple of 64.
+// level (blockIdx.z).  128x64 tile, 256 threads, 8x4 register micro-tile, register-staged
+// prefetch of the next k-tile; g multiple of 64.
 // Items whose A or B operand does not exist (no neighbour on that side) are skipped.
 // ------------------------------------------------------------------------------------
+#define TM 128         // k_bgemm tile: 128 x 64, 8 x 4 register micro-tile per thread
 __global__ void __launch_bounds__(256)
 k_bgemm(int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha, double beta) {
   const int z = blockIdx.z, node = (2 * z + 1 + kept) * s - 1;
   const long long ia = opnd_block(A, node, z, K), ib = opnd_block(B, node, z, K), ic = opnd_block(C, node, z, K);
   if (ia < 0 || ib < 0 || ic < 0) return;
   const size_t gg = (size_t)g * g;
-  const double *Ab = A.p + ia * gg, *Bb = B.p + ib * gg;
+  const double *__restrict__ Ab = A.p + ia * gg, *__restrict__ Bb = B.p + ib * gg;
   double *Cb = const_cast<double *>(C.p) + ic * gg;
-  __shared__ double sA[GK][GT + 1], sB[GK][GT + 1];
+  __shared__ double sA[GK][TM + 1], sB[GK][GT + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
-  double acc[4][4] = {};
+  const int i0 = blockIdx.y * TM, j0 = blockIdx.x * GT;
+  // global -> register staging of the next k-tile (hides the load latency behind the FMAs)
+  const int a_kk = threadIdx.x & 15, a_ii = threadIdx.x >> 4;     // A: rows a_ii + 16 q (q < 8), column k0 + a_kk
+  const int b_jj = threadIdx.x & 63, b_kk = threadIdx.x >> 6;     // B: rows k0 + b_kk + 4 q (q < 4), column j0 + b_jj
+  double ra[8], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) { const int i = i0 + a_ii + 16 * q; ra[q] = i < g ? Ab[(size_t)i * g + k0 + a_kk] : 0.0; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) rb[q] = Bb[(size_t)(k0 + b_kk + 4 * q) * g + j0 + b_jj];
+  };
+  double acc[8][4] = {};
+  fetch(0);
   for (int k0 = 0; k0 < g; k0 += GK) {
-    for (int q = threadIdx.x; q < GT * GK; q += 256) {
-      const int ii = q / GK, kk = q % GK;
-      sA[kk][ii] = Ab[(size_t)(i0 + ii) * g + k0 + kk];
-      const int k2 = q / GT, jj = q % GT;
-      sB[k2][jj] = Bb[(size_t)(k0 + k2) * g + j0 + jj];
-    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) sA[a_kk][a_ii + 16 * q] = ra[q];
+#pragma unroll
+    for (int q = 0; q < 4; q++) sB[b_kk + 4 * q][b_jj] = rb[q];
     __syncthreads();
+    if (k0 + GK < g) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; kk++) {
-      double a[4], b[4];
+      double a[8], b[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++) { a[q] = sA[kk][ty + 16 * q]; b[q] = sB[kk][tx + 16 * q]; }   // conflict-free, rows broadcast
+      for (int q = 0; q < 8; q++) a[q] = sA[kk][ty + 16 * q];       // two addresses per warp: broadcast
 #pragma unroll
-      for (int p = 0; p < 4; p++)
+      for (int q = 0; q < 4; q++) b[q] = sB[kk][tx + 16 * q];       // 16 consecutive doubles: conflict-free
+#pragma unroll
+      for (int p = 0; p < 8; p++)
 #pragma unroll
         for (int q = 0; q < 4; q++) acc[p][q] += a[p] * b[q];
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int p = 0; p < 4; p++)
+  for (int p = 0; p < 8; p++) {
+    const int i = i0 + ty + 16 * p;
+    if (i >= g) continue;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const size_t o = (size_t)(i0 + ty + 16 * p) * g + j0 + tx + 16 * q;
+      const size_t o = (size_t)i * g + j0 + tx + 16 * q;
       Cb[o] = (beta == 0.0 ? 0.0 : beta * Cb[o]) + alpha * acc[p][q];
     }
+  }
 }
 
 // zero the blocks of a level's items (for outputs whose producing GEMM may be skipped)
@@ -446,7 +463,8 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
       k_gjb_update<<<dim3(nt, nt, lv.nE), 256, 0, st>>>(g, s, b, pc->D, pc->colbuf);
     }
     g_launch_count += 3 * nbk;
-    const dim3 gE(nt, nt, lv.nE), gK(nt, nt, lv.nK > 0 ? lv.nK : 1);
+    const int ntm = (g + TM - 1) / TM;
+    const dim3 gE(nt, ntm, lv.nE), gK(nt, ntm, lv.nK > 0 ? lv.nK : 1);
     const Opnd Dn{pc->D, 0, 0}, Ln{L, 0, 0}, Un{U, 0, 0}, Pn{pc->Pm, 0, 0}, Qn{pc->Qm, 0, 0};
     k_bgemm<<<gE, 256, 0, st>>>(g, K, s, 0, Dn, Ln, Pn, 1.0, 0.0);
     k_bgemm<<<gE, 256, 0, st>>>(g, K, s, 0, Dn, Un, Qn, 1.0, 0.0);
