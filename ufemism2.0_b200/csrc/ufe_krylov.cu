@@ -34,7 +34,7 @@
 #define GM_INVHN(gm) ((gm) + 31 * 30 + 60 + 31 + 30 + 32)
 #define GM_SIZE (31 * 30 + 60 + 31 + 30 + 32 + 1)
 
-enum { ST_INIT = 0, ST_A = 1, ST_B = 2, ST_C = 3, ST_GM_INIT = 4, ST_GM_H = 5, ST_GM_NORM = 6 };
+enum { ST_INIT = 0, ST_A = 1, ST_B = 2, ST_C = 3, ST_GM_INIT = 4, ST_GM_H = 5, ST_GM_NORM = 6, ST_S = 7 };
 
 __device__ void gmres_givens(KrylovScalars *sc, double *gm, double hn);
 
@@ -54,6 +54,13 @@ __device__ void post_reduce(int stage, KrylovScalars *sc, double *gm, double rto
       const double rv = sc->dots[0];
       if (rv == 0.0) { sc->done = 1; sc->reason = -5; break; }
       sc->alpha = sc->rho / rv;
+      break;
+    }
+    case ST_S: {      // dots: (s,s) -- half-step exit: x + alpha p already satisfies the stopping rule
+      const double snorm = sqrt(sc->dots[0]);
+      if (snorm <= sc->ttol) {
+        sc->rnorm = snorm; sc->its += 1; sc->pad0 = 1; sc->done = 1; sc->reason = (snorm <= abstol) ? 3 : 2;
+      }
       break;
     }
     case ST_B: {      // dots: (t,s), (t,t)
@@ -359,6 +366,31 @@ k_bicg_s(int n, int r0, const double *__restrict__ r, const double *__restrict__
     sg[r0 + i] = r[i] - alpha * v[i];
 }
 
+// s = r - alpha v with (s,s): used with an explicit preconditioner, where an iteration is
+// expensive and the first half-step usually converges already
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_bicg_s_norm(int n, int r0, const double *__restrict__ r, const double *__restrict__ v, double *__restrict__ sg,
+              double *partials, unsigned *counter, double *dots_local, KrylovScalars *sc, int single, double rtol,
+              double abstol) {
+  if (sc->done) return;
+  const double alpha = sc->alpha;
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double si = r[i] - alpha * v[i];
+    sg[r0 + i] = si;
+    acc[0] += si * si;
+  }
+  finish_stage<1>(acc, ST_S, partials, counter, dots_local, sc, nullptr, single, rtol, abstol);
+}
+// x += alpha p, once, if the half-step exit fired (pad0 == 1); k_half_ack then retires the flag
+__global__ void __launch_bounds__(UFE_RED_THREADS)
+k_bicg_xhalf(int n, int r0, double *__restrict__ xg, const double *__restrict__ pg, const KrylovScalars *sc) {
+  if (sc->pad0 != 1) return;
+  const double alpha = sc->alpha;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xg[r0 + i] += alpha * pg[r0 + i];
+}
+__global__ void k_half_ack(KrylovScalars *sc) { if (sc->pad0 == 1) sc->pad0 = 2; }
+
 // x += alpha p + omega s ; r = s - omega t ; dots (r,r), (rhat,r)
 __global__ void __launch_bounds__(UFE_RED_THREADS)
 k_bicg_xr(int n, int r0, double *__restrict__ xg, const double *__restrict__ pg, const double *__restrict__ sg,
@@ -380,7 +412,7 @@ k_bicg_xr(int n, int r0, double *__restrict__ xg, const double *__restrict__ pg,
 
 __global__ void k_sc_reset(KrylovScalars *sc, int maxits, double abstol) {
   sc->abstol = abstol;
-  sc->its = 0; sc->done = 0; sc->reason = 0; sc->maxits = maxits; sc->jcount = 0; sc->finalized = 0;
+  sc->its = 0; sc->done = 0; sc->reason = 0; sc->maxits = maxits; sc->jcount = 0; sc->finalized = 0; sc->pad0 = 0;
   sc->bnorm = -1.0; sc->rnorm = 0.0; sc->ttol = 0.0; sc->rho = 1.0; sc->alpha = 1.0; sc->omega = 1.0; sc->beta = 0.0;
 }
 
@@ -574,14 +606,20 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
                                kw.dots_local, kw.sc, single, rtol, abstol);
   UFE_LAUNCH_CHECK();
   UFE_TRY(allreduce_stage(st, comm, kw, ST_INIT, 2, rtol, abstol));
-  int launched = 0, batch = 4;
+  int launched = 0, batch = pc ? 1 : 4;     // an exact block solve converges in the first (half) step
   while (true) {
     for (int b = 0; b < batch; b++, launched++) {
       if (launched > 0) { k_bicg_p<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.pg, kw.sc); UFE_LAUNCH_CHECK(); }
       if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.pg, 0, 1, 2));
       UFE_TRY(apply_op<1>(st, S, pc, kw.pg, kw.v, kw.rhat, ST_A, kw, single, rtol, abstol));
       UFE_TRY(allreduce_stage(st, comm, kw, ST_A, 1, rtol, abstol));
-      k_bicg_s<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.sc); UFE_LAUNCH_CHECK();
+      if (pc) {
+        k_bicg_s_norm<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.partials, kw.counter, kw.dots_local, kw.sc, single, rtol, abstol);
+        UFE_LAUNCH_CHECK();
+        UFE_TRY(allreduce_stage(st, comm, kw, ST_S, 1, rtol, abstol));
+        k_bicg_xhalf<<<G, B, 0, st>>>(n, r0, xg, kw.pg, kw.sc); UFE_LAUNCH_CHECK();
+        k_half_ack<<<1, 1, 0, st>>>(kw.sc); UFE_LAUNCH_CHECK();
+      } else { k_bicg_s<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.sc); UFE_LAUNCH_CHECK(); }
       if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.sg, 0, 1, 2));
       UFE_TRY(apply_op<2>(st, S, pc, kw.sg, kw.t, nullptr, ST_B, kw, single, rtol, abstol));
       UFE_TRY(allreduce_stage(st, comm, kw, ST_B, 2, rtol, abstol));

@@ -135,61 +135,74 @@ __global__ void k_pad_identity(int n_loc, int g, int K, double *__restrict__ D) 
 // prefetch of the next k-tile; g multiple of 64.
 // Items whose A or B operand does not exist (no neighbour on that side) are skipped.
 // ------------------------------------------------------------------------------------
-#define TM 128         // k_bgemm tile: 128 x 64, 8 x 4 register micro-tile per thread
+// tile = (16 MI) x (16 NI); MI x NI register micro-tile per thread (rows ty + 16 p, columns tx + 16 q)
+template <int MI, int NI>
 __global__ void __launch_bounds__(256)
 k_bgemm(int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha, double beta) {
+  constexpr int TMv = 16 * MI, TNv = 16 * NI, BROWS = 256 / TNv;     // B rows staged per pass
   const int z = blockIdx.z, node = (2 * z + 1 + kept) * s - 1;
   const long long ia = opnd_block(A, node, z, K), ib = opnd_block(B, node, z, K), ic = opnd_block(C, node, z, K);
   if (ia < 0 || ib < 0 || ic < 0) return;
   const size_t gg = (size_t)g * g;
   const double *__restrict__ Ab = A.p + ia * gg, *__restrict__ Bb = B.p + ib * gg;
   double *Cb = const_cast<double *>(C.p) + ic * gg;
-  __shared__ double sA[GK][TM + 1], sB[GK][GT + 1];
+  __shared__ double sA[GK][TMv + 1], sB[GK][TNv + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = blockIdx.y * TM, j0 = blockIdx.x * GT;
+  const int i0 = blockIdx.y * TMv, j0 = blockIdx.x * TNv;
   // global -> register staging of the next k-tile (hides the load latency behind the FMAs)
-  const int a_kk = threadIdx.x & 15, a_ii = threadIdx.x >> 4;     // A: rows a_ii + 16 q (q < 8), column k0 + a_kk
-  const int b_jj = threadIdx.x & 63, b_kk = threadIdx.x >> 6;     // B: rows k0 + b_kk + 4 q (q < 4), column j0 + b_jj
-  double ra[8], rb[4];
+  const int a_kk = threadIdx.x & 15, a_ii = threadIdx.x >> 4;             // A: rows a_ii + 16 q, column k0 + a_kk
+  const int b_jj = threadIdx.x & (TNv - 1), b_kk = threadIdx.x / TNv;     // B: rows k0 + b_kk + BROWS q, column j0 + b_jj
+  double ra[MI], rb[NI];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int q = 0; q < 8; q++) { const int i = i0 + a_ii + 16 * q; ra[q] = i < g ? Ab[(size_t)i * g + k0 + a_kk] : 0.0; }
+    for (int q = 0; q < MI; q++) { const int i = i0 + a_ii + 16 * q; ra[q] = i < g ? Ab[(size_t)i * g + k0 + a_kk] : 0.0; }
 #pragma unroll
-    for (int q = 0; q < 4; q++) rb[q] = Bb[(size_t)(k0 + b_kk + 4 * q) * g + j0 + b_jj];
+    for (int q = 0; q < NI; q++) rb[q] = Bb[(size_t)(k0 + b_kk + BROWS * q) * g + j0 + b_jj];
   };
-  double acc[8][4] = {};
+  double acc[MI][NI] = {};
   fetch(0);
   for (int k0 = 0; k0 < g; k0 += GK) {
 #pragma unroll
-    for (int q = 0; q < 8; q++) sA[a_kk][a_ii + 16 * q] = ra[q];
+    for (int q = 0; q < MI; q++) sA[a_kk][a_ii + 16 * q] = ra[q];
 #pragma unroll
-    for (int q = 0; q < 4; q++) sB[b_kk + 4 * q][b_jj] = rb[q];
+    for (int q = 0; q < NI; q++) sB[b_kk + BROWS * q][b_jj] = rb[q];
     __syncthreads();
     if (k0 + GK < g) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; kk++) {
-      double a[8], b[4];
+      double a[MI], b[NI];
 #pragma unroll
-      for (int q = 0; q < 8; q++) a[q] = sA[kk][ty + 16 * q];       // two addresses per warp: broadcast
+      for (int q = 0; q < MI; q++) a[q] = sA[kk][ty + 16 * q];       // two addresses per warp: broadcast
 #pragma unroll
-      for (int q = 0; q < 4; q++) b[q] = sB[kk][tx + 16 * q];       // 16 consecutive doubles: conflict-free
+      for (int q = 0; q < NI; q++) b[q] = sB[kk][tx + 16 * q];       // 16 consecutive doubles: conflict-free
 #pragma unroll
-      for (int p = 0; p < 8; p++)
+      for (int p = 0; p < MI; p++)
 #pragma unroll
-        for (int q = 0; q < 4; q++) acc[p][q] += a[p] * b[q];
+        for (int q = 0; q < NI; q++) acc[p][q] += a[p] * b[q];
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int p = 0; p < 8; p++) {
+  for (int p = 0; p < MI; p++) {
     const int i = i0 + ty + 16 * p;
     if (i >= g) continue;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < NI; q++) {
       const size_t o = (size_t)i * g + j0 + tx + 16 * q;
       Cb[o] = (beta == 0.0 ? 0.0 : beta * Cb[o]) + alpha * acc[p][q];
     }
   }
+}
+
+// picks the tile so that small batches (upper reduction levels) still fill the GPU
+static void launch_bgemm(cudaStream_t st, int items, int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha,
+                         double beta) {
+  if (items <= 0) return;
+  const long long big = (long long)items * ((g + 127) / 128) * (g / 64), mid = (long long)items * (g / 64) * (g / 64);
+  if (big >= 296) k_bgemm<8, 4><<<dim3(g / 64, (g + 127) / 128, items), 256, 0, st>>>(g, K, s, kept, A, B, C, alpha, beta);
+  else if (mid >= 296) k_bgemm<4, 4><<<dim3(g / 64, g / 64, items), 256, 0, st>>>(g, K, s, kept, A, B, C, alpha, beta);
+  else k_bgemm<2, 2><<<dim3(g / 32, g / 32, items), 256, 0, st>>>(g, K, s, kept, A, B, C, alpha, beta);
+  g_launch_count++;
 }
 
 // zero the blocks of a level's items (for outputs whose producing GEMM may be skipped)
@@ -206,59 +219,60 @@ __global__ void k_bzero(int g, int K, int s, int kept, Opnd C) {
 // For pivot block P:  Ipp = inv(A_PP);  A_PJ <- Ipp A_PJ (J != P);  A_IJ <- A_IJ - A_IP A_PJ
 // (I,J != P);  A_IP <- -A_IP Ipp;  A_PP <- Ipp.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_gjb_pivot(int g, int s, int b, const double *__restrict__ D, double *__restrict__ ipp) {
-  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
-  __shared__ double S[NB][NB + 1], I2[NB][NB + 1];
-  __shared__ int piv_row;
-  const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
-  const double *A = D + (size_t)node * g * g + (size_t)(b * NB) * g + b * NB;
-  S[i][j] = A[(size_t)i * g + j];
+// 32 x 32 inverse in shared memory by 1024 threads (i, j): Gauss-Jordan on [S | I2] with partial
+// pivoting tracked as a row permutation (no physical swaps, three barriers per pivot).  On return
+// Ip = S^-1.  The inverse is unique, so the pivoting leaves no trace outside this routine.
+__device__ __forceinline__ void invert32(double (*S)[NB + 1], double (*I2)[NB + 1], double (*Ip)[NB + 1], int *perm,
+                                         int i, int j) {
   I2[i][j] = (i == j) ? 1.0 : 0.0;
+  if (i == 0) perm[j] = j;
   __syncthreads();
   for (int p = 0; p < NB; p++) {
-    if (i == 0) {                       // warp 0: arg max |S[r][p]|, r >= p
-      double v = (j >= p) ? fabs(S[j][p]) : -1.0;
+    if (i == 0) {                       // warp 0: arg max over logical rows r >= p of |S[perm[r]][p]|
+      double v = (j >= p) ? fabs(S[perm[j]][p]) : -1.0;
       int r = j;
       for (int o = 16; o > 0; o >>= 1) {
         const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
         const int r2 = __shfl_xor_sync(0xffffffffu, r, o);
         if (v2 > v || (v2 == v && r2 < r)) { v = v2; r = r2; }
       }
-      if (j == 0) piv_row = r;
+      if (j == 0) { const int t = perm[p]; perm[p] = perm[r]; perm[r] = t; }
     }
     __syncthreads();
-    const int pr = piv_row;
-    const bool sw = pr != p && (i == p || i == pr);  // swap rows p <-> pr: read, barrier, write
-    double a = 0.0, c = 0.0;
-    if (sw) { const int other = (i == p) ? pr : p; a = S[other][j]; c = I2[other][j]; }
-    __syncthreads();
-    if (sw) { S[i][j] = a; I2[i][j] = c; }
-    __syncthreads();
-    double piv = S[p][p];
+    const int P = perm[p];              // physical pivot row
+    double piv = S[P][p];
     if (fabs(piv) < 1e-13) piv = piv < 0.0 ? -1e-13 : 1e-13;      // static perturbation
     const double d = 1.0 / piv;
     const double f = S[i][p];
-    const double sp = S[p][j] * d, ip = I2[p][j] * d;
+    const double sp = S[P][j] * d, ip = I2[P][j] * d;
     __syncthreads();
-    if (i == p) { S[i][j] = sp; I2[i][j] = ip; }
+    if (i == P) { S[i][j] = sp; I2[i][j] = ip; }
     else { S[i][j] -= f * sp; I2[i][j] -= f * ip; }
     __syncthreads();
   }
-  ipp[(size_t)z * NB * NB + i * NB + j] = I2[i][j];
+  Ip[i][j] = I2[perm[i]][j];
+  __syncthreads();
 }
 
-// y = 0: row panel tiles (J = blockIdx.x);  y = 1: column panel tiles (I = blockIdx.x)
+// Panel step for pivot block b.  Every CTA inverts A_PP itself (redundant, but it removes a
+// serial launch from the critical path), then  y = 0: row panel tile (P, J = blockIdx.x):
+// A_PJ <- Ipp A_PJ;  y = 1: column panel tile (I = blockIdx.x, P): colbuf <- A_IP (old),
+// A_IP <- -A_IP Ipp.  A_PP itself is left untouched here (other CTAs are reading it); the
+// CTA (y = 0, J = b) stores Ipp to `ipp` and the update kernel copies it into place.
 __global__ void __launch_bounds__(1024)
-k_gjb_panel(int g, int s, int b, double *__restrict__ D, const double *__restrict__ ipp, double *__restrict__ colbuf) {
+k_gjb_panel(int g, int s, int b, double *__restrict__ D, double *__restrict__ ipp, double *__restrict__ colbuf) {
   const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
-  __shared__ double X[NB][NB + 1], Ip[NB][NB + 1];
+  __shared__ double X[NB][NB + 1], Ip[NB][NB + 1], W1[NB][NB + 1], W2[NB][NB + 1];
+  __shared__ int perm[NB];
   const int j = threadIdx.x & 31, i = threadIdx.x >> 5, q = blockIdx.x;
+  if (blockIdx.y == 1 && q == b) return;
   double *A = D + (size_t)node * g * g;
-  Ip[i][j] = ipp[(size_t)z * NB * NB + i * NB + j];
+  W1[i][j] = A[(size_t)(b * NB + i) * g + b * NB + j];
+  __syncthreads();
+  invert32(W1, W2, Ip, perm, i, j);
   if (blockIdx.y == 0) {
+    if (q == b) { ipp[(size_t)z * NB * NB + i * NB + j] = Ip[i][j]; return; }
     double *T = A + (size_t)(b * NB) * g + q * NB;             // tile (P, J=q)
-    if (q == b) { T[(size_t)i * g + j] = Ip[i][j]; return; }
     X[i][j] = T[(size_t)i * g + j];
     __syncthreads();
     double sum = 0.0;
@@ -266,7 +280,6 @@ k_gjb_panel(int g, int s, int b, double *__restrict__ D, const double *__restric
     for (int k = 0; k < NB; k++) sum += Ip[i][k] * X[k][j];
     T[(size_t)i * g + j] = sum;
   } else {
-    if (q == b) return;
     double *T = A + (size_t)(q * NB) * g + b * NB;             // tile (I=q, P)
     X[i][j] = T[(size_t)i * g + j];
     colbuf[((size_t)z * g + q * NB + i) * NB + j] = X[i][j];   // old A_IP for the trailing update
@@ -280,7 +293,8 @@ k_gjb_panel(int g, int s, int b, double *__restrict__ D, const double *__restric
 
 // trailing update, 64 x 64 tile per CTA (256 threads, 4 x 4 micro-tile), inner dimension 32
 __global__ void __launch_bounds__(256)
-k_gjb_update(int g, int s, int b, double *__restrict__ D, const double *__restrict__ colbuf) {
+k_gjb_update(int g, int s, int b, double *__restrict__ D, const double *__restrict__ colbuf,
+             const double *__restrict__ ipp) {
   const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
   __shared__ double Cb[GT][NB + 1], R[NB][GT + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -293,6 +307,9 @@ k_gjb_update(int g, int s, int b, double *__restrict__ D, const double *__restri
     R[k2][jj] = A[(size_t)(b * NB + k2) * g + j0 + jj];
   }
   __syncthreads();
+  if ((int)blockIdx.y == (b * NB) / GT && (int)blockIdx.x == (b * NB) / GT)       // A_PP <- Ipp
+    for (int q = threadIdx.x; q < NB * NB; q += 256)
+      A[(size_t)(b * NB + q / NB) * g + b * NB + q % NB] = ipp[(size_t)z * NB * NB + q];
   double acc[4][4] = {};
 #pragma unroll
   for (int kk = 0; kk < NB; kk++) {
@@ -458,29 +475,25 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
     double *L = pc->Lc[cur], *U = pc->Uc[cur], *L2 = pc->Lc[cur ^ 1], *U2 = pc->Uc[cur ^ 1];
     // eliminated nodes: Dinv (in place), P = Dinv L, Q = Dinv U
     for (int b = 0; b < nbk; b++) {
-      k_gjb_pivot<<<dim3(1, 1, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp);
       k_gjb_panel<<<dim3(nbk, 2, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp, pc->colbuf);
-      k_gjb_update<<<dim3(nt, nt, lv.nE), 256, 0, st>>>(g, s, b, pc->D, pc->colbuf);
+      k_gjb_update<<<dim3(nt, nt, lv.nE), 256, 0, st>>>(g, s, b, pc->D, pc->colbuf, pc->ipp);
     }
-    g_launch_count += 3 * nbk;
-    const int ntm = (g + TM - 1) / TM;
-    const dim3 gE(nt, ntm, lv.nE), gK(nt, ntm, lv.nK > 0 ? lv.nK : 1);
+    g_launch_count += 2 * nbk;
     const Opnd Dn{pc->D, 0, 0}, Ln{L, 0, 0}, Un{U, 0, 0}, Pn{pc->Pm, 0, 0}, Qn{pc->Qm, 0, 0};
-    k_bgemm<<<gE, 256, 0, st>>>(g, K, s, 0, Dn, Ln, Pn, 1.0, 0.0);
-    k_bgemm<<<gE, 256, 0, st>>>(g, K, s, 0, Dn, Un, Qn, 1.0, 0.0);
-    g_launch_count += 2;
+    launch_bgemm(st, lv.nE, g, K, s, 0, Dn, Ln, Pn, 1.0, 0.0);
+    launch_bgemm(st, lv.nE, g, K, s, 0, Dn, Un, Qn, 1.0, 0.0);
     if (lv.nK > 0) {
       const Opnd Da{pc->D, 0, -s}, Db{pc->D, 0, s}, Pa{pc->Pm, 0, -s}, Pb{pc->Pm, 0, s}, Qa{pc->Qm, 0, -s}, Qb{pc->Qm, 0, s};
       const Opnd As{pc->AL, 1, lv.slot0}, Bs{pc->BL, 1, lv.slot0}, L2n{L2, 0, 0}, U2n{U2, 0, 0};
-      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Ln, Da, As, 1.0, 0.0);        // A_i = L_i Dinv_a
-      k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, Bs);          // right neighbour may not exist
-      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Un, Db, Bs, 1.0, 0.0);        // B_i = U_i Dinv_b
-      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Ln, Qa, Dn, -1.0, 1.0);       // D_i -= L_i Q_a
-      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Un, Pb, Dn, -1.0, 1.0);       // D_i -= U_i P_b
-      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Ln, Pa, L2n, -1.0, 0.0);      // L_i' = -L_i P_a
+      launch_bgemm(st, lv.nK, g, K, s, 1, Ln, Da, As, 1.0, 0.0);        // A_i = L_i Dinv_a
+      k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, Bs);      // right neighbour may not exist
+      launch_bgemm(st, lv.nK, g, K, s, 1, Un, Db, Bs, 1.0, 0.0);        // B_i = U_i Dinv_b
+      launch_bgemm(st, lv.nK, g, K, s, 1, Ln, Qa, Dn, -1.0, 1.0);       // D_i -= L_i Q_a
+      launch_bgemm(st, lv.nK, g, K, s, 1, Un, Pb, Dn, -1.0, 1.0);       // D_i -= U_i P_b
+      launch_bgemm(st, lv.nK, g, K, s, 1, Ln, Pa, L2n, -1.0, 0.0);      // L_i' = -L_i P_a
       k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, U2n);
-      k_bgemm<<<gK, 256, 0, st>>>(g, K, s, 1, Un, Qb, U2n, -1.0, 0.0);      // U_i' = -U_i Q_b
-      g_launch_count += 8;
+      launch_bgemm(st, lv.nK, g, K, s, 1, Un, Qb, U2n, -1.0, 0.0);      // U_i' = -U_i Q_b
+      g_launch_count += 2;
     }
     if (cudaGetLastError() != cudaSuccess) { ufe_set_error("bjacobi_lu factorisation launch failed"); return UFE_ERR_CUDA; }
     cur ^= 1;
