@@ -11,11 +11,11 @@
 // i_q = (q+1) 2^l - 1; the even positions q are eliminated, the odd ones kept,
 //   eliminated j :  Dinv_j = D_j^-1,  P_j = Dinv_j L_j,  Q_j = Dinv_j U_j
 //   kept i (a = i - 2^l, b = i + 2^l):
-//        A_i = L_i Dinv_a,  B_i = U_i Dinv_b            (kept for the solve, one slot per level)
-//        D_i <- D_i - L_i Q_a - U_i P_b,  L_i <- -L_i P_a,  U_i <- -U_i Q_b
+//        D_i <- D_i - L_i Q_a - U_i P_b,   L_i' = -L_i P_a,   U_i' = -U_i Q_b   (next level's couplings)
 // so every level is a handful of batched dense launches over all its nodes (log2 K levels in
-// all), and applying the preconditioner is 2 log2 K batched GEMV launches:
-//   down:  r_i <- r_i - A_i r_a - B_i r_b        up:  x_j = Dinv_j r_j - P_j x_{j-s} - Q_j x_{j+s}.
+// all; the couplings L, U of every level are kept), and applying the preconditioner is
+// 3 log2 K batched GEMV launches:
+//   down:  y_j = Dinv_j r_j,   r_i <- r_i - L_i y_a - U_i y_b        up:  x_j = y_j - P_j x_{j-s} - Q_j x_{j+s}.
 // With one GPU the preconditioner is the exact inverse (the Krylov loop then converges in one or
 // two steps and acts as iterative refinement); with several GPUs it is block Jacobi over the
 // ranks' strips (couplings to other ranks' columns are dropped).
@@ -29,15 +29,14 @@
 #define GK 16
 #define NB 32          // Gauss-Jordan panel width
 
-struct PcLevel { int s, n, nE, nK, slot0; };
+struct PcLevel { int s, n, nE, nK, base; };    // base: first slot of this level's couplings in LS / US
 
 struct PcLU {
   int n_loc = 0, g = 0, K = 0;
   std::vector<PcLevel> lev;
   double *D = nullptr;                       // K blocks: D_i, overwritten by Dinv_i when i is eliminated
-  double *Lc[2] = {nullptr, nullptr}, *Uc[2] = {nullptr, nullptr};   // couplings of the current level (ping-pong)
+  double *LS = nullptr, *US = nullptr;       // couplings of the active nodes of every level: slot base_l + position (< 2K slots)
   double *Pm = nullptr, *Qm = nullptr;       // K blocks, per eliminated node
-  double *AL = nullptr, *BL = nullptr;       // one block per kept node per level (<= K slots)
   double *ipp = nullptr, *colbuf = nullptr;  // Gauss-Jordan scratch: [items][32*32], [items][g][32]
   double *c = nullptr;                       // 2*K*g work vectors (rhs -> solution, staging)
   size_t bytes = 0;
@@ -45,10 +44,12 @@ struct PcLU {
 
 // operand addressing for the batched kernels: item z of a level works on node
 //   node(z) = (2z + 1 + kept) * s - 1 ;   operand block = node + off   (mode 0)
-//                                                        = off + z      (mode 1, slot arrays)
+//                                                        = off + z      (mode 1: next level's slot)
+//                                                        = off + 2z     (mode 2: this level's slot)
 struct Opnd { const double *p; int mode, off; };
 __device__ __forceinline__ long long opnd_block(const Opnd &o, int node, int z, int K) {
   if (o.mode == 1) return o.off + z;
+  if (o.mode == 2) return o.off + 2 * z;
   const int b = node + o.off;
   return (b < 0 || b >= K) ? -1 : b;
 }
@@ -254,24 +255,31 @@ __device__ __forceinline__ void invert32(double (*S)[NB + 1], double (*I2)[NB + 
   __syncthreads();
 }
 
-// Panel step for pivot block b.  Every CTA inverts A_PP itself (redundant, but it removes a
-// serial launch from the critical path), then  y = 0: row panel tile (P, J = blockIdx.x):
-// A_PJ <- Ipp A_PJ;  y = 1: column panel tile (I = blockIdx.x, P): colbuf <- A_IP (old),
-// A_IP <- -A_IP Ipp.  A_PP itself is left untouched here (other CTAs are reading it); the
-// CTA (y = 0, J = b) stores Ipp to `ipp` and the update kernel copies it into place.
+// pivot block inverse, one CTA per eliminated node: ipp <- inv(A_PP)
 __global__ void __launch_bounds__(1024)
-k_gjb_panel(int g, int s, int b, double *__restrict__ D, double *__restrict__ ipp, double *__restrict__ colbuf) {
+k_gjb_pivot(int g, int s, int b, const double *__restrict__ D, double *__restrict__ ipp) {
   const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
-  __shared__ double X[NB][NB + 1], Ip[NB][NB + 1], W1[NB][NB + 1], W2[NB][NB + 1];
+  __shared__ double W1[NB][NB + 1], W2[NB][NB + 1], Ip[NB][NB + 1];
   __shared__ int perm[NB];
-  const int j = threadIdx.x & 31, i = threadIdx.x >> 5, q = blockIdx.x;
-  if (blockIdx.y == 1 && q == b) return;
-  double *A = D + (size_t)node * g * g;
-  W1[i][j] = A[(size_t)(b * NB + i) * g + b * NB + j];
+  const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
+  W1[i][j] = D[(size_t)node * g * g + (size_t)(b * NB + i) * g + b * NB + j];
   __syncthreads();
   invert32(W1, W2, Ip, perm, i, j);
+  ipp[(size_t)z * NB * NB + i * NB + j] = Ip[i][j];
+}
+
+// Panel step for pivot block b:  y = 0: row panel tile (P, J = blockIdx.x): A_PJ <- Ipp A_PJ;
+// y = 1: column panel tile (I = blockIdx.x, P): colbuf <- A_IP (old), A_IP <- -A_IP Ipp.
+// A_PP itself is replaced by Ipp in the update kernel.
+__global__ void __launch_bounds__(1024)
+k_gjb_panel(int g, int s, int b, double *__restrict__ D, const double *__restrict__ ipp, double *__restrict__ colbuf) {
+  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
+  __shared__ double X[NB][NB + 1], Ip[NB][NB + 1];
+  const int j = threadIdx.x & 31, i = threadIdx.x >> 5, q = blockIdx.x;
+  if (q == b) return;
+  double *A = D + (size_t)node * g * g;
+  Ip[i][j] = ipp[(size_t)z * NB * NB + i * NB + j];
   if (blockIdx.y == 0) {
-    if (q == b) { ipp[(size_t)z * NB * NB + i * NB + j] = Ip[i][j]; return; }
     double *T = A + (size_t)(b * NB) * g + q * NB;             // tile (P, J=q)
     X[i][j] = T[(size_t)i * g + j];
     __syncthreads();
@@ -337,55 +345,62 @@ k_gjb_update(int g, int s, int b, double *__restrict__ D, const double *__restri
 // ------------------------------------------------------------------------------------
 // solve kernels: one warp per row of a g x g block
 // ------------------------------------------------------------------------------------
-// down sweep, kept nodes:  r_i <- r_i - A_i r_{i-s} - B_i r_{i+s}
+// y_j = Dinv_j r_j for the eliminated nodes of a level
 __global__ void __launch_bounds__(256)
-k_bcr_down(int g, int K, int s, int slot0, const double *__restrict__ AL, const double *__restrict__ BL,
-           double *__restrict__ c) {
+k_bcr_y(int g, int s, const double *__restrict__ D, const double *__restrict__ c, double *__restrict__ y) {
+  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= g) return;
+  const double *Mr = D + (size_t)node * g * g + (size_t)row * g, *r = c + (size_t)node * g;
+  double sum = 0.0;
+  for (int j = lane; j < g; j += 32) sum += Mr[j] * r[j];
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+  if (lane == 0) y[(size_t)node * g + row] = sum;
+}
+
+// down sweep, kept nodes:  r_i <- r_i - L_i y_{i-s} - U_i y_{i+s}
+__global__ void __launch_bounds__(256)
+k_bcr_down(int g, int K, int s, int base, const double *__restrict__ LS, const double *__restrict__ US,
+           const double *__restrict__ y, double *__restrict__ c) {
   const int z = blockIdx.z, node = (2 * z + 2) * s - 1;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= g) return;
-  const size_t mo = (size_t)(slot0 + z) * g * g + (size_t)row * g;
-  const double *xa = c + (size_t)(node - s) * g;
+  const size_t mo = (size_t)(base + 2 * z + 1) * g * g + (size_t)row * g;
+  const double *ya = y + (size_t)(node - s) * g;
   const bool hasb = node + s < K;
-  const double *xb = c + (size_t)(hasb ? node + s : node) * g;
+  const double *yb = y + (size_t)(hasb ? node + s : node) * g;
   double sum = 0.0;
   for (int j = lane; j < g; j += 32) {
-    sum += AL[mo + j] * xa[j];
-    if (hasb) sum += BL[mo + j] * xb[j];
+    sum += LS[mo + j] * ya[j];
+    if (hasb) sum += US[mo + j] * yb[j];
   }
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
   if (lane == 0) c[(size_t)node * g + row] -= sum;
 }
 
-// up sweep, eliminated nodes:  x_j = Dinv_j r_j - P_j x_{j-s} - Q_j x_{j+s}   (out of place: xo)
+// up sweep, eliminated nodes:  x_j = y_j - P_j x_{j-s} - Q_j x_{j+s}   (solutions live in c)
 __global__ void __launch_bounds__(256)
-k_bcr_up(int g, int K, int s, const double *__restrict__ D, const double *__restrict__ Pm,
-         const double *__restrict__ Qm, const double *__restrict__ c, double *__restrict__ xo) {
+k_bcr_up(int g, int K, int s, const double *__restrict__ Pm, const double *__restrict__ Qm,
+         const double *__restrict__ y, double *__restrict__ c) {
   const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= g) return;
   const size_t mo = (size_t)node * g * g + (size_t)row * g;
   const bool hasa = node - s >= 0, hasb = node + s < K;
-  const double *r = c + (size_t)node * g, *xa = c + (size_t)(hasa ? node - s : node) * g,
-               *xb = c + (size_t)(hasb ? node + s : node) * g;
+  const double *xa = c + (size_t)(hasa ? node - s : node) * g, *xb = c + (size_t)(hasb ? node + s : node) * g;
   double sum = 0.0;
-  for (int j = lane; j < g; j += 32) {
-    sum += D[mo + j] * r[j];
-    if (hasa) sum -= Pm[mo + j] * xa[j];
-    if (hasb) sum -= Qm[mo + j] * xb[j];
-  }
+  if (hasa || hasb)
+    for (int j = lane; j < g; j += 32) {
+      if (hasa) sum += Pm[mo + j] * xa[j];
+      if (hasb) sum += Qm[mo + j] * xb[j];
+    }
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-  if (lane == 0) xo[(size_t)node * g + row] = sum;
+  if (lane == 0) c[(size_t)node * g + row] = y[(size_t)node * g + row] - sum;
 }
 
 __global__ void k_vec_in(int n, int total, const double *__restrict__ r, double *__restrict__ c) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) c[i] = i < n ? r[i] : 0.0;
-}
-__global__ void k_vec_level(int g, int s, const double *__restrict__ src, double *__restrict__ dst) {
-  const int node = (2 * blockIdx.z + 1) * s - 1;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < g) dst[(size_t)node * g + i] = src[(size_t)node * g + i];
 }
 __global__ void k_vec_out(int n, const double *__restrict__ c, double *__restrict__ z) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,8 +412,7 @@ __global__ void k_vec_out(int n, const double *__restrict__ c, double *__restric
 // ------------------------------------------------------------------------------------
 void ufe_pclu_free(PcLU *pc) {
   if (!pc) return;
-  cudaFree(pc->D); cudaFree(pc->Lc[0]); cudaFree(pc->Lc[1]); cudaFree(pc->Uc[0]); cudaFree(pc->Uc[1]);
-  cudaFree(pc->Pm); cudaFree(pc->Qm); cudaFree(pc->AL); cudaFree(pc->BL);
+  cudaFree(pc->D); cudaFree(pc->LS); cudaFree(pc->US); cudaFree(pc->Pm); cudaFree(pc->Qm);
   cudaFree(pc->ipp); cudaFree(pc->colbuf); cudaFree(pc->c);
   delete pc;
 }
@@ -427,16 +441,16 @@ int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int /*segments: reserved
   int slots = 0, maxE = 0;
   for (int s = 1;; s *= 2) {
     PcLevel lv;
-    lv.s = s; lv.n = pc->K / s; lv.nE = (lv.n + 1) / 2; lv.nK = lv.n / 2; lv.slot0 = slots;
+    lv.s = s; lv.n = pc->K / s; lv.nE = (lv.n + 1) / 2; lv.nK = lv.n / 2; lv.base = slots;
     if (lv.n < 1) break;
-    slots += lv.nK;
+    slots += lv.n;
     if (lv.nE > maxE) maxE = lv.nE;
     pc->lev.push_back(lv);
     if (lv.n == 1) break;
   }
   const size_t gg = (size_t)g * g, blk = gg * pc->K * sizeof(double);
   const size_t slot_bytes = gg * (slots > 0 ? slots : 1) * sizeof(double);
-  pc->bytes = 7 * blk + 2 * slot_bytes;
+  pc->bytes = 3 * blk + 2 * slot_bytes;
   if (pc->bytes > max_bytes) {
     ufe_set_error("bjacobi_lu preconditioner needs %.1f GB (bandwidth %d -> dense block %d, %d blocks) which exceeds the %.1f GB budget; "
                   "use 'bjacobi2' or 'jacobi' for this mesh", pc->bytes / 1e9, bw, g, pc->K, max_bytes / 1e9);
@@ -444,10 +458,9 @@ int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int /*segments: reserved
     return UFE_ERR_INVALID;
   }
   UFE_CUDA(cudaMalloc(&pc->D, blk));
-  for (int q = 0; q < 2; q++) { UFE_CUDA(cudaMalloc(&pc->Lc[q], blk)); UFE_CUDA(cudaMalloc(&pc->Uc[q], blk)); }
   UFE_CUDA(cudaMalloc(&pc->Pm, blk)); UFE_CUDA(cudaMalloc(&pc->Qm, blk));
-  UFE_CUDA(cudaMalloc(&pc->AL, slot_bytes));
-  UFE_CUDA(cudaMalloc(&pc->BL, slot_bytes));
+  UFE_CUDA(cudaMalloc(&pc->LS, slot_bytes));
+  UFE_CUDA(cudaMalloc(&pc->US, slot_bytes));
   UFE_CUDA(cudaMalloc(&pc->ipp, sizeof(double) * (size_t)maxE * NB * NB));
   UFE_CUDA(cudaMalloc(&pc->colbuf, sizeof(double) * (size_t)maxE * g * NB));
   UFE_CUDA(cudaMalloc(&pc->c, sizeof(double) * (size_t)pc->K * g * 2));
@@ -459,44 +472,43 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
   const int g = pc->g, K = pc->K;
   const size_t blk = (size_t)g * g * K * sizeof(double);
   UFE_CUDA(cudaMemsetAsync(pc->D, 0, blk, st));
-  UFE_CUDA(cudaMemsetAsync(pc->Lc[0], 0, blk, st));
-  UFE_CUDA(cudaMemsetAsync(pc->Uc[0], 0, blk, st));
+  UFE_CUDA(cudaMemsetAsync(pc->LS, 0, blk, st));      // level 0 occupies the first K slots (slot = node)
+  UFE_CUDA(cudaMemsetAsync(pc->US, 0, blk, st));
   if (S.bell_val)
     k_bell_to_blocks<<<ufe_div_up((long long)S.nslices * 32, 256), 256, 0, st>>>(S.m_loc / 2, (S.r1 - 1) / 2, S.nslices, S.bell_off, S.bell_col,
-                                                                                 S.bell_val, g, pc->D, pc->Lc[0], pc->Uc[0]);
+                                                                                 S.bell_val, g, pc->D, pc->LS, pc->US);
   else
-    k_csr_to_blocks<<<ufe_div_up(S.m_loc, 256), 256, 0, st>>>(S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, g, pc->D, pc->Lc[0], pc->Uc[0], nullptr);
+    k_csr_to_blocks<<<ufe_div_up(S.m_loc, 256), 256, 0, st>>>(S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, g, pc->D, pc->LS, pc->US, nullptr);
   UFE_LAUNCH_CHECK();
   if (K * g > pc->n_loc) { k_pad_identity<<<ufe_div_up(K * g - pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, g, K, pc->D); UFE_LAUNCH_CHECK(); }
   const int nbk = g / NB, nt = g / GT;
-  int cur = 0;
-  for (const PcLevel &lv : pc->lev) {
+  for (size_t l = 0; l < pc->lev.size(); l++) {
+    const PcLevel &lv = pc->lev[l];
     const int s = lv.s;
-    double *L = pc->Lc[cur], *U = pc->Uc[cur], *L2 = pc->Lc[cur ^ 1], *U2 = pc->Uc[cur ^ 1];
     // eliminated nodes: Dinv (in place), P = Dinv L, Q = Dinv U
     for (int b = 0; b < nbk; b++) {
+      k_gjb_pivot<<<dim3(1, 1, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp);
       k_gjb_panel<<<dim3(nbk, 2, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp, pc->colbuf);
       k_gjb_update<<<dim3(nt, nt, lv.nE), 256, 0, st>>>(g, s, b, pc->D, pc->colbuf, pc->ipp);
     }
-    g_launch_count += 2 * nbk;
-    const Opnd Dn{pc->D, 0, 0}, Ln{L, 0, 0}, Un{U, 0, 0}, Pn{pc->Pm, 0, 0}, Qn{pc->Qm, 0, 0};
-    launch_bgemm(st, lv.nE, g, K, s, 0, Dn, Ln, Pn, 1.0, 0.0);
-    launch_bgemm(st, lv.nE, g, K, s, 0, Dn, Un, Qn, 1.0, 0.0);
+    g_launch_count += 3 * nbk;
+    const Opnd Dn{pc->D, 0, 0}, Pn{pc->Pm, 0, 0}, Qn{pc->Qm, 0, 0};
+    const Opnd Le{pc->LS, 2, lv.base}, Ue{pc->US, 2, lv.base};               // this level, eliminated (position 2z)
+    launch_bgemm(st, lv.nE, g, K, s, 0, Dn, Le, Pn, 1.0, 0.0);
+    launch_bgemm(st, lv.nE, g, K, s, 0, Dn, Ue, Qn, 1.0, 0.0);
     if (lv.nK > 0) {
-      const Opnd Da{pc->D, 0, -s}, Db{pc->D, 0, s}, Pa{pc->Pm, 0, -s}, Pb{pc->Pm, 0, s}, Qa{pc->Qm, 0, -s}, Qb{pc->Qm, 0, s};
-      const Opnd As{pc->AL, 1, lv.slot0}, Bs{pc->BL, 1, lv.slot0}, L2n{L2, 0, 0}, U2n{U2, 0, 0};
-      launch_bgemm(st, lv.nK, g, K, s, 1, Ln, Da, As, 1.0, 0.0);        // A_i = L_i Dinv_a
-      k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, Bs);      // right neighbour may not exist
-      launch_bgemm(st, lv.nK, g, K, s, 1, Un, Db, Bs, 1.0, 0.0);        // B_i = U_i Dinv_b
-      launch_bgemm(st, lv.nK, g, K, s, 1, Ln, Qa, Dn, -1.0, 1.0);       // D_i -= L_i Q_a
-      launch_bgemm(st, lv.nK, g, K, s, 1, Un, Pb, Dn, -1.0, 1.0);       // D_i -= U_i P_b
-      launch_bgemm(st, lv.nK, g, K, s, 1, Ln, Pa, L2n, -1.0, 0.0);      // L_i' = -L_i P_a
-      k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, U2n);
-      launch_bgemm(st, lv.nK, g, K, s, 1, Un, Qb, U2n, -1.0, 0.0);      // U_i' = -U_i Q_b
-      g_launch_count += 2;
+      const int nbase = pc->lev[l + 1].base;
+      const Opnd Lk{pc->LS, 2, lv.base + 1}, Uk{pc->US, 2, lv.base + 1};     // this level, kept (position 2z+1)
+      const Opnd Pa{pc->Pm, 0, -s}, Pb{pc->Pm, 0, s}, Qa{pc->Qm, 0, -s}, Qb{pc->Qm, 0, s};
+      const Opnd L2n{pc->LS, 1, nbase}, U2n{pc->US, 1, nbase};               // next level (position z)
+      launch_bgemm(st, lv.nK, g, K, s, 1, Lk, Qa, Dn, -1.0, 1.0);       // D_i -= L_i Q_a
+      launch_bgemm(st, lv.nK, g, K, s, 1, Uk, Pb, Dn, -1.0, 1.0);       // D_i -= U_i P_b
+      launch_bgemm(st, lv.nK, g, K, s, 1, Lk, Pa, L2n, -1.0, 0.0);      // L_i' = -L_i P_a
+      k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, U2n);     // right neighbour may not exist
+      launch_bgemm(st, lv.nK, g, K, s, 1, Uk, Qb, U2n, -1.0, 0.0);      // U_i' = -U_i Q_b
+      g_launch_count += 1;
     }
     if (cudaGetLastError() != cudaSuccess) { ufe_set_error("bjacobi_lu factorisation launch failed"); return UFE_ERR_CUDA; }
-    cur ^= 1;
   }
   return UFE_OK;
 }
@@ -504,20 +516,18 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
 // z = M^-1 r  (r, z owned-length vectors; may alias)
 int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z) {
   const int g = pc->g, K = pc->K, total = K * g;
-  double *c = pc->c, *x = pc->c + total;
+  double *c = pc->c, *y = pc->c + total;
   k_vec_in<<<ufe_div_up(total, 256), 256, 0, st>>>(pc->n_loc, total, r, c);
   UFE_LAUNCH_CHECK();
   for (const PcLevel &lv : pc->lev) {
-    if (lv.nK == 0) continue;
-    k_bcr_down<<<dim3(g / 8, 1, lv.nK), 256, 0, st>>>(g, K, lv.s, lv.slot0, pc->AL, pc->BL, c);
-    UFE_LAUNCH_CHECK();
+    k_bcr_y<<<dim3(g / 8, 1, lv.nE), 256, 0, st>>>(g, lv.s, pc->D, c, y);
+    if (lv.nK > 0) k_bcr_down<<<dim3(g / 8, 1, lv.nK), 256, 0, st>>>(g, K, lv.s, lv.base, pc->LS, pc->US, y, c);
+    g_launch_count += lv.nK > 0 ? 2 : 1;
   }
   for (int l = (int)pc->lev.size() - 1; l >= 0; l--) {
     const PcLevel &lv = pc->lev[l];
-    // x_j from r_j and the already solved neighbours (c is overwritten level by level)
-    k_bcr_up<<<dim3(g / 8, 1, lv.nE), 256, 0, st>>>(g, K, lv.s, pc->D, pc->Pm, pc->Qm, c, x);
-    k_vec_level<<<dim3(ufe_div_up(g, 256), 1, lv.nE), 256, 0, st>>>(g, lv.s, x, c);
-    g_launch_count += 2;
+    k_bcr_up<<<dim3(g / 8, 1, lv.nE), 256, 0, st>>>(g, K, lv.s, pc->Pm, pc->Qm, y, c);
+    g_launch_count++;
   }
   if (cudaGetLastError() != cudaSuccess) { ufe_set_error("bjacobi_lu apply launch failed"); return UFE_ERR_CUDA; }
   k_vec_out<<<ufe_div_up(pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, c, z);
