@@ -141,7 +141,7 @@ _PINNED = []
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_kspmv_bell launch on the 1 M-vertex mesh (one GPU),
 # from the committed ncu capture profiles/r1_kspmv_bell_ncu_full_summary.txt
-NCU_TRAFFIC_BYTES_1M = None
+NCU_TRAFFIC_BYTES_1M = 745554944   # k_kspmv_bell<1,4>: 711.08 MB read + 34.48 MB written (0.79 x the algorithmic 939.3 MB)
 
 
 def cpu_reference_leg(mesh, C, ice, seconds, n_visc_full=None):
