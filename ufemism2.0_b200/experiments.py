@@ -77,7 +77,7 @@ def MISMIP_8km(h=8e3, seed=synthetic.SEED):
     return mesh, C, ice
 
 
-def MISMIPplus(h=2e3, seed=synthetic.SEED):
+def MISMIPplus(h=2e3, seed=synthetic.SEED, calving_front=None):
     """config-files/benchmarks/MISMIP+/config_MISMIPplus_2km_spinup.cfg: 800x80 km,
     Schoof2005 (alpha^2 = 0.5, beta^2 = 1e4), A = 1.428e-17, Picard 5e-5 / 50 / relax 0.2,
     Krylov 1e-7 / 1e-5, BC u: west zero, others infinite; v: zero everywhere.  Uniform
@@ -85,7 +85,7 @@ def MISMIPplus(h=2e3, seed=synthetic.SEED):
     nx = int(round(800e3 / h)) + 1
     ny = int(round(80e3 / h)) + 1
     mesh = synthetic.lattice_mesh(0.0, 800e3, -40e3, 40e3, nx, ny, seed=seed)
-    ice = synthetic.geometry_MISMIPplus(mesh)
+    ice = synthetic.geometry_MISMIPplus(mesh, calving_front=calving_front)
     C = Config(visc_it_norm_dUV_tol=5e-5, visc_it_nit=50, visc_it_relax=0.2,
                stress_balance_PETSc_rtol=1e-7, stress_balance_PETSc_abstol=1e-5,
                choice_sliding_law="Schoof2005", choice_ice_rheology_Glen="uniform",

@@ -188,9 +188,15 @@ def mismipplus_bed(x, y):
     return np.maximum(Bx + By, zbdeep)
 
 
-def geometry_MISMIPplus(mesh: Mesh, x_gl=450e3, H0=1500.0, H_shelf=300.0) -> IceInputs:
+def geometry_MISMIPplus(mesh: Mesh, x_gl=450e3, H0=1500.0, H_shelf=300.0, calving_front=None) -> IceInputs:
     """MISMIP+ bed with a synthetic Vialov-like grounded profile to x_gl and a shelf
-    thinning to ``H_shelf`` at the calving front x = 640 km."""
+    thinning to ``H_shelf`` at x = 640 km.  ``calving_front=None`` (default):
+    the shelf continues at ``H_shelf`` to the domain edge, so there is no ice-free ocean;
+    ``calving_front=640e3`` removes the ice beyond it.  With an ice-free part of the domain the
+    cold-start Picard iteration of the reference algorithm never reaches
+    ``visc_it_norm_dUV_tol`` (the velocities of the ice-free triangles keep oscillating at the
+    ``vel_max`` cap; the oracle's direct-solve loop shows the same), which makes a poor
+    benchmark step; without it the loop converges in 46 iterations at 4 km."""
     x, y = mesh.V[:, 0], mesh.V[:, 1]
     Hb = mismipplus_bed(x, y)
     SL = np.zeros(mesh.nV)
@@ -202,7 +208,8 @@ def geometry_MISMIPplus(mesh: Mesh, x_gl=450e3, H0=1500.0, H_shelf=300.0) -> Ice
     t = np.clip((x - x_gl) / (640e3 - x_gl), 0.0, 1.0)
     Hf = H_gl + (H_shelf - H_gl) * t
     Hi = np.where(x <= x_gl, Hg, Hf)
-    Hi = np.where(x > 640e3, 0.0, Hi)
+    if calving_front is not None:
+        Hi = np.where(x > calving_front, 0.0, Hi)
     return _finish_inputs(mesh, Hi, Hb, SL, hydrology="Martin2011")
 
 
