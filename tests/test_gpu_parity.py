@@ -410,3 +410,66 @@ def test_against_committed_golden_fixture():
         assert np.array_equal(A.ptr, G["A_ptr"]) and np.array_equal(A.ind, G["A_ind"])
     finally:
         S.close()
+
+
+# ------------------------------------------------------------------------------------------
+# every sliding law / rheology / option of the path against the oracle (few Picard iterations)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("law", ["Weertman", "Coulomb", "Budd", "Tsai2015", "Schoof2005", "Zoet-Iverson", "no_sliding"])
+def test_sliding_laws(oracle, law):
+    mesh, C, ice = experiments.MISMIPplus(8e3)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C.choice_sliding_law = law
+    C.slid_beta_max = 1e9
+    C.visc_it_nit = 3
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
+    ice.till_friction_angle[:] = 15.0
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        info = S.solve_DIVA(ice)
+        D = oracle.new_DIVA_state(mesh)
+        nv, _ = oracle.solve_DIVA(mesh, ice, C, D, "direct")
+        assert info.n_visc_its == nv
+        _check_uv(S, D)
+        r = rel(S.basal_friction_coefficient_a, D["basal_friction_coefficient_a"])
+        assert r[1] < 1e-9, r
+    finally:
+        S.close()
+
+
+@pytest.mark.parametrize("variant", ["Huybrechts1992", "enh_interp", "no_crossterms", "no_GL_subgrid", "SSA"])
+def test_rheology_and_options(oracle, variant):
+    mesh, C, ice = experiments.MISMIPplus(8e3)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C.visc_it_nit = 3
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
+    if variant in ("Huybrechts1992", "enh_interp"):
+        C.choice_ice_rheology_Glen = "Huybrechts1992"
+        C.m_enh_sheet, C.m_enh_shelf = 1.3, 0.6
+        z = np.linspace(0.0, 1.0, mesh.nz)
+        ice.Ti[:, :] = np.asfortranarray(250.0 + 20.0 * z[None, :] ** 2 + 1e-5 * mesh.V[:, 0:1])
+        if variant == "enh_interp":
+            C.choice_enhancement_factor_transition = "interp"
+    elif variant == "no_crossterms":
+        C.do_include_SSADIVA_crossterms = False
+    elif variant == "no_GL_subgrid":
+        C.do_GL_subgrid_friction = False
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        if variant == "SSA":
+            info = S.solve_SSA(ice)
+            R = dict(u_b=np.zeros(mesh.nTri), v_b=np.zeros(mesh.nTri))
+            nv, _ = oracle.solve_SSA(mesh, ice, C, R, "direct")
+            assert info.n_visc_its == nv
+            ref = np.concatenate([R["u_b"], R["v_b"]])
+            for k in ("u_b", "v_b"):
+                r = rel(getattr(S, k), R[k], ref)
+                assert r[0] < TOL_UV and r[1] < TOL_UV, (k, r)
+        else:
+            info = S.solve_DIVA(ice)
+            D = oracle.new_DIVA_state(mesh)
+            nv, _ = oracle.solve_DIVA(mesh, ice, C, D, "direct")
+            assert info.n_visc_its == nv
+            _check_uv(S, D)
+    finally:
+        S.close()
