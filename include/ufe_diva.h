@@ -172,6 +172,14 @@ typedef struct ufe_ssa_state {
   double *basal_friction_coefficient_a;              /* (nV) out, may be NULL */
 } ufe_ssa_state;
 
+/* outputs of calc_secondary_velocities (type_ice_model members, ice_model_types.f90); every pointer may
+ * be NULL (that field is then not copied back).  Full-length arrays. */
+typedef struct ufe_secondary_velocities {
+  double *u_surf_b, *v_surf_b, *uabs_surf_b, *u_base_b, *v_base_b, *uabs_base_b, *u_vav_b, *v_vav_b, *uabs_vav_b; /* (nTri) */
+  double *u_3D, *v_3D;                                                                                             /* (nV,nz) */
+  double *u_surf, *v_surf, *uabs_surf, *u_base, *v_base, *uabs_base, *u_vav, *v_vav, *uabs_vav, *R_shear;          /* (nV) */
+} ufe_secondary_velocities;
+
 typedef struct ufe_solve_info {
   int32_t n_visc_its, n_Axb_its;   /* solve_DIVA outputs, DIVA_main.f90:97-98 */
   int32_t flags;                   /* UFE_FLAG_* */
@@ -238,6 +246,12 @@ int ufe_diva_download(ufe_handle *h, ufe_diva_state *state);
 /* initialise_DIVA_solver with choice_initial_velocity = 'zero' (DIVA_main.f90:60-68) on the
  * resident state: the seven restart fields are zeroed on the device (no host traffic). */
 int ufe_diva_reset_state(ufe_handle *h);
+
+/* SURVEY.md 8(f) rank 1 -- replaces set_ice_velocities_to_DIVA_results + calc_secondary_velocities
+ * (conservation_of_momentum_main.f90:470-510, 176-245), the step right after solve_DIVA, on the
+ * device-resident u_3D_b / v_3D_b of the most recent DIVA solve: surface, base and vertically
+ * averaged velocities on the b- and a-grid, u_3D / v_3D on the a-grid, absolute values, R_shear. */
+int ufe_calc_secondary_velocities(ufe_handle *h, ufe_secondary_velocities *out);
 
 /* L1 -- replaces solve_SSA_DIVA_linearised (solve_linearised_SSA_DIVA.f90:23-178; call
  * sites DIVA_main.f90:189-192, SSA_main.f90:178-181).  Full-length (nTri) arrays.

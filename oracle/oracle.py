@@ -610,3 +610,26 @@ def solve_SSA(mesh, ice, C, S, linear_solver="direct", nranks=1, bc_mask=None, b
         if it > C.visc_it_nit:
             break
     return it, n_Axb_its
+
+
+# --------------------------------------------------------------------------------------
+# calc_secondary_velocities (conservation_of_momentum_main.f90:176-245)
+# --------------------------------------------------------------------------------------
+def calc_secondary_velocities(mesh, u_3D_b, v_3D_b):
+    """Surface / base / vertically averaged velocities on both grids, u_3D / v_3D on the a-grid,
+    absolute values and the slide/shear ratio R_shear (:236-239)."""
+    ops, zeta = mesh.ops, mesh.zeta
+    o = {}
+    o["u_surf_b"], o["v_surf_b"] = u_3D_b[:, 0].copy(), v_3D_b[:, 0].copy()          # :196-198
+    o["u_base_b"], o["v_base_b"] = u_3D_b[:, -1].copy(), v_3D_b[:, -1].copy()        # :201-203
+    o["u_vav_b"], o["v_vav_b"] = vertical_average(zeta, u_3D_b), vertical_average(zeta, v_3D_b)   # :206-210
+    for k in ("surf", "base", "vav"):
+        o[f"uabs_{k}_b"] = np.sqrt(o[f"u_{k}_b"] ** 2 + o[f"v_{k}_b"] ** 2)
+    o["u_3D"] = spmv_2D(ops["M_map_b_a"], np.asfortranarray(u_3D_b))                  # :217-218
+    o["v_3D"] = spmv_2D(ops["M_map_b_a"], np.asfortranarray(v_3D_b))
+    for k in ("surf", "base", "vav"):                                                 # :221-230
+        o[f"u_{k}"] = spmv(ops["M_map_b_a"], o[f"u_{k}_b"])
+        o[f"v_{k}"] = spmv(ops["M_map_b_a"], o[f"v_{k}_b"])
+        o[f"uabs_{k}"] = np.sqrt(o[f"u_{k}"] ** 2 + o[f"v_{k}"] ** 2)                 # :233-237
+    o["R_shear"] = (o["uabs_base"] + 0.1) / (o["uabs_surf"] + 0.1)                    # :240-242
+    return o

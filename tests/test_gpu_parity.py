@@ -473,3 +473,17 @@ def test_rheology_and_options(oracle, variant):
             _check_uv(S, D)
     finally:
         S.close()
+
+
+def test_calc_secondary_velocities(homA, oracle):
+    """the step right after the solve, on the device-resident 3-D velocities."""
+    mesh, C, ice, S = homA
+    S.set_config(C)
+    S.solve_DIVA(ice)
+    got = S.calc_secondary_velocities()
+    want = oracle.calc_secondary_velocities(mesh, S.u_3D_b, S.v_3D_b)
+    assert set(got) == set(want)
+    for k, w in want.items():
+        scale = max(np.abs(w).max(), 1e-300)
+        assert np.abs(got[k] - w).max() / scale < 1e-12, k
+    assert np.array_equal(got["u_surf"], got["u_3D"][:, 0])      # same sums in the same order

@@ -261,3 +261,24 @@ def test_oracle_reproduces_committed_lattice_fixture(oracle):
     for nm, A in mesh.ops.items():
         assert np.array_equal(A.ptr, G[nm + "_ptr"]) and np.array_equal(A.ind, G[nm + "_ind"]), nm
         assert np.allclose(A.val, G[nm + "_val"], rtol=1e-12, atol=0), nm
+
+
+def test_secondary_velocities_closed_forms(oracle, mesh41):
+    """calc_secondary_velocities (conservation_of_momentum_main.f90:176-245) on a field with a known
+    answer: u = (a + b x)(2 - zeta) is linear in x and zeta, so the b->a map and the trapezoidal
+    vertical average are exact."""
+    mesh = mesh41
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    z = mesh.zeta
+    gx = mesh.TriGC[:, 0]
+    u3 = np.asfortranarray((3.0 + 1e-5 * gx)[:, None] * (2.0 - z)[None, :])
+    v3 = np.asfortranarray(-0.5 * u3)
+    o = oracle.calc_secondary_velocities(mesh, u3, v3)
+    interior = mesh.VBI == 0
+    xa = mesh.V[:, 0]
+    assert np.allclose(o["u_surf"][interior], (3.0 + 1e-5 * xa[interior]) * 2.0, rtol=1e-12)
+    assert np.allclose(o["u_base"][interior], (3.0 + 1e-5 * xa[interior]) * 1.0, rtol=1e-12)
+    assert np.allclose(o["u_vav_b"], (3.0 + 1e-5 * gx) * 1.5, rtol=1e-13)
+    assert np.allclose(o["uabs_vav_b"], np.sqrt(1.25) * np.abs(o["u_vav_b"]), rtol=1e-13)
+    assert np.allclose(o["R_shear"], (o["uabs_base"] + 0.1) / (o["uabs_surf"] + 0.1))
+    assert np.array_equal(o["u_3D"][:, 0], o["u_surf"])

@@ -88,6 +88,15 @@ class ufe_solve_info(ct.Structure):
                 ("krylov_pc_used", c_i32), ("reserved", c_i32)]
 
 
+SECONDARY_FIELDS = ("u_surf_b", "v_surf_b", "uabs_surf_b", "u_base_b", "v_base_b", "uabs_base_b", "u_vav_b", "v_vav_b",
+                    "uabs_vav_b", "u_3D", "v_3D", "u_surf", "v_surf", "uabs_surf", "u_base", "v_base", "uabs_base", "u_vav",
+                    "v_vav", "uabs_vav", "R_shear")
+
+
+class ufe_secondary_velocities(ct.Structure):
+    _fields_ = [(n, ct.c_void_p) for n in SECONDARY_FIELDS]
+
+
 class ufe_comm(ct.Structure):
     _fields_ = [("rank", c_i32), ("nranks", c_i32), ("device", c_i32), ("nccl_unique_id", ct.c_char_p)]
 
@@ -96,7 +105,7 @@ EXPORTS = [
     "ufe_last_error_string", "ufe_comm_get_unique_id", "ufe_version", "ufe_partition_list",
     "ufe_krylov_solve", "ufe_spmv", "ufe_diva_create", "ufe_diva_destroy", "ufe_diva_set_config",
     "ufe_diva_solve", "ufe_ssa_solve", "ufe_diva_upload", "ufe_diva_solve_resident",
-    "ufe_diva_download", "ufe_diva_reset_state", "ufe_ssa_diva_linearised", "ufe_mesh_get_operator",
+    "ufe_diva_download", "ufe_diva_reset_state", "ufe_calc_secondary_velocities", "ufe_ssa_diva_linearised", "ufe_mesh_get_operator",
     "ufe_mesh_apply_operator", "ufe_get_stiffness_csr", "ufe_bench_spmv", "ufe_get_ownership",
 ]
 

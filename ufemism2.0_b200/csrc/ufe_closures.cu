@@ -366,6 +366,62 @@ __global__ void k_vel3d(int t0, int nt, int nTri, int nz, ClosureParams P, DivaF
 }
 
 // ---------------------------------------------------------------------------------
+// calc_secondary_velocities (conservation_of_momentum_main.f90:176-245), the step right after the
+// solve: surface / base / vertically averaged velocities on the b-grid from u_3D_b, v_3D_b, then the
+// b->a maps (map_b_a_3D x2, map_b_a_2D x6) fused into one pass over the shared M_map_b_a pattern,
+// absolute values and the slide/shear ratio.
+// ---------------------------------------------------------------------------------
+__global__ void k_secondary_b(int t0, int nt, int nTri, int nz, ClosureParams P, const double *__restrict__ u3,
+                              const double *__restrict__ v3, SecondaryFields O) {
+  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tl >= nt) return;
+  const int ti = t0 + tl;
+  const double us = u3[ti], vs = v3[ti];
+  const double ub = u3[(size_t)(nz - 1) * nTri + ti], vb = v3[(size_t)(nz - 1) * nTri + ti];
+  O.u_surf_b[ti] = us; O.v_surf_b[ti] = vs; O.uabs_surf_b[ti] = sqrt(us * us + vs * vs);
+  O.u_base_b[ti] = ub; O.v_base_b[ti] = vb; O.uabs_base_b[ti] = sqrt(ub * ub + vb * vb);
+  double ua = 0.0, va = 0.0;                    // vertical_average, mesh_zeta.f90:257-283
+  for (int k = 0; k < nz - 1; k++) {
+    const double dz = P.zeta[k + 1] - P.zeta[k];
+    ua = ua + 0.5 * (u3[(size_t)(k + 1) * nTri + ti] + u3[(size_t)k * nTri + ti]) * dz;
+    va = va + 0.5 * (v3[(size_t)(k + 1) * nTri + ti] + v3[(size_t)k * nTri + ti]) * dz;
+  }
+  O.u_vav_b[ti] = ua; O.v_vav_b[ti] = va; O.uabs_vav_b[ti] = sqrt(ua * ua + va * va);
+}
+
+template <int NZ>
+__global__ void __launch_bounds__(128)
+k_secondary_a(int v0, int nv, int nV, int nTri, int nz_rt, DevFamilyView ba, const double *__restrict__ u3,
+              const double *__restrict__ v3, SecondaryFields O) {
+  const int vl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vl >= nv) return;
+  const int vi = v0 + vl, nz = NZ > 0 ? NZ : nz_rt;
+  double us = 0.0, vs = 0.0, ub = 0.0, vb = 0.0, ua = 0.0, va = 0.0;
+  const int k0 = ba.ptr[vl] - 1, k1 = ba.ptr[vl + 1] - 1;
+  for (int l = 0; l < nz; l++) {                 // map_b_a_3D, one layer at a time in the row's entry order
+    double su = 0.0, sv = 0.0;
+    for (int k = k0; k < k1; k++) {
+      const int tj = ba.ind[k] - 1;
+      const double w = ba.v0[k];
+      su += w * u3[(size_t)l * nTri + tj];
+      sv += w * v3[(size_t)l * nTri + tj];
+    }
+    O.u_3D[(size_t)l * nV + vi] = su; O.v_3D[(size_t)l * nV + vi] = sv;
+  }
+  for (int k = k0; k < k1; k++) {                // map_b_a_2D of the six b-grid fields
+    const int tj = ba.ind[k] - 1;
+    const double w = ba.v0[k];
+    us += w * O.u_surf_b[tj]; vs += w * O.v_surf_b[tj];
+    ub += w * O.u_base_b[tj]; vb += w * O.v_base_b[tj];
+    ua += w * O.u_vav_b[tj];  va += w * O.v_vav_b[tj];
+  }
+  O.u_surf[vi] = us; O.v_surf[vi] = vs; O.u_base[vi] = ub; O.v_base[vi] = vb; O.u_vav[vi] = ua; O.v_vav[vi] = va;
+  const double as = sqrt(us * us + vs * vs), ab = sqrt(ub * ub + vb * vb), aa = sqrt(ua * ua + va * va);
+  O.uabs_surf[vi] = as; O.uabs_base[vi] = ab; O.uabs_vav[vi] = aa;
+  O.R_shear[vi] = (ab + 0.1) / (as + 0.1);
+}
+
+// ---------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------
 int ufe_launch_driving_stress(cudaStream_t st, int t0, int nt, DevFamilyView ab, const double *Hi,
@@ -414,6 +470,22 @@ int ufe_launch_vel3d(cudaStream_t st, int t0, int nt, int nTri, int nz, const Cl
                      const DivaFields &F) {
   if (nt <= 0) return UFE_OK;
   k_vel3d<<<ufe_div_up(nt, 256), 256, 0, st>>>(t0, nt, nTri, nz, P, F);
+  UFE_LAUNCH_CHECK();
+  return UFE_OK;
+}
+
+int ufe_launch_secondary_b(cudaStream_t st, int t0, int nt, int nTri, int nz, const ClosureParams &P, const double *u3,
+                           const double *v3, const SecondaryFields &O) {
+  if (nt <= 0) return UFE_OK;
+  k_secondary_b<<<ufe_div_up(nt, 256), 256, 0, st>>>(t0, nt, nTri, nz, P, u3, v3, O);
+  UFE_LAUNCH_CHECK();
+  return UFE_OK;
+}
+int ufe_launch_secondary_a(cudaStream_t st, int v0, int nv, int nV, int nTri, int nz, DevFamilyView ba, const double *u3,
+                           const double *v3, const SecondaryFields &O) {
+  if (nv <= 0) return UFE_OK;
+  if (nz == 12) k_secondary_a<12><<<ufe_div_up(nv, 128), 128, 0, st>>>(v0, nv, nV, nTri, nz, ba, u3, v3, O);
+  else k_secondary_a<0><<<ufe_div_up(nv, 128), 128, 0, st>>>(v0, nv, nV, nTri, nz, ba, u3, v3, O);
   UFE_LAUNCH_CHECK();
   return UFE_OK;
 }

@@ -36,6 +36,17 @@ struct DivaFields {
   double *u_b_prev, *v_b_prev;
 };
 
+// outputs of calc_secondary_velocities (full-length device arrays)
+struct SecondaryFields {
+  double *u_surf_b, *v_surf_b, *uabs_surf_b, *u_base_b, *v_base_b, *uabs_base_b, *u_vav_b, *v_vav_b, *uabs_vav_b;   // (nTri)
+  double *u_3D, *v_3D;                                                                                               // (nV,nz)
+  double *u_surf, *v_surf, *uabs_surf, *u_base, *v_base, *uabs_base, *u_vav, *v_vav, *uabs_vav, *R_shear;            // (nV)
+};
+int ufe_launch_secondary_b(cudaStream_t st, int t0, int nt, int nTri, int nz, const ClosureParams &P, const double *u3,
+                           const double *v3, const SecondaryFields &O);
+int ufe_launch_secondary_a(cudaStream_t st, int v0, int nv, int nV, int nTri, int nz, DevFamilyView ba, const double *u3,
+                           const double *v3, const SecondaryFields &O);
+
 int ufe_launch_driving_stress(cudaStream_t st, int t0, int nt, DevFamilyView ab, const double *Hi,
                               const double *Hs, double *tdx, double *tdy);
 int ufe_launch_till(cudaStream_t st, int nV, const ClosureParams &P, const double *Neff, const double *phi,

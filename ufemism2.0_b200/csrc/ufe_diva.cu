@@ -110,6 +110,8 @@ struct ufe_handle {
   int *rowkind = nullptr;
   bool pattern_valid = false;
   KrylovWork kw;
+  SecondaryFields sec;                         // calc_secondary_velocities outputs (allocated on first use)
+  bool sec_alloc = false;
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
   int pc_used = -1;                            // resolved preconditioner for the cached pattern (-1 = undecided)
   int pc_age = -1, pc_last_its = 0;            // bjacobi_lu reuse: solves since the last factorisation (-1 = never), its of the last solve
@@ -336,6 +338,7 @@ extern "C" int ufe_diva_destroy(ufe_handle *h) {
   }
   cudaFree(h->red_counter); cudaFree(h->flush_buf);
   if (h->red_host) cudaFreeHost(h->red_host);
+  if (h->sec_alloc) { double **sp = reinterpret_cast<double **>(&h->sec); for (size_t i = 0; i < sizeof(SecondaryFields) / sizeof(double *); i++) cudaFree(sp[i]); }
   ufe_krylov_free(h->kw);
   ufe_pclu_free(h->pclu);
   for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -830,6 +833,55 @@ extern "C" int ufe_ssa_diva_linearised(ufe_handle *h, double *u_b, double *v_b, 
   UFE_CUDA(cudaStreamSynchronize(h->st));
   for (size_t t = 0; t < nT; t++) { u_b[t] = x[2 * t]; v_b[t] = x[2 * t + 1]; }
   if (n_Axb_its) *n_Axb_its = its;
+  return UFE_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// calc_secondary_velocities on the resident result of the last DIVA solve
+// ------------------------------------------------------------------------------------
+extern "C" int ufe_calc_secondary_velocities(ufe_handle *h, ufe_secondary_velocities *out) {
+  if (!h || !out) { ufe_set_error("null argument"); return UFE_ERR_INVALID; }
+  UFE_CUDA(cudaSetDevice(h->device));
+  const size_t nV = h->dm.nV, nT = h->dm.nTri, nz = h->dm.nz;
+  SecondaryFields &O = h->sec;
+  if (!h->sec_alloc) {
+    memset(&O, 0, sizeof O);
+    double **b9[] = {&O.u_surf_b, &O.v_surf_b, &O.uabs_surf_b, &O.u_base_b, &O.v_base_b, &O.uabs_base_b, &O.u_vav_b, &O.v_vav_b, &O.uabs_vav_b};
+    for (double **p : b9) UFE_TRY(dalloc(p, nT));
+    UFE_TRY(dalloc(&O.u_3D, nV * nz)); UFE_TRY(dalloc(&O.v_3D, nV * nz));
+    double **a10[] = {&O.u_surf, &O.v_surf, &O.uabs_surf, &O.u_base, &O.v_base, &O.uabs_base, &O.u_vav, &O.v_vav, &O.uabs_vav, &O.R_shear};
+    for (double **p : a10) UFE_TRY(dalloc(p, nV));
+    h->sec_alloc = true;
+  }
+  const int nv = h->vi2 - h->vi1 + 1, nt = h->ti2 - h->ti1 + 1;
+  ClosureParams P = make_params(h, h->cfg.Glens_flow_law_epsilon_sq_0);
+  UFE_TRY(ufe_launch_secondary_b(h->st, h->ti1 - 1, nt, (int)nT, (int)nz, P, h->F.u_3D_b, h->F.v_3D_b, O));
+  if (h->comm.nranks > 1) {     // the b->a maps read the triangles around the owned vertices
+    UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, h->F.u_3D_b, (long long)nT, (int)nz, 1));
+    UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, h->F.v_3D_b, (long long)nT, (int)nz, 1));
+    double *b6[] = {O.u_surf_b, O.v_surf_b, O.u_base_b, O.v_base_b, O.u_vav_b, O.v_vav_b};
+    for (double *p : b6) UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, p, 0, 1, 1));
+  }
+  UFE_TRY(ufe_launch_secondary_a(h->st, h->vi1 - 1, nv, (int)nV, (int)nT, (int)nz, view_of(h->fam[1]), h->F.u_3D_b, h->F.v_3D_b, O));
+  if (h->comm.nranks > 1) {     // full-length results on every rank, like the other outputs of the C ABI
+    HaloPlan pb = h->plan_b_for_b, pa = h->plan_a_for_b;
+    for (int q = 0; q < pb.nranks; q++) { pb.need_lo[q] = 0; pb.need_hi[q] = (int)nT; pa.need_lo[q] = 0; pa.need_hi[q] = (int)nV; }
+    double *b9[] = {O.u_surf_b, O.v_surf_b, O.uabs_surf_b, O.u_base_b, O.v_base_b, O.uabs_base_b, O.u_vav_b, O.v_vav_b, O.uabs_vav_b};
+    for (double *p : b9) UFE_TRY(ufe_halo_exchange(h->st, h->comm, pb, p, 0, 1, 1));
+    double *a10[] = {O.u_surf, O.v_surf, O.uabs_surf, O.u_base, O.v_base, O.uabs_base, O.u_vav, O.v_vav, O.uabs_vav, O.R_shear};
+    for (double *p : a10) UFE_TRY(ufe_halo_exchange(h->st, h->comm, pa, p, 0, 1, 1));
+    UFE_TRY(ufe_halo_exchange(h->st, h->comm, pa, O.u_3D, (long long)nV, (int)nz, 1));
+    UFE_TRY(ufe_halo_exchange(h->st, h->comm, pa, O.v_3D, (long long)nV, (int)nz, 1));
+  }
+  D2H(out->u_surf_b, O.u_surf_b, nT); D2H(out->v_surf_b, O.v_surf_b, nT); D2H(out->uabs_surf_b, O.uabs_surf_b, nT);
+  D2H(out->u_base_b, O.u_base_b, nT); D2H(out->v_base_b, O.v_base_b, nT); D2H(out->uabs_base_b, O.uabs_base_b, nT);
+  D2H(out->u_vav_b, O.u_vav_b, nT); D2H(out->v_vav_b, O.v_vav_b, nT); D2H(out->uabs_vav_b, O.uabs_vav_b, nT);
+  D2H(out->u_3D, O.u_3D, nV * nz); D2H(out->v_3D, O.v_3D, nV * nz);
+  D2H(out->u_surf, O.u_surf, nV); D2H(out->v_surf, O.v_surf, nV); D2H(out->uabs_surf, O.uabs_surf, nV);
+  D2H(out->u_base, O.u_base, nV); D2H(out->v_base, O.v_base, nV); D2H(out->uabs_base, O.uabs_base, nV);
+  D2H(out->u_vav, O.u_vav, nV); D2H(out->v_vav, O.v_vav, nV); D2H(out->uabs_vav, O.uabs_vav, nV);
+  D2H(out->R_shear, O.R_shear, nV);
+  UFE_CUDA(cudaStreamSynchronize(h->st));
   return UFE_OK;
 }
 

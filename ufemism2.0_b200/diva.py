@@ -289,6 +289,20 @@ class DIVASolver:
         st = self._state_struct(outputs)
         check(capi.lib().ufe_diva_download(self._h, ct.byref(st)))
 
+    # ---- the step right after the solve
+    def calc_secondary_velocities(self) -> dict:
+        """set_ice_velocities_to_DIVA_results + calc_secondary_velocities
+        (conservation_of_momentum_main.f90:470-510, 176-245) on the resident result of the last
+        solve_DIVA.  Returns the ice%... fields by name."""
+        nT, nV, nz = self.mesh.nTri, self.mesh.nV, self.mesh.nz
+        out, st = {}, capi.ufe_secondary_velocities()
+        for n in capi.SECONDARY_FIELDS:
+            shape = (nV, nz) if n in ("u_3D", "v_3D") else ((nT,) if n.endswith("_b") else (nV,))
+            out[n] = np.zeros(shape, order="F")
+            setattr(st, n, vp(out[n]))
+        check(capi.lib().ufe_calc_secondary_velocities(self._h, ct.byref(st)))
+        return out
+
     # ---- L1
     def solve_SSA_DIVA_linearised(self, u_b, v_b, N_b, dN_dx_b, dN_dy_b, basal_friction_coefficient_b,
                                   tau_dx_b, tau_dy_b, PETSc_rtol, PETSc_abstol, BC_prescr_mask_b=None,
