@@ -344,6 +344,7 @@ def main():
     roofline_small = spmv_roofline(S, "bench workload's own matrix, per rank; L2 flushed (512 MiB memset) between launches; "
                                       "launch-latency-bound at this size")
     roofline = roofline_small
+    krylov_iteration = None
     if not args.no_large_roofline:
         # the configuration the north_star quotes the SpMV roofline on: ~1 M vertices, N ~ 4 M unknowns,
         # ~76 M non-zeros, partitioned over the ranks; one truncated Picard iteration assembles the matrix
@@ -363,12 +364,27 @@ def main():
             commL = (rank, world, local, bytes(uid.cpu().tolist()))
         SL = diva.initialise_DIVA_solver(meshL, CL, commL)
         SL.solve_DIVA(iceL, outputs=False)
+        # whole Krylov iteration: a capped BiCGStab run on the same matrix; bytes per
+        # iteration without fusion credit = 2 B_spmv + 16 vector passes of 8 B per unknown
+        CK = copy.copy(CL)
+        CK.b200_krylov_maxits = 200
+        SL.set_config(CK)
+        SL.reset_state_resident()
+        ik = SL.solve_DIVA_resident()
         roofline = spmv_roofline(SL, f"synthetic Antarctic-scale mesh nV={meshL.nV} nTri={meshL.nTri} (N={2 * meshL.nTri} unknowns), rows "
                                      f"partitioned over {world} rank(s), figure per rank; L2 flushed (512 MiB memset) between launches")
         # DRAM bytes per launch of this kernel at this size on one GPU from `ncu --set full`
         # (profiles/r1_kspmv_bell_ncu_full_summary.txt); null when the sizes differ
         if world == 1 and args.large_vertices == 1_000_000:
             roofline["traffic"] = NCU_TRAFFIC_BYTES_1M
+        if ik.n_Axb_its > 0:
+            n_loc = 2 * meshL.nTri / world
+            it_bytes = 2.0 * roofline["algorithmic_bytes_per_launch"] + 16 * 8.0 * n_loc
+            it_ms = max_over_ranks(ik.ms_krylov / ik.n_Axb_its)
+            krylov_iteration = {"method": "bicgstab+bjacobi2", "its_timed": ik.n_Axb_its, "ms_per_iteration": it_ms,
+                                "algorithmic_bytes_per_iteration": it_bytes, "achieved": it_bytes / (it_ms * 1e-3) / 1e9,
+                                "unit": "GB/s", "frac": it_bytes / (it_ms * 1e-3) / 1e9 / peak,
+                                "note": "per rank, same mesh as `roofline`; includes the host polls between iteration batches"}
         SL.close()
         del meshL, iceL
     if rank != 0:
@@ -392,7 +408,8 @@ def main():
                   "ms_closures": last.ms_closures, "ms_assembly": last.ms_assembly, "ms_krylov": last.ms_krylov,
                   "wall_ms_per_step": 1e3 * wall_value / args.steps, "create_s": t_create},
         "e2e": e2e, "warm": warm, "gpu_launches": int(sum(i.gpu_launches for i in infos)),
-        "roofline": roofline, "roofline_bench_workload": roofline_small, "clocks": clocks,
+        "roofline": roofline, "roofline_bench_workload": roofline_small, "krylov_iteration": krylov_iteration,
+        "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_leg(mesh, C, ice, args.cpu_seconds, n_visc_full=last.n_visc_its)

@@ -606,7 +606,7 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
                                kw.dots_local, kw.sc, single, rtol, abstol);
   UFE_LAUNCH_CHECK();
   UFE_TRY(allreduce_stage(st, comm, kw, ST_INIT, 2, rtol, abstol));
-  int launched = 0, batch = pc ? 1 : 4;     // an exact block solve converges in the first (half) step
+  int launched = 0, batch = (pc && single) ? 1 : 4;     // an exact block solve converges in the first (half) step
   while (true) {
     for (int b = 0; b < batch; b++, launched++) {
       if (launched > 0) { k_bicg_p<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.pg, kw.sc); UFE_LAUNCH_CHECK(); }
