@@ -344,7 +344,7 @@ def main():
     roofline_small = spmv_roofline(S, "bench workload's own matrix, per rank; L2 flushed (512 MiB memset) between launches; "
                                       "launch-latency-bound at this size")
     roofline = roofline_small
-    krylov_iteration = None
+    krylov_iteration = other_kernels = None
     if not args.no_large_roofline:
         # the configuration the north_star quotes the SpMV roofline on: ~1 M vertices, N ~ 4 M unknowns,
         # ~76 M non-zeros, partitioned over the ranks; one truncated Picard iteration assembles the matrix
@@ -377,6 +377,18 @@ def main():
         # (profiles/r1_kspmv_bell_ncu_full_summary.txt); null when the sizes differ
         if world == 1 and args.large_vertices == 1_000_000:
             roofline["traffic"] = NCU_TRAFFIC_BYTES_1M
+        # closures and assembly of one Picard iteration at this size (reported, not optimised this round);
+        # bytes: SURVEY.md 8d B_asm = 44 nnz(M2) + 8 nnz(A) + 68 n_b (+ 8 nnz(A): the blocked copy is written too)
+        nT_loc, nV_loc, nzL = meshL.nTri / world, meshL.nV / world, meshL.nz
+        nnz_M2 = 10.0 * nT_loc
+        asm_bytes = 44 * nnz_M2 + 2 * 8 * 4 * nnz_M2 + 68 * nT_loc
+        clo_bytes = nV_loc * (6 * 28 + 6 * (6 + 3 * nzL) * 8 + (7 + 5 * nzL) * 8) + nT_loc * (3 * 28 + 3 * (3 + 3 * nzL) * 8 + (5 + 3 * nzL) * 8)
+        other_kernels = {
+            "assembly": {"ms": max_over_ranks(ik.ms_assembly), "algorithmic_bytes": asm_bytes,
+                         "achieved_GBs": asm_bytes / (max_over_ranks(ik.ms_assembly) * 1e-3) / 1e9},
+            "closures": {"ms": max_over_ranks(ik.ms_closures), "algorithmic_bytes": clo_bytes,
+                         "achieved_GBs": clo_bytes / (max_over_ranks(ik.ms_closures) * 1e-3) / 1e9},
+            "note": "k_assemble and k_vertex_diva + k_triangle_diva, one Picard iteration on the same large mesh, per rank"}
         if ik.n_Axb_its > 0:
             n_loc = 2 * meshL.nTri / world
             it_bytes = 2.0 * roofline["algorithmic_bytes_per_launch"] + 16 * 8.0 * n_loc
@@ -409,7 +421,7 @@ def main():
                   "wall_ms_per_step": 1e3 * wall_value / args.steps, "create_s": t_create},
         "e2e": e2e, "warm": warm, "gpu_launches": int(sum(i.gpu_launches for i in infos)),
         "roofline": roofline, "roofline_bench_workload": roofline_small, "krylov_iteration": krylov_iteration,
-        "clocks": clocks,
+        "other_kernels_large_mesh": other_kernels, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_leg(mesh, C, ice, args.cpu_seconds, n_visc_full=last.n_visc_its)
