@@ -133,6 +133,9 @@ typedef struct ufe_config {
   int32_t krylov_guess_nonzero; /* 0 = KSP default (x0 = 0, petsc_basic.f90:99-128) */
   int32_t krylov_pc_lag;        /* UFE_PC_BJACOBI_LU: reuse a factorisation across Picard iterations until a solve
                                  * needs more than this many Krylov iterations; 0 = factorise every iteration */
+  int32_t krylov_pc_strip_only; /* UFE_PC_BJACOBI_LU with several ranks: 0 = replicate the exact factorisation on every
+                                 * rank when the whole system's dense blocks fit (small systems), else one strip block
+                                 * per rank; 1 = always one strip block per rank (PETSc bjacobi structure) */
 } ufe_config;
 
 /* ---- inputs read from type_ice_model / type_bed_roughness_model ------------------

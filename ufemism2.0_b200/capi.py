@@ -58,7 +58,7 @@ class ufe_config(ct.Structure):
                 ("refgeo_idealised_SSA_icestream_L", c_f64), ("refgeo_idealised_SSA_icestream_m", c_f64),
                 ("refgeo_idealised_ISMIP_HOM_L", c_f64),
                 ("krylov_method", c_i32), ("krylov_pc", c_i32), ("krylov_maxits", c_i32),
-                ("krylov_guess_nonzero", c_i32), ("krylov_pc_lag", c_i32)]
+                ("krylov_guess_nonzero", c_i32), ("krylov_pc_lag", c_i32), ("krylov_pc_strip_only", c_i32)]
 
 
 class ufe_ice_inputs(ct.Structure):

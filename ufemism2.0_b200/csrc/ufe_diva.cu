@@ -566,10 +566,18 @@ static int linearised_resident(ufe_handle *h, double rtol, double abstol, int *n
   PcLU *pc = nullptr;
   if (h->pc_used < 0) {                               // once per cached pattern
     h->pc_used = h->cfg.krylov_pc;
-    if (h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) UFE_TRY(ufe_pclu_setup(h->st, h->S, 0, (size_t)100 << 30, &h->pclu));
-    if (h->cfg.krylov_pc == UFE_PC_AUTO) {
-      const int rc = ufe_pclu_setup(h->st, h->S, 0, (size_t)24 << 30, &h->pclu);
+    if (h->cfg.krylov_pc == UFE_PC_BJACOBI_LU || h->cfg.krylov_pc == UFE_PC_AUTO) {
+      const size_t budget = h->cfg.krylov_pc == UFE_PC_AUTO ? (size_t)24 << 30 : (size_t)100 << 30;
+      int rc = UFE_ERR_INVALID;
+      if (h->comm.nranks > 1 && !h->cfg.krylov_pc_strip_only) {      // replicated exact solve when the whole system fits
+        HaloPlan all = h->plan_b_for_b;
+        for (int q = 0; q < all.nranks; q++) { all.need_lo[q] = 0; all.need_hi[q] = h->dm.nTri; }
+        rc = ufe_pclu_setup(h->st, h->S, 1, (size_t)24 << 30, &h->pclu, &h->comm, &all);
+        if (rc == UFE_ERR_CUDA) return rc;
+      }
+      if (rc != UFE_OK) rc = ufe_pclu_setup(h->st, h->S, 0, budget, &h->pclu);
       if (rc == UFE_ERR_CUDA) return rc;
+      if (rc != UFE_OK && h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) return rc;
       h->pc_used = rc == UFE_OK ? UFE_PC_BJACOBI_LU : UFE_PC_BJACOBI2;
     }
   }

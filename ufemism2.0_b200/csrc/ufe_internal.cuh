@@ -134,7 +134,8 @@ void ufe_krylov_free(KrylovWork &kw);
 // halo: callback-free -- single GPU handled inline, multi-GPU through the exchange plan.
 struct HaloPlan;
 struct PcLU;     // block-Jacobi / block-tridiagonal LU preconditioner (ufe_pclu.cu); nullptr = none
-int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int segments, size_t max_bytes, PcLU **out);
+int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int replicate, size_t max_bytes, PcLU **out,
+                   const Comm *comm = nullptr, const HaloPlan *gather_all = nullptr);
 int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc);
 int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z);
 void ufe_pclu_free(PcLU *pc);

@@ -17,8 +17,14 @@
 // 3 log2 K batched GEMV launches:
 //   down:  y_j = Dinv_j r_j,   r_i <- r_i - L_i y_a - U_i y_b        up:  x_j = y_j - P_j x_{j-s} - Q_j x_{j+s}.
 // With one GPU the preconditioner is the exact inverse (the Krylov loop then converges in one or
-// two steps and acts as iterative refinement); with several GPUs it is block Jacobi over the
-// ranks' strips (couplings to other ranks' columns are dropped).
+// two steps and acts as iterative refinement).  With several GPUs there are two modes:
+//   strip mode     : block Jacobi over the ranks' strips (couplings to other ranks' columns are
+//                    dropped), each rank factorises its own strip -- PETSc's bjacobi structure;
+//   replicated mode: when the whole system's dense blocks fit one GPU, every rank assembles the
+//                    global block-tridiagonal matrix (its own rows + one all-reduce), factorises it
+//                    redundantly and applies it to the all-gathered residual, so the preconditioner
+//                    stays exact and the Krylov count does not grow with the rank count (small
+//                    systems cannot amortise more communication than that).
 // Inverses: blocked in-place Gauss-Jordan (32-wide panels, partial pivoting inside the 32 x 32
 // pivot block, static perturbation of vanishing pivots; the Krylov iteration absorbs it).
 #include <stdlib.h>
@@ -32,7 +38,11 @@
 struct PcLevel { int s, n, nE, nK, base; };    // base: first slot of this level's couplings in LS / US
 
 struct PcLU {
-  int n_loc = 0, g = 0, K = 0;
+  int n_loc = 0, g = 0, K = 0;               // n_loc: rows the factorisation covers (all N in replicated mode)
+  int replicated = 0, own_n = 0, own_r0 = 0; // replicated mode: this rank's rows [own_r0, own_r0 + own_n)
+  const Comm *comm = nullptr;
+  HaloPlan gather;                           // all-gather plan in triangle units (mult 2)
+  double *gvec = nullptr;                    // global-length staging vector
   std::vector<PcLevel> lev;
   double *D = nullptr;                       // K blocks: D_i, overwritten by Dinv_i when i is eliminated
   double *LS = nullptr, *US = nullptr;       // couplings of the active nodes of every level: slot base_l + position (< 2K slots)
@@ -57,17 +67,18 @@ __device__ __forceinline__ long long opnd_block(const Opnd &o, int node, int z, 
 // ------------------------------------------------------------------------------------
 // matrix -> dense block-tridiagonal storage
 // ------------------------------------------------------------------------------------
-__global__ void k_bell_bandwidth(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off,
+// rows: local block row t -> t + tshift; columns: bcol - cshift, kept when inside [0, ncols)
+__global__ void k_bell_bandwidth(int nt_loc, int tshift, int cshift, int ncols, int nslices, const int *__restrict__ bell_off,
                                  const int *__restrict__ bcol, int *bw) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= nslices) return;
   const int off = bell_off[s] - 1, w = bell_off[s + 1] - 1 - off;
-  const int r = s * 32 + lane;
+  const int rl = s * 32 + lane, r = rl + tshift;
   int b = 0;
-  if (r < nt_loc)
+  if (rl < nt_loc)
     for (int e = 0; e < w; e++) {
-      const int c = bcol[(size_t)(off + e) * 32 + lane] - t0;
-      if (c < 0 || c >= nt_loc) continue;        // another rank's column: dropped by block Jacobi
+      const int c = bcol[(size_t)(off + e) * 32 + lane] - cshift;
+      if (c < 0 || c >= ncols) continue;         // strip mode: another rank's column, dropped by block Jacobi
       const int d = c > r ? c - r : r - c;
       b = max(b, 2 * d + 1);
     }
@@ -75,18 +86,18 @@ __global__ void k_bell_bandwidth(int nt_loc, int t0, int nslices, const int *__r
   if (lane == 0) atomicMax(bw, b);
 }
 
-__global__ void k_bell_to_blocks(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off,
+__global__ void k_bell_to_blocks(int nt_loc, int tshift, int cshift, int ncols, int nslices, const int *__restrict__ bell_off,
                                  const int *__restrict__ bcol, const double *__restrict__ bval, int g,
                                  double *__restrict__ D, double *__restrict__ L, double *__restrict__ U) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= nslices) return;
   const int off = bell_off[s] - 1, w = bell_off[s + 1] - 1 - off;
-  const int t = s * 32 + lane;
-  if (t >= nt_loc) return;
+  const int tl = s * 32 + lane, t = tl + tshift;
+  if (tl >= nt_loc) return;
   const size_t gg = (size_t)g * g;
   for (int e = 0; e < w; e++) {
-    const int ct = bcol[(size_t)(off + e) * 32 + lane] - t0;
-    if (ct < 0 || ct >= nt_loc) continue;
+    const int ct = bcol[(size_t)(off + e) * 32 + lane] - cshift;
+    if (ct < 0 || ct >= ncols) continue;
     const double *p = bval + (size_t)(off + e) * 128 + lane;
     const double a[4] = {p[0], p[32], p[64], p[96]};
     for (int q = 0; q < 4; q++) {
@@ -402,6 +413,10 @@ __global__ void k_vec_in(int n, int total, const double *__restrict__ r, double 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) c[i] = i < n ? r[i] : 0.0;
 }
+__global__ void k_vec_place(int n, int r0, const double *__restrict__ r, double *__restrict__ gv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gv[r0 + i] = r[i];
+}
 __global__ void k_vec_out(int n, const double *__restrict__ c, double *__restrict__ z) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) z[i] = c[i];
@@ -413,30 +428,37 @@ __global__ void k_vec_out(int n, const double *__restrict__ c, double *__restric
 void ufe_pclu_free(PcLU *pc) {
   if (!pc) return;
   cudaFree(pc->D); cudaFree(pc->LS); cudaFree(pc->US); cudaFree(pc->Pm); cudaFree(pc->Qm);
-  cudaFree(pc->ipp); cudaFree(pc->colbuf); cudaFree(pc->c);
+  cudaFree(pc->ipp); cudaFree(pc->colbuf); cudaFree(pc->c); cudaFree(pc->gvec);
   delete pc;
 }
 
-int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int /*segments: reserved*/, size_t max_bytes, PcLU **out) {
+int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int replicate, size_t max_bytes, PcLU **out, const Comm *comm,
+                   const HaloPlan *gather_all) {
   *out = nullptr;
+  const bool repl = replicate && comm && comm->nranks > 1 && S.bell_val;
+  const int tshift = repl ? (S.r1 - 1) / 2 : 0, cshift = repl ? 0 : (S.r1 - 1) / 2, ncols = repl ? S.N / 2 : S.m_loc / 2;
+  const int n_cover = repl ? S.N : S.m_loc;
   int *d_bw = nullptr, bw = 0;
   UFE_CUDA(cudaMalloc(&d_bw, sizeof(int)));
   UFE_CUDA(cudaMemsetAsync(d_bw, 0, sizeof(int), st));
   if (S.bell_val)
-    k_bell_bandwidth<<<ufe_div_up((long long)S.nslices * 32, 256), 256, 0, st>>>(S.m_loc / 2, (S.r1 - 1) / 2, S.nslices, S.bell_off, S.bell_col, d_bw);
+    k_bell_bandwidth<<<ufe_div_up((long long)S.nslices * 32, 256), 256, 0, st>>>(S.m_loc / 2, tshift, cshift, ncols, S.nslices, S.bell_off, S.bell_col, d_bw);
   else
     k_csr_to_blocks<<<ufe_div_up(S.m_loc, 256), 256, 0, st>>>(S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, 1, nullptr, nullptr, nullptr, d_bw);
   UFE_LAUNCH_CHECK();
+  if (repl) { UFE_NCCL(ncclAllReduce(d_bw, d_bw, 1, ncclInt32, ncclMax, comm->nccl, st)); g_launch_count++; }
   UFE_CUDA(cudaMemcpyAsync(&bw, d_bw, sizeof(int), cudaMemcpyDeviceToHost, st));
   UFE_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_bw);
   PcLU *pc = new PcLU();
-  pc->n_loc = S.m_loc;
+  pc->n_loc = n_cover;
+  pc->replicated = repl ? 1 : 0; pc->own_n = S.m_loc; pc->own_r0 = S.r1 - 1; pc->comm = comm;
+  if (repl) pc->gather = *gather_all;
   int g = ((bw > 0 ? bw : 1) + GT - 1) / GT * GT;
-  if (g > S.m_loc) g = (S.m_loc + GT - 1) / GT * GT;
+  if (g > n_cover) g = (n_cover + GT - 1) / GT * GT;
   if (g < GT) g = GT;
   pc->g = g;
-  pc->K = (S.m_loc + g - 1) / g;
+  pc->K = (n_cover + g - 1) / g;
   if (pc->K < 1) pc->K = 1;
   int slots = 0, maxE = 0;
   for (int s = 1;; s *= 2) {
@@ -464,6 +486,7 @@ int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int /*segments: reserved
   UFE_CUDA(cudaMalloc(&pc->ipp, sizeof(double) * (size_t)maxE * NB * NB));
   UFE_CUDA(cudaMalloc(&pc->colbuf, sizeof(double) * (size_t)maxE * g * NB));
   UFE_CUDA(cudaMalloc(&pc->c, sizeof(double) * (size_t)pc->K * g * 2));
+  if (repl) UFE_CUDA(cudaMalloc(&pc->gvec, sizeof(double) * (size_t)S.N));
   *out = pc;
   return UFE_OK;
 }
@@ -475,12 +498,25 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
   UFE_CUDA(cudaMemsetAsync(pc->LS, 0, blk, st));      // level 0 occupies the first K slots (slot = node)
   UFE_CUDA(cudaMemsetAsync(pc->US, 0, blk, st));
   if (S.bell_val)
-    k_bell_to_blocks<<<ufe_div_up((long long)S.nslices * 32, 256), 256, 0, st>>>(S.m_loc / 2, (S.r1 - 1) / 2, S.nslices, S.bell_off, S.bell_col,
-                                                                                 S.bell_val, g, pc->D, pc->LS, pc->US);
+    k_bell_to_blocks<<<ufe_div_up((long long)S.nslices * 32, 256), 256, 0, st>>>(S.m_loc / 2, pc->replicated ? (S.r1 - 1) / 2 : 0,
+                                                                                 pc->replicated ? 0 : (S.r1 - 1) / 2,
+                                                                                 pc->replicated ? S.N / 2 : S.m_loc / 2, S.nslices,
+                                                                                 S.bell_off, S.bell_col, S.bell_val, g, pc->D, pc->LS, pc->US);
   else
     k_csr_to_blocks<<<ufe_div_up(S.m_loc, 256), 256, 0, st>>>(S.m_loc, S.r1 - 1, S.ptr, S.ind, S.valS, g, pc->D, pc->LS, pc->US, nullptr);
   UFE_LAUNCH_CHECK();
-  if (K * g > pc->n_loc) { k_pad_identity<<<ufe_div_up(K * g - pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, g, K, pc->D); UFE_LAUNCH_CHECK(); }
+  if (K * g > pc->n_loc && (!pc->replicated || pc->comm->rank == 0)) {
+    k_pad_identity<<<ufe_div_up(K * g - pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, g, K, pc->D); UFE_LAUNCH_CHECK();
+  }
+  if (pc->replicated) {      // every rank contributed its own rows: sum = the global block-tridiagonal matrix
+    const size_t cnt = (size_t)g * g * K;
+    UFE_NCCL(ncclGroupStart());
+    UFE_NCCL(ncclAllReduce(pc->D, pc->D, cnt, ncclDouble, ncclSum, pc->comm->nccl, st));
+    UFE_NCCL(ncclAllReduce(pc->LS, pc->LS, cnt, ncclDouble, ncclSum, pc->comm->nccl, st));
+    UFE_NCCL(ncclAllReduce(pc->US, pc->US, cnt, ncclDouble, ncclSum, pc->comm->nccl, st));
+    UFE_NCCL(ncclGroupEnd());
+    g_launch_count += 3;
+  }
   const int nbk = g / NB, nt = g / GT;
   for (size_t l = 0; l < pc->lev.size(); l++) {
     const PcLevel &lv = pc->lev[l];
@@ -517,6 +553,12 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
 int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z) {
   const int g = pc->g, K = pc->K, total = K * g;
   double *c = pc->c, *y = pc->c + total;
+  if (pc->replicated) {      // all-gather the distributed residual, solve globally, keep the own slice
+    k_vec_place<<<ufe_div_up(pc->own_n, 256), 256, 0, st>>>(pc->own_n, pc->own_r0, r, pc->gvec);
+    UFE_LAUNCH_CHECK();
+    UFE_TRY(ufe_halo_exchange(st, *pc->comm, pc->gather, pc->gvec, 0, 1, 2));
+    r = pc->gvec;
+  }
   k_vec_in<<<ufe_div_up(total, 256), 256, 0, st>>>(pc->n_loc, total, r, c);
   UFE_LAUNCH_CHECK();
   for (const PcLevel &lv : pc->lev) {
@@ -530,7 +572,8 @@ int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z) {
     g_launch_count++;
   }
   if (cudaGetLastError() != cudaSuccess) { ufe_set_error("bjacobi_lu apply launch failed"); return UFE_ERR_CUDA; }
-  k_vec_out<<<ufe_div_up(pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, c, z);
+  if (pc->replicated) k_vec_out<<<ufe_div_up(pc->own_n, 256), 256, 0, st>>>(pc->own_n, c + pc->own_r0, z);
+  else k_vec_out<<<ufe_div_up(pc->n_loc, 256), 256, 0, st>>>(pc->n_loc, c, z);
   UFE_LAUNCH_CHECK();
   return UFE_OK;
 }

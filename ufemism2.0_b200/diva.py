@@ -69,6 +69,7 @@ def config_struct(C: Config) -> capi.ufe_config:
     s.krylov_maxits = C.b200_krylov_maxits
     s.krylov_guess_nonzero = int(C.b200_krylov_guess_nonzero)
     s.krylov_pc_lag = int(C.b200_krylov_pc_lag)
+    s.krylov_pc_strip_only = int(C.b200_krylov_pc_strip_only)
     return s
 
 

@@ -50,7 +50,7 @@ module diva_gpu_bindings
     real(c_double)     :: refgeo_idealised_SSA_icestream_Hi, refgeo_idealised_SSA_icestream_dhdx
     real(c_double)     :: refgeo_idealised_SSA_icestream_L, refgeo_idealised_SSA_icestream_m
     real(c_double)     :: refgeo_idealised_ISMIP_HOM_L
-    integer(c_int32_t) :: krylov_method, krylov_pc, krylov_maxits, krylov_guess_nonzero, krylov_pc_lag
+    integer(c_int32_t) :: krylov_method, krylov_pc, krylov_maxits, krylov_guess_nonzero, krylov_pc_lag, krylov_pc_strip_only
   end type ufe_config
 
   type, bind(C) :: ufe_ice_inputs
