@@ -4,6 +4,7 @@
 // solve_SSA_DIVA_linearised : .../solve_linearised_SSA_DIVA.f90:23-178
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -110,6 +111,7 @@ struct ufe_handle {
   int *rowkind = nullptr;
   bool pattern_valid = false;
   KrylovWork kw;
+  double *sym = nullptr;                       // symmetric peer buffer (several ranks): owns S.x, kw.pg, kw.sg
   SecondaryFields sec;                         // calc_secondary_velocities outputs (allocated on first use)
   bool sec_alloc = false;
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
@@ -319,10 +321,29 @@ static int alloc_fields(ufe_handle *h) {
   return UFE_OK;
 }
 
+static void peer_teardown(ufe_handle *h) {
+  if (!h->sym) return;
+  if (h->comm.nccl && h->st) {            // nobody may still be reading this rank's buffer
+    int *d = nullptr;
+    if (cudaMalloc(&d, sizeof(int)) == cudaSuccess) {
+      cudaMemsetAsync(d, 0, sizeof(int), h->st);
+      ncclAllReduce(d, d, 1, ncclInt32, ncclSum, h->comm.nccl, h->st);
+      cudaStreamSynchronize(h->st);
+      cudaFree(d);
+    }
+  }
+  PeerComm &pc = h->comm.peer;
+  if (pc.on) for (int q = 0; q < pc.P; q++) if (q != pc.me && pc.base[q]) cudaIpcCloseMemHandle(pc.base[q]);
+  pc.on = 0;
+  cudaFree(h->sym);
+  h->sym = nullptr; h->S.x = nullptr;
+}
+
 extern "C" int ufe_diva_destroy(ufe_handle *h) {
   if (!h) return UFE_OK;
   cudaSetDevice(h->device);
   if (h->st) cudaStreamSynchronize(h->st);
+  peer_teardown(h);
   for (double *p : h->owned_ptrs) cudaFree(p);
   double *dl[] = {h->Hi, h->Hs, h->Hib, h->SL, h->fraction_gr, h->fraction_gr_b, h->Neff, h->Ti, h->phi, h->alpha_sq,
                   h->beta_sq, h->tys, h->bc_u, h->bc_v, h->bc_copy_w, h->red_partials, h->red_out, h->dm.V, h->dm.TriGC,
@@ -361,6 +382,62 @@ extern "C" int ufe_diva_set_config(ufe_handle *h, const ufe_config *cfg) {
     h->bc_slot = h->bc_copy_ti = nullptr; h->bc_copy_w = nullptr;
     UFE_TRY(build_bc_tables(h));
   }
+  return UFE_OK;
+}
+
+// Symmetric buffer + CUDA-IPC mapping of the other ranks' buffers (PeerComm, ufe_internal.cuh).
+// If any rank cannot map a peer (no P2P / IPC in this environment) every rank falls back to the
+// NCCL halo exchange and all-reduces; UFE_COMM=nccl forces that path (A/B measurements).
+static int peer_setup(ufe_handle *h) {
+  PeerComm &pc = h->comm.peer;
+  const int P = h->comm.nranks, me = h->comm.rank;
+  const size_t N = (size_t)2 * h->dm.nTri;
+  if (P > UFE_MAX_RANKS) { ufe_set_error("at most %d ranks are supported", UFE_MAX_RANKS); return UFE_ERR_INVALID; }
+  pc.P = P; pc.me = me;
+  pc.off_pg = 0; pc.off_sg = (long long)N; pc.off_x = 2 * (long long)N; pc.off_dots = 3 * (long long)N;
+  pc.off_flags = pc.off_dots + 2LL * P * UFE_PEER_DOTS;
+  const size_t total = (size_t)pc.off_flags + 64;
+  UFE_CUDA(cudaMalloc(&h->sym, total * sizeof(double)));
+  UFE_CUDA(cudaMemset(h->sym, 0, total * sizeof(double)));
+  h->S.x = h->sym + pc.off_x;
+  for (int q = 0; q <= P; q++) {
+    int i1, i2;
+    if (q < P) { ufe_partition_list(h->dm.nTri, q, P, &i1, &i2); pc.bounds[q] = i1 - 1; }
+    else pc.bounds[q] = h->dm.nTri;
+  }
+  for (int q = 1; q < P; q++) if (pc.bounds[q] < pc.bounds[q - 1]) pc.bounds[q] = pc.bounds[q - 1];   // ranks without rows
+  const char *env = getenv("UFE_COMM");
+  int ok = (env && strcmp(env, "nccl") == 0) ? 0 : 1;
+  cudaIpcMemHandle_t mine, *all = nullptr;
+  std::vector<cudaIpcMemHandle_t> hall(P);
+  if (ok && cudaIpcGetMemHandle(&mine, h->sym) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  char *d = nullptr;
+  UFE_CUDA(cudaMalloc(&d, sizeof(mine) * (P + 1)));
+  UFE_CUDA(cudaMemcpy(d + sizeof(mine) * P, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  UFE_NCCL(ncclAllGather(d + sizeof(mine) * P, d, sizeof(mine), ncclChar, h->comm.nccl, h->st));
+  UFE_CUDA(cudaStreamSynchronize(h->st));
+  UFE_CUDA(cudaMemcpy(hall.data(), d, sizeof(mine) * P, cudaMemcpyDeviceToHost));
+  (void)all;
+  for (int q = 0; q < P; q++) pc.base[q] = nullptr;
+  pc.base[me] = h->sym;
+  for (int q = 0; q < P && ok; q++) {
+    if (q == me) continue;
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, hall[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    pc.base[q] = static_cast<double *>(ptr);
+  }
+  // all ranks must agree
+  int *dok = reinterpret_cast<int *>(d);
+  UFE_CUDA(cudaMemcpy(dok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  UFE_NCCL(ncclAllReduce(dok, dok, 1, ncclInt32, ncclMin, h->comm.nccl, h->st));
+  UFE_CUDA(cudaStreamSynchronize(h->st));
+  int all_ok = 0;
+  UFE_CUDA(cudaMemcpy(&all_ok, dok, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  if (!all_ok) {
+    for (int q = 0; q < P; q++) if (q != me && pc.base[q]) { cudaIpcCloseMemHandle(pc.base[q]); pc.base[q] = nullptr; }
+    pc.on = 0;
+  } else pc.on = 1;
   return UFE_OK;
 }
 
@@ -428,8 +505,13 @@ extern "C" int ufe_diva_create(const ufe_mesh *mesh, const ufe_config *cfg, cons
   }
   if ((rc = alloc_fields(h)) != UFE_OK) return fail(rc);
   if ((rc = build_bc_tables(h)) != UFE_OK) return fail(rc);
-  if ((rc = dalloc(&h->S.x, (size_t)2 * nT)) != UFE_OK) return fail(rc);
-  if ((rc = ufe_krylov_alloc(h->kw, 2 * dm.nTri, 2 * nt_loc, true)) != UFE_OK) return fail(rc);
+  if (h->comm.nranks > 1) {
+    if ((rc = peer_setup(h)) != UFE_OK) return fail(rc);
+    if ((rc = ufe_krylov_alloc(h->kw, 2 * dm.nTri, 2 * nt_loc, true, h->sym + h->comm.peer.off_pg, h->sym + h->comm.peer.off_sg)) != UFE_OK) return fail(rc);
+  } else {
+    if ((rc = dalloc(&h->S.x, (size_t)2 * nT)) != UFE_OK) return fail(rc);
+    if ((rc = ufe_krylov_alloc(h->kw, 2 * dm.nTri, 2 * nt_loc, true)) != UFE_OK) return fail(rc);
+  }
   if ((rc = dalloc(&h->red_partials, (size_t)UFE_RED_BLOCKS * 2)) != UFE_OK) return fail(rc);
   if ((rc = dalloc(&h->red_out, 4)) != UFE_OK) return fail(rc);
   if ((rc = dalloc(&h->red_counter, 1)) != UFE_OK) return fail(rc);
@@ -721,6 +803,7 @@ static int picard_resident(ufe_handle *h, int is_diva, ufe_solve_info *info) {
   info->ms_total = tot; info->ms_closures = ms_clo; info->ms_assembly = ms_asm; info->ms_krylov = ms_kry;
   info->gpu_launches = g_launch_count - launches0;
   info->krylov_pc_used = h->pc_used;
+  info->reserved = h->comm.peer.on;        // 1: peer-memory halo reads + reductions inside the Krylov loop
   return UFE_OK;
 }
 

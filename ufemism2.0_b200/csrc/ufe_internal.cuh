@@ -96,11 +96,32 @@ struct KrylovWork {
   double *gm = nullptr;   // GMRES small dense state: H(31x30), cs, sn, g, y, hcol
   KrylovScalars *sc_host = nullptr;  // pinned mirror
   double *pctmp = nullptr, *bP = nullptr;   // explicit-preconditioner work vectors (owned length)
+  bool ext_vecs = false;                    // pg / sg live in the symmetric peer buffer (not freed here)
 };
+
+#define UFE_MAX_RANKS 8
+#define UFE_PEER_DOTS 48        // doubles per rank per reduction slot
+
+// Peer-memory view of the other ranks' Krylov vectors (NVLink P2P through CUDA IPC): every rank
+// allocates one symmetric buffer  [pg (N) | sg (N) | x (N) | dots 2 x P x 48 | flags]  and maps
+// the others'.  SpMV kernels read halo entries of the input vector straight from the owner's
+// buffer; reductions are all-to-all stores into the peers' dot slots followed by a fixed-order
+// sum, so no NCCL call is left inside a Krylov iteration.
+struct PeerComm {
+  int on = 0, P = 1, me = 0;
+  double *base[UFE_MAX_RANKS] = {};     // mapped symmetric buffers (base[me] = own)
+  long long off_pg = 0, off_sg = 0, off_x = 0, off_dots = 0, off_flags = 0;   // offsets in doubles
+  int bounds[UFE_MAX_RANKS + 1] = {};   // triangle ownership: rank q owns [bounds[q], bounds[q+1])
+  long long halo_epoch = 0, red_epoch = 0;   // host-side counters (identical on every rank)
+};
+
+struct PeerFlagPtrs { int *f[UFE_MAX_RANKS]; };      // every rank's flag array (P2P mapped)
+struct PeerDotPtrs { double *d[UFE_MAX_RANKS]; };    // every rank's dot-slot array (P2P mapped)
 
 struct Comm {
   int rank = 0, nranks = 1;
   ncclComm_t nccl = nullptr;
+  mutable PeerComm peer;
 };
 
 // A distributed square CSR system on the device (rows r1..r1+m_loc-1, 1-based global).
@@ -128,7 +149,7 @@ int ufe_spmv_launch(cudaStream_t st, int m_loc, int nnz, const int *ptr, const i
                     const double *val, const double *x, long long ldx, double *y, long long ldy,
                     int nlayers);
 
-int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres);
+int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres, double *ext_pg = nullptr, double *ext_sg = nullptr);
 void ufe_krylov_free(KrylovWork &kw);
 // solves valS * x = bS on the owned rows; x full-length global vector (x[r1-1 ..] owned).
 // halo: callback-free -- single GPU handled inline, multi-GPU through the exchange plan.

@@ -191,6 +191,63 @@ k_kspmv(int m_loc, int r0, const int *__restrict__ ptr, const int *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------
+// Peer-memory communication inside the Krylov loop (PeerComm, ufe_internal.cuh)
+// ---------------------------------------------------------------------------------
+struct PeerView {             // by-value kernel argument
+  int P, me, epoch;           // epoch: halo signal count the consumer must see from every rank
+  int bounds[UFE_MAX_RANKS + 1];
+  const double2 *xp[UFE_MAX_RANKS];   // the input vector of this SpMV in every rank's buffer
+  const volatile int *flags;          // own flag array: [0, P) halo epochs, [P, 3P) reduction epochs (2 parities)
+};
+
+__device__ __forceinline__ double2 peer_load(const PeerView &pv, int c) {
+  int q = 0;
+#pragma unroll
+  for (int k = 1; k < UFE_MAX_RANKS; k++) if (k < pv.P && c >= pv.bounds[k]) q = k;
+  const double2 *p = pv.xp[q] + c;
+  double2 v;
+  asm volatile("ld.global.cv.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));   // never a stale cached line
+  return v;
+}
+
+// every rank tells every other rank that its SpMV input vector is complete (P2P store of the epoch)
+__global__ void k_peer_signal(int P, int me, int epoch, PeerFlagPtrs fp) {
+  const int q = threadIdx.x;
+  if (q >= P || q == me) return;
+  __threadfence_system();
+  *reinterpret_cast<volatile int *>(fp.f[q] + me) = epoch;
+}
+
+// all-to-all of the local partial dot products + fixed-order sum + scalar recurrence of the stage.
+// stage < 0: GMRES Gram-Schmidt coefficients -> hcol (no recurrence).
+__global__ void k_peer_reduce(int P, int me, int epoch, int nd, int stage, PeerFlagPtrs fp, PeerDotPtrs dp,
+                              const double *__restrict__ dots_local, KrylovScalars *sc, double *gm, double rtol, double abstol) {
+  if (sc->done) return;
+  const int par = epoch & 1, t = threadIdx.x;
+  if (t < P) {
+    double *dst = dp.d[t] + ((size_t)par * P + me) * UFE_PEER_DOTS;
+    for (int i = 0; i < nd; i++) dst[i] = dots_local[i];
+    __threadfence_system();
+    *reinterpret_cast<volatile int *>(fp.f[t] + P + par * P + me) = epoch;
+  }
+  if (t < P) {
+    const volatile int *mine = reinterpret_cast<const volatile int *>(fp.f[me] + P + par * P + t);
+    while (*mine < epoch) {}
+  }
+  __syncthreads();
+  if (t == 0) {
+    __threadfence_system();
+    const volatile double *src = dp.d[me] + (size_t)par * P * UFE_PEER_DOTS;
+    if (stage < 0) {
+      for (int i = 0; i < nd; i++) { double sum = 0.0; for (int q = 0; q < P; q++) sum += src[(size_t)q * UFE_PEER_DOTS + i]; GM_HCOL(gm)[i] = sum; }
+    } else {
+      for (int i = 0; i < nd; i++) { double sum = 0.0; for (int q = 0; q < P; q++) sum += src[(size_t)q * UFE_PEER_DOTS + i]; sc->dots[i] = sum; }
+      post_reduce(stage, sc, gm, rtol, abstol);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // The same three modes on the blocked sliced-ELL copy of the DIVA/SSA stiffness matrix
 // (2x2 u-v blocks per triangle pair, one warp per slice of 32 block rows, layout in
 // DevSystem).  One thread owns a block row = matrix rows (2t, 2t+1): per block entry it
@@ -198,13 +255,18 @@ k_kspmv(int m_loc, int r0, const int *__restrict__ ptr, const int *__restrict__ 
 // and gathers x as one 16-byte (u,v) pair; y is written as 16-byte pairs.  36 B per block
 // instead of 48 B in CSR, no shuffles, loads of U consecutive entries are issued together.
 // ---------------------------------------------------------------------------------
-template <int MODE, int U>
+template <int MODE, int U, int PEER>
 __global__ void __launch_bounds__(256)
 k_kspmv_bell(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off, const int *__restrict__ bcol,
              const double *__restrict__ bval, const double *__restrict__ xg, double *__restrict__ y,
              const double *__restrict__ z, int stage, double *partials, unsigned *counter, double *dots_local,
-             KrylovScalars *sc, double *gm, int single, double rtol, double abstol) {
+             KrylovScalars *sc, double *gm, int single, double rtol, double abstol, PeerView peer) {
   if (sc->done) return;
+  if (PEER) {       // wait until every rank has published this input vector (flags are in own memory)
+    if ((int)threadIdx.x < peer.P && (int)threadIdx.x != peer.me) while (peer.flags[threadIdx.x] < peer.epoch) {}
+    __syncthreads();
+  }
+  const int own_lo = PEER ? peer.bounds[peer.me] : 0, own_hi = PEER ? peer.bounds[peer.me + 1] : 0x7fffffff;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const double2 *__restrict__ x2 = reinterpret_cast<const double2 *>(xg);
@@ -224,7 +286,7 @@ k_kspmv_bell(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off, 
         a00[q] = __ldg(p); a01[q] = __ldg(p + 32); a10[q] = __ldg(p + 64); a11[q] = __ldg(p + 96);
       }
 #pragma unroll
-      for (int q = 0; q < U; q++) xx[q] = __ldg(x2 + c[q]);
+      for (int q = 0; q < U; q++) xx[q] = (!PEER || (c[q] >= own_lo && c[q] < own_hi)) ? __ldg(x2 + c[q]) : peer_load(peer, c[q]);
 #pragma unroll
       for (int q = 0; q < U; q++) { yu += a00[q] * xx[q].x + a01[q] * xx[q].y; yv += a10[q] * xx[q].x + a11[q] * xx[q].y; }
     }
@@ -232,7 +294,7 @@ k_kspmv_bell(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off, 
       const int c = __ldg(pc + (size_t)e * 32);
       const double *p = pv + (size_t)e * 128;
       const double a00 = __ldg(p), a01 = __ldg(p + 32), a10 = __ldg(p + 64), a11 = __ldg(p + 96);
-      const double2 xx = __ldg(x2 + c);
+      const double2 xx = (!PEER || (c >= own_lo && c < own_hi)) ? __ldg(x2 + c) : peer_load(peer, c);
       yu += a00 * xx.x + a01 * xx.y; yv += a10 * xx.x + a11 * xx.y;
     }
     const int r = s * 32 + lane;
@@ -248,14 +310,19 @@ k_kspmv_bell(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off, 
 
 template <int MODE>
 static int launch_kspmv(cudaStream_t st, const DevSystem &S, const double *xg, double *y, const double *z,
-                        int stage, KrylovWork &kw, int single, double rtol, double abstol) {
+                        int stage, KrylovWork &kw, int single, double rtol, double abstol, const PeerView *pv = nullptr) {
   if (S.bell_val) {
     int blocks = ufe_div_up(S.nslices, 8);
     if (blocks > KGRID) blocks = KGRID;
     if (blocks < 1) blocks = 1;
-    k_kspmv_bell<MODE, 4><<<blocks, 256, 0, st>>>(S.m_loc / 2, (S.r1 - 1) / 2, S.nslices, S.bell_off, S.bell_col, S.bell_val,
-                                                  xg, y, z, stage, kw.partials, kw.counter, kw.dots_local, kw.sc, kw.gm,
-                                                  single, rtol, abstol);
+    if (pv)
+      k_kspmv_bell<MODE, 4, 1><<<blocks, 256, 0, st>>>(S.m_loc / 2, (S.r1 - 1) / 2, S.nslices, S.bell_off, S.bell_col, S.bell_val,
+                                                       xg, y, z, stage, kw.partials, kw.counter, kw.dots_local, kw.sc, kw.gm,
+                                                       single, rtol, abstol, *pv);
+    else
+      k_kspmv_bell<MODE, 4, 0><<<blocks, 256, 0, st>>>(S.m_loc / 2, (S.r1 - 1) / 2, S.nslices, S.bell_off, S.bell_col, S.bell_val,
+                                                       xg, y, z, stage, kw.partials, kw.counter, kw.dots_local, kw.sc, kw.gm,
+                                                       single, rtol, abstol, PeerView());
     UFE_LAUNCH_CHECK();
     return UFE_OK;
   }
@@ -315,9 +382,9 @@ k_stage_dots(int n, int r0, const double *__restrict__ y, const double *__restri
 
 template <int MODE>
 static int apply_op(cudaStream_t st, const DevSystem &S, PcLU *pc, const double *xg, double *y, const double *z,
-                    int stage, KrylovWork &kw, int single, double rtol, double abstol) {
-  if (!pc) return launch_kspmv<MODE>(st, S, xg, y, z, stage, kw, single, rtol, abstol);
-  UFE_TRY(launch_kspmv<0>(st, S, xg, kw.pctmp, nullptr, 0, kw, single, rtol, abstol));
+                    int stage, KrylovWork &kw, int single, double rtol, double abstol, const PeerView *pv = nullptr) {
+  if (!pc) return launch_kspmv<MODE>(st, S, xg, y, z, stage, kw, single, rtol, abstol, pv);
+  UFE_TRY(launch_kspmv<0>(st, S, xg, kw.pctmp, nullptr, 0, kw, single, rtol, abstol, pv));
   UFE_TRY(ufe_pclu_apply(st, pc, kw.pctmp, y));
   if (MODE != 0) {
     k_stage_dots<MODE><<<UFE_RED_BLOCKS, UFE_RED_THREADS, 0, st>>>(S.m_loc, S.r1 - 1, y, z, xg, stage, kw.partials, kw.counter,
@@ -543,7 +610,7 @@ int ufe_halo_exchange(cudaStream_t st, const Comm &comm, const HaloPlan &plan, d
 // ---------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------
-int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres) {
+int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres, double *ext_pg, double *ext_sg) {
   kw.n_loc = n_loc; kw.N = N;
   size_t nb = (size_t)(n_loc > 0 ? n_loc : 1) * sizeof(double);
   size_t Nb = (size_t)(N > 0 ? N : 1) * sizeof(double);
@@ -551,7 +618,8 @@ int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres) {
   UFE_CUDA(cudaMalloc(&kw.v, nb)); UFE_CUDA(cudaMalloc(&kw.t, nb));
   UFE_CUDA(cudaMalloc(&kw.w, nb));
   UFE_CUDA(cudaMalloc(&kw.pctmp, nb)); UFE_CUDA(cudaMalloc(&kw.bP, nb));
-  UFE_CUDA(cudaMalloc(&kw.pg, Nb)); UFE_CUDA(cudaMalloc(&kw.sg, Nb));
+  if (ext_pg && ext_sg) { kw.pg = ext_pg; kw.sg = ext_sg; kw.ext_vecs = true; }
+  else { UFE_CUDA(cudaMalloc(&kw.pg, Nb)); UFE_CUDA(cudaMalloc(&kw.sg, Nb)); }
   UFE_CUDA(cudaMemset(kw.pg, 0, Nb)); UFE_CUDA(cudaMemset(kw.sg, 0, Nb));
   if (gmres) UFE_CUDA(cudaMalloc(&kw.Vb, nb * (GM_RESTART + 1)));
   UFE_CUDA(cudaMalloc(&kw.partials, sizeof(double) * KGRID * 8));
@@ -568,15 +636,57 @@ int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres) {
 
 void ufe_krylov_free(KrylovWork &kw) {
   cudaFree(kw.r); cudaFree(kw.rhat); cudaFree(kw.v); cudaFree(kw.t); cudaFree(kw.w);
-  cudaFree(kw.pg); cudaFree(kw.sg); cudaFree(kw.Vb); cudaFree(kw.partials); cudaFree(kw.dots_local);
+  if (!kw.ext_vecs) { cudaFree(kw.pg); cudaFree(kw.sg); }
+  cudaFree(kw.Vb); cudaFree(kw.partials); cudaFree(kw.dots_local);
   cudaFree(kw.counter); cudaFree(kw.sc); cudaFree(kw.gm); cudaFree(kw.pctmp); cudaFree(kw.bP);
   if (kw.sc_host) cudaFreeHost(kw.sc_host);
   kw = KrylovWork();
 }
 
+static PeerFlagPtrs peer_flags(const PeerComm &pc) {
+  PeerFlagPtrs f;
+  for (int q = 0; q < UFE_MAX_RANKS; q++) f.f[q] = q < pc.P ? reinterpret_cast<int *>(pc.base[q] + pc.off_flags) : nullptr;
+  return f;
+}
+static PeerDotPtrs peer_dots(const PeerComm &pc) {
+  PeerDotPtrs d;
+  for (int q = 0; q < UFE_MAX_RANKS; q++) d.d[q] = q < pc.P ? pc.base[q] + pc.off_dots : nullptr;
+  return d;
+}
+
+// Make the SpMV input vector `vec` (global-indexed, owned part valid) usable by the next SpMV:
+// peer mode: publish an epoch to every rank and hand the kernel a PeerView (the halo is read in
+// place from the owners' buffers); otherwise exchange the halo ranges through NCCL.
+static int sync_input(cudaStream_t st, const Comm &comm, const HaloPlan *halo, double *vec, PeerView *pv, bool *use_pv) {
+  *use_pv = false;
+  if (!halo || comm.nranks <= 1) return UFE_OK;
+  PeerComm &pc = comm.peer;
+  if (!pc.on) return ufe_halo_exchange(st, comm, *halo, vec, 0, 1, 2);
+  const int epoch = (int)(++pc.halo_epoch);
+  k_peer_signal<<<1, 32, 0, st>>>(pc.P, pc.me, epoch, peer_flags(pc));
+  UFE_LAUNCH_CHECK();
+  const long long off = vec - pc.base[pc.me];
+  pv->P = pc.P; pv->me = pc.me; pv->epoch = epoch;
+  for (int q = 0; q <= UFE_MAX_RANKS; q++) pv->bounds[q] = q <= pc.P ? pc.bounds[q] : 0x7fffffff;
+  for (int q = 0; q < UFE_MAX_RANKS; q++) pv->xp[q] = q < pc.P ? reinterpret_cast<const double2 *>(pc.base[q] + off) : nullptr;
+  pv->flags = reinterpret_cast<const volatile int *>(pc.base[pc.me] + pc.off_flags);
+  *use_pv = true;
+  return UFE_OK;
+}
+
+static int peer_reduce(cudaStream_t st, const Comm &comm, KrylovWork &kw, int stage, int nd, const double *dots_local,
+                       double rtol, double abstol) {
+  PeerComm &pc = comm.peer;
+  const int epoch = (int)(++pc.red_epoch);
+  k_peer_reduce<<<1, 32, 0, st>>>(pc.P, pc.me, epoch, nd, stage, peer_flags(pc), peer_dots(pc), dots_local, kw.sc, kw.gm, rtol, abstol);
+  UFE_LAUNCH_CHECK();
+  return UFE_OK;
+}
+
 static int allreduce_stage(cudaStream_t st, const Comm &comm, KrylovWork &kw, int stage, int nd, double rtol,
                            double abstol) {
   if (comm.nranks <= 1) return UFE_OK;
+  if (comm.peer.on) return peer_reduce(st, comm, kw, stage, nd, kw.dots_local, rtol, abstol);
   UFE_NCCL(ncclAllReduce(kw.dots_local, kw.dots_local, nd, ncclDouble, ncclSum, comm.nccl, st));
   g_launch_count++;
   k_post<<<1, 1, 0, st>>>(stage, kw.sc, kw.gm, kw.dots_local, nd, rtol, abstol);
@@ -595,10 +705,11 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
   const int n = S.m_loc, r0 = S.r1 - 1, single = comm.nranks <= 1;
   const int G = UFE_RED_BLOCKS, B = UFE_RED_THREADS;
   double *xg = S.x;
+  PeerView pv; bool use_pv = false;
   k_sc_reset<<<1, 1, 0, st>>>(kw.sc, maxits, abstol); UFE_LAUNCH_CHECK();
   if (guess_nonzero) {
-    if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, xg, 0, 1, 2));
-    UFE_TRY(apply_op<0>(st, S, pc, xg, kw.r, nullptr, 0, kw, single, rtol, abstol));
+    UFE_TRY(sync_input(st, comm, halo, xg, &pv, &use_pv));
+    UFE_TRY(apply_op<0>(st, S, pc, xg, kw.r, nullptr, 0, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
   }
   const double *bS = S.bS;
   if (pc) { UFE_TRY(ufe_pclu_apply(st, pc, S.bS, kw.bP)); bS = kw.bP; }
@@ -610,8 +721,8 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
   while (true) {
     for (int b = 0; b < batch; b++, launched++) {
       if (launched > 0) { k_bicg_p<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.pg, kw.sc); UFE_LAUNCH_CHECK(); }
-      if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.pg, 0, 1, 2));
-      UFE_TRY(apply_op<1>(st, S, pc, kw.pg, kw.v, kw.rhat, ST_A, kw, single, rtol, abstol));
+      UFE_TRY(sync_input(st, comm, halo, kw.pg, &pv, &use_pv));
+      UFE_TRY(apply_op<1>(st, S, pc, kw.pg, kw.v, kw.rhat, ST_A, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
       UFE_TRY(allreduce_stage(st, comm, kw, ST_A, 1, rtol, abstol));
       if (pc) {
         k_bicg_s_norm<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.partials, kw.counter, kw.dots_local, kw.sc, single, rtol, abstol);
@@ -620,8 +731,8 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
         k_bicg_xhalf<<<G, B, 0, st>>>(n, r0, xg, kw.pg, kw.sc); UFE_LAUNCH_CHECK();
         k_half_ack<<<1, 1, 0, st>>>(kw.sc); UFE_LAUNCH_CHECK();
       } else { k_bicg_s<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.sc); UFE_LAUNCH_CHECK(); }
-      if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.sg, 0, 1, 2));
-      UFE_TRY(apply_op<2>(st, S, pc, kw.sg, kw.t, nullptr, ST_B, kw, single, rtol, abstol));
+      UFE_TRY(sync_input(st, comm, halo, kw.sg, &pv, &use_pv));
+      UFE_TRY(apply_op<2>(st, S, pc, kw.sg, kw.t, nullptr, ST_B, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
       UFE_TRY(allreduce_stage(st, comm, kw, ST_B, 2, rtol, abstol));
       k_bicg_xr<<<G, B, 0, st>>>(n, r0, xg, kw.pg, kw.sg, kw.t, kw.rhat, kw.r, kw.partials, kw.counter,
                                  kw.dots_local, kw.sc, single, rtol, abstol);
@@ -645,11 +756,12 @@ static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const 
   const double *bS = S.bS;
   if (pc) { UFE_TRY(ufe_pclu_apply(st, pc, S.bS, kw.bP)); bS = kw.bP; }
   bool first = true;
+  PeerView pv; bool use_pv = false;
   while (true) {
     const int have_ax = (!first || guess_nonzero) ? 1 : 0;
     if (have_ax) {
-      if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, xg, 0, 1, 2));
-      UFE_TRY(apply_op<0>(st, S, pc, xg, kw.w, nullptr, 0, kw, single, rtol, abstol));
+      UFE_TRY(sync_input(st, comm, halo, xg, &pv, &use_pv));
+      UFE_TRY(apply_op<0>(st, S, pc, xg, kw.w, nullptr, 0, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
     }
     k_gm_resid<<<G, B, 0, st>>>(n, r0, bS, kw.w, xg, have_ax, (first && !guess_nonzero) ? 1 : 0, kw.partials,
                                 kw.counter, kw.dots_local, kw.sc, kw.gm, single, rtol, abstol);
@@ -658,23 +770,29 @@ static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const 
     first = false;
     for (int j = 0; j < GM_RESTART; j++) {
       k_gm_scale<<<G, B, 0, st>>>(n, r0, kw.w, kw.Vb + (size_t)j * ldv, kw.pg, kw.sc, kw.gm, j); UFE_LAUNCH_CHECK();
-      if (halo) UFE_TRY(ufe_halo_exchange(st, comm, *halo, kw.pg, 0, 1, 2));
-      UFE_TRY(apply_op<0>(st, S, pc, kw.pg, kw.w, nullptr, 0, kw, single, rtol, abstol));
+      UFE_TRY(sync_input(st, comm, halo, kw.pg, &pv, &use_pv));
+      UFE_TRY(apply_op<0>(st, S, pc, kw.pg, kw.w, nullptr, 0, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
       for (int i0 = 0; i0 <= j; i0 += 8) {
         const int cnt = (j + 1 - i0) < 8 ? (j + 1 - i0) : 8;
         k_gm_mdot<8><<<G, B, 0, st>>>(n, kw.Vb, ldv, kw.w, i0, cnt, kw.partials, kw.counter, kw.dots_local, kw.sc);
         UFE_LAUNCH_CHECK();
       }
-      if (!single) {
-        UFE_NCCL(ncclAllReduce(kw.dots_local, kw.dots_local, j + 1, ncclDouble, ncclSum, comm.nccl, st));
-        g_launch_count++;
+      if (!single && comm.peer.on) {
+        UFE_TRY(peer_reduce(st, comm, kw, -1, j + 1, kw.dots_local, rtol, abstol));     // sums straight into hcol
+      } else {
+        if (!single) {
+          UFE_NCCL(ncclAllReduce(kw.dots_local, kw.dots_local, j + 1, ncclDouble, ncclSum, comm.nccl, st));
+          g_launch_count++;
+        }
+        k_gm_sethcol<<<1, 1, 0, st>>>(kw.sc, kw.gm, kw.dots_local, j + 1);
+        UFE_LAUNCH_CHECK();
       }
-      k_gm_sethcol<<<1, 1, 0, st>>>(kw.sc, kw.gm, kw.dots_local, j + 1);
-      UFE_LAUNCH_CHECK();
       k_gm_update<<<G, B, 0, st>>>(n, kw.Vb, ldv, kw.w, j, kw.partials, kw.counter, kw.dots_local + 40, kw.sc,
                                    kw.gm, single, rtol, abstol);
       UFE_LAUNCH_CHECK();
-      if (!single) {
+      if (!single && comm.peer.on) {
+        UFE_TRY(peer_reduce(st, comm, kw, ST_GM_NORM, 1, kw.dots_local + 40, rtol, abstol));
+      } else if (!single) {
         UFE_NCCL(ncclAllReduce(kw.dots_local + 40, kw.dots_local + 40, 1, ncclDouble, ncclSum, comm.nccl, st));
         g_launch_count++;
         k_post<<<1, 1, 0, st>>>(ST_GM_NORM, kw.sc, kw.gm, kw.dots_local + 40, 1, rtol, abstol); UFE_LAUNCH_CHECK();
