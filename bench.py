@@ -419,6 +419,7 @@ def main():
         "solve": {"n_visc_its": last.n_visc_its, "n_Axb_its": last.n_Axb_its, "flags": last.flags, "L2_uv": last.L2_uv,
                   "ms_closures": last.ms_closures, "ms_assembly": last.ms_assembly, "ms_krylov": last.ms_krylov,
                   "wall_ms_per_step": 1e3 * wall_value / args.steps, "create_s": t_create},
+        "comm": ("single GPU" if world == 1 else ("peer memory (IPC/NVLink) inside the Krylov loop, NCCL outside" if last.reserved else "NCCL")),
         "e2e": e2e, "warm": warm, "gpu_launches": int(sum(i.gpu_launches for i in infos)),
         "roofline": roofline, "roofline_bench_workload": roofline_small, "krylov_iteration": krylov_iteration,
         "other_kernels_large_mesh": other_kernels, "clocks": clocks,

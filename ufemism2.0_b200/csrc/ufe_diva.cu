@@ -4,6 +4,7 @@
 // solve_SSA_DIVA_linearised : .../solve_linearised_SSA_DIVA.f90:23-178
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -508,6 +509,17 @@ extern "C" int ufe_diva_create(const ufe_mesh *mesh, const ufe_config *cfg, cons
   if (h->comm.nranks > 1) {
     if ((rc = peer_setup(h)) != UFE_OK) return fail(rc);
     if ((rc = ufe_krylov_alloc(h->kw, 2 * dm.nTri, 2 * nt_loc, true, h->sym + h->comm.peer.off_pg, h->sym + h->comm.peer.off_sg)) != UFE_OK) return fail(rc);
+    if (h->comm.peer.on) {      // device-side description of the peers for the fused reductions / signals
+      const PeerComm &pc = h->comm.peer;
+      PeerDev pd;
+      memset(&pd, 0, sizeof pd);
+      pd.P = pc.P; pd.me = pc.me;
+      for (int q = 0; q < pc.P; q++) { pd.flags[q] = reinterpret_cast<int *>(pc.base[q] + pc.off_flags); pd.dots[q] = pc.base[q] + pc.off_dots; }
+      if (cudaMalloc(&h->kw.peer_dev, sizeof pd) != cudaSuccess ||
+          cudaMemcpy(h->kw.peer_dev, &pd, sizeof pd, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(reinterpret_cast<char *>(h->kw.sc) + offsetof(KrylovScalars, peer), &h->kw.peer_dev, sizeof(PeerDev *),
+                     cudaMemcpyHostToDevice) != cudaSuccess) { ufe_set_error("peer description upload failed"); return fail(UFE_ERR_CUDA); }
+    }
   } else {
     if ((rc = dalloc(&h->S.x, (size_t)2 * nT)) != UFE_OK) return fail(rc);
     if ((rc = ufe_krylov_alloc(h->kw, 2 * dm.nTri, 2 * nt_loc, true)) != UFE_OK) return fail(rc);

@@ -73,6 +73,7 @@ struct DevMesh {
       *VBI = nullptr, *TriBI = nullptr;
 };
 
+struct PeerDev;
 // Krylov scalars living in device memory
 struct KrylovScalars {
   double dots[8];       // raw (all-reduced) dot products of the current stage
@@ -80,6 +81,7 @@ struct KrylovScalars {
   double bnorm, ttol, rnorm, dtol_bnorm, abstol;
   int its, done, reason, maxits;   // reason: 2 rtol, 3 atol, -3 maxits, -4 dtol, -5 breakdown
   int jcount, finalized, pad0, pad1; // GMRES: steps completed in the current cycle; x updated after convergence
+  const struct PeerDev *peer;        // several ranks with peer-memory communication, else nullptr
 };
 
 struct KrylovWork {
@@ -97,6 +99,7 @@ struct KrylovWork {
   KrylovScalars *sc_host = nullptr;  // pinned mirror
   double *pctmp = nullptr, *bP = nullptr;   // explicit-preconditioner work vectors (owned length)
   bool ext_vecs = false;                    // pg / sg live in the symmetric peer buffer (not freed here)
+  PeerDev *peer_dev = nullptr;              // device copy of the peer description
 };
 
 #define UFE_MAX_RANKS 8
@@ -115,6 +118,8 @@ struct PeerComm {
   long long halo_epoch = 0, red_epoch = 0;   // host-side counters (identical on every rank)
 };
 
+// device-resident description of the peers (pointed to by KrylovScalars::peer)
+struct PeerDev { int P, me; int *flags[UFE_MAX_RANKS]; double *dots[UFE_MAX_RANKS]; };
 struct PeerFlagPtrs { int *f[UFE_MAX_RANKS]; };      // every rank's flag array (P2P mapped)
 struct PeerDotPtrs { double *d[UFE_MAX_RANKS]; };    // every rank's dot-slot array (P2P mapped)
 

@@ -143,15 +143,61 @@ __global__ void k_gm_sethcol(const KrylovScalars *sc, double *gm, const double *
 
 // finish a reduction stage inside the producing kernel (single GPU) or leave the local
 // partial sums in dots_local for the all-reduce (multi GPU)
+// `single`:  > 0 one rank: finish the stage here;  == 0 several ranks over NCCL: leave the local
+// partial sums in dots_local for the all-reduce;  < 0 several ranks with peer memory, epoch =
+// -single: the last block stores its partial sums into every rank's slot (NVLink P2P), waits
+// for everybody's, sums them in rank order and runs the recurrence -- the collective is part of
+// the producing kernel, there is no separate reduction launch.
 template <int NV>
 __device__ __forceinline__ void finish_stage(double (&acc)[NV], int stage, double *partials, unsigned *counter,
                                              double *dots_local, KrylovScalars *sc, double *gm, int single,
                                              double rtol, double abstol) {
   if (reduce_publish<NV>(acc, partials, counter, dots_local)) {
-    if (single && threadIdx.x == 0) {
-      for (int i = 0; i < NV; i++) sc->dots[i] = dots_local[i];
-      post_reduce(stage, sc, gm, rtol, abstol);
+    if (single > 0) {
+      if (threadIdx.x == 0) {
+        for (int i = 0; i < NV; i++) sc->dots[i] = dots_local[i];
+        post_reduce(stage, sc, gm, rtol, abstol);
+      }
+    } else if (single < 0) {
+      const PeerDev *pd = sc->peer;
+      const int epoch = -single, par = epoch & 1, P = pd->P, me = pd->me, t = threadIdx.x;
+      if (t < P) {
+        double *dst = pd->dots[t] + ((size_t)par * P + me) * UFE_PEER_DOTS;
+        for (int i = 0; i < NV; i++) dst[i] = dots_local[i];
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(pd->flags[t] + P + par * P + me) = epoch;
+        const volatile int *mine = reinterpret_cast<const volatile int *>(pd->flags[me] + P + par * P + t);
+        while (*mine < epoch) {}
+      }
+      __syncthreads();
+      if (t == 0) {
+        __threadfence_system();
+        const volatile double *src = pd->dots[me] + (size_t)par * P * UFE_PEER_DOTS;
+        for (int i = 0; i < NV; i++) { double sum = 0.0; for (int q = 0; q < P; q++) sum += src[(size_t)q * UFE_PEER_DOTS + i]; sc->dots[i] = sum; }
+        post_reduce(stage, sc, gm, rtol, abstol);
+      }
     }
+  }
+}
+
+// tail of a kernel that produces an SpMV input vector without reducing anything: the last block
+// to finish publishes `epoch` to every peer (replaces a separate signal launch); epoch 0 = off
+__device__ __forceinline__ void signal_peers_when_done(unsigned *counter, const KrylovScalars *sc, int epoch) {
+  if (epoch <= 0) return;
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  const PeerDev *pd = sc->peer;
+  if ((int)threadIdx.x < pd->P && (int)threadIdx.x != pd->me) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int *>(pd->flags[threadIdx.x] + pd->me) = epoch;
   }
 }
 
@@ -416,21 +462,23 @@ k_bicg_init(int n, int r0, const double *__restrict__ b, double *__restrict__ r,
 // p = r + beta (p - omega v)
 __global__ void __launch_bounds__(UFE_RED_THREADS)
 k_bicg_p(int n, int r0, const double *__restrict__ r, const double *__restrict__ v, double *__restrict__ pg,
-         const KrylovScalars *sc) {
+         const KrylovScalars *sc, unsigned *counter, int sig_epoch) {
   if (sc->done) return;
   const double beta = sc->beta, omega = sc->omega;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     pg[r0 + i] = r[i] + beta * (pg[r0 + i] - omega * v[i]);
+  signal_peers_when_done(counter, sc, sig_epoch);
 }
 
 // s = r - alpha v
 __global__ void __launch_bounds__(UFE_RED_THREADS)
 k_bicg_s(int n, int r0, const double *__restrict__ r, const double *__restrict__ v, double *__restrict__ sg,
-         const KrylovScalars *sc) {
+         const KrylovScalars *sc, unsigned *counter, int sig_epoch) {
   if (sc->done) return;
   const double alpha = sc->alpha;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     sg[r0 + i] = r[i] - alpha * v[i];
+  signal_peers_when_done(counter, sc, sig_epoch);
 }
 
 // s = r - alpha v with (s,s): used with an explicit preconditioner, where an iteration is
@@ -507,13 +555,14 @@ k_gm_resid(int n, int r0, const double *__restrict__ b, double *__restrict__ w, 
 // V_j = w * inv_hn -> Vb[j], pg
 __global__ void __launch_bounds__(UFE_RED_THREADS)
 k_gm_scale(int n, int r0, const double *__restrict__ w, double *__restrict__ Vj, double *__restrict__ pg,
-           const KrylovScalars *sc, const double *gm, int j) {
+           const KrylovScalars *sc, const double *gm, int j, unsigned *counter, int sig_epoch) {
   if (sc->done || sc->jcount != j) return;
   const double inv = *GM_INVHN(gm);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double vi = w[i] * inv;
     Vj[i] = vi; pg[r0 + i] = vi;
   }
+  signal_peers_when_done(counter, sc, sig_epoch);
 }
 
 // h_i = (V_i, w), i = i0 .. i0+NV-1 (<= j)
@@ -638,7 +687,7 @@ void ufe_krylov_free(KrylovWork &kw) {
   cudaFree(kw.r); cudaFree(kw.rhat); cudaFree(kw.v); cudaFree(kw.t); cudaFree(kw.w);
   if (!kw.ext_vecs) { cudaFree(kw.pg); cudaFree(kw.sg); }
   cudaFree(kw.Vb); cudaFree(kw.partials); cudaFree(kw.dots_local);
-  cudaFree(kw.counter); cudaFree(kw.sc); cudaFree(kw.gm); cudaFree(kw.pctmp); cudaFree(kw.bP);
+  cudaFree(kw.counter); cudaFree(kw.sc); cudaFree(kw.gm); cudaFree(kw.pctmp); cudaFree(kw.bP); cudaFree(kw.peer_dev);
   if (kw.sc_host) cudaFreeHost(kw.sc_host);
   kw = KrylovWork();
 }
@@ -657,14 +706,18 @@ static PeerDotPtrs peer_dots(const PeerComm &pc) {
 // Make the SpMV input vector `vec` (global-indexed, owned part valid) usable by the next SpMV:
 // peer mode: publish an epoch to every rank and hand the kernel a PeerView (the halo is read in
 // place from the owners' buffers); otherwise exchange the halo ranges through NCCL.
-static int sync_input(cudaStream_t st, const Comm &comm, const HaloPlan *halo, double *vec, PeerView *pv, bool *use_pv) {
+static int sync_input(cudaStream_t st, const Comm &comm, const HaloPlan *halo, double *vec, PeerView *pv, bool *use_pv,
+                      int pre_epoch = 0) {
   *use_pv = false;
   if (!halo || comm.nranks <= 1) return UFE_OK;
   PeerComm &pc = comm.peer;
   if (!pc.on) return ufe_halo_exchange(st, comm, *halo, vec, 0, 1, 2);
-  const int epoch = (int)(++pc.halo_epoch);
-  k_peer_signal<<<1, 32, 0, st>>>(pc.P, pc.me, epoch, peer_flags(pc));
-  UFE_LAUNCH_CHECK();
+  int epoch = pre_epoch;          // > 0: the producing kernel has published this epoch itself
+  if (epoch <= 0) {
+    epoch = (int)(++pc.halo_epoch);
+    k_peer_signal<<<1, 32, 0, st>>>(pc.P, pc.me, epoch, peer_flags(pc));
+    UFE_LAUNCH_CHECK();
+  }
   const long long off = vec - pc.base[pc.me];
   pv->P = pc.P; pv->me = pc.me; pv->epoch = epoch;
   for (int q = 0; q <= UFE_MAX_RANKS; q++) pv->bounds[q] = q <= pc.P ? pc.bounds[q] : 0x7fffffff;
@@ -686,7 +739,7 @@ static int peer_reduce(cudaStream_t st, const Comm &comm, KrylovWork &kw, int st
 static int allreduce_stage(cudaStream_t st, const Comm &comm, KrylovWork &kw, int stage, int nd, double rtol,
                            double abstol) {
   if (comm.nranks <= 1) return UFE_OK;
-  if (comm.peer.on) return peer_reduce(st, comm, kw, stage, nd, kw.dots_local, rtol, abstol);
+  if (comm.peer.on) return UFE_OK;     // fused into the producing kernel (finish_stage, single < 0)
   UFE_NCCL(ncclAllReduce(kw.dots_local, kw.dots_local, nd, ncclDouble, ncclSum, comm.nccl, st));
   g_launch_count++;
   k_post<<<1, 1, 0, st>>>(stage, kw.sc, kw.gm, kw.dots_local, nd, rtol, abstol);
@@ -703,9 +756,13 @@ static int poll(cudaStream_t st, KrylovWork &kw) {
 static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm,
                         const HaloPlan *halo, double rtol, double abstol, int maxits, int guess_nonzero, PcLU *pc) {
   const int n = S.m_loc, r0 = S.r1 - 1, single = comm.nranks <= 1;
+  const bool peer = !single && comm.peer.on && halo;
   const int G = UFE_RED_BLOCKS, B = UFE_RED_THREADS;
   double *xg = S.x;
   PeerView pv; bool use_pv = false;
+  // `single` argument of a reducing kernel: 1 one rank, 0 NCCL, -epoch peer memory (fused all-to-all)
+  auto sarg = [&]() { return single ? 1 : (peer ? -(int)(++comm.peer.red_epoch) : 0); };
+  auto sig = [&]() { return peer ? (int)(++comm.peer.halo_epoch) : 0; };   // epoch a producer kernel publishes itself
   k_sc_reset<<<1, 1, 0, st>>>(kw.sc, maxits, abstol); UFE_LAUNCH_CHECK();
   if (guess_nonzero) {
     UFE_TRY(sync_input(st, comm, halo, xg, &pv, &use_pv));
@@ -714,28 +771,30 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
   const double *bS = S.bS;
   if (pc) { UFE_TRY(ufe_pclu_apply(st, pc, S.bS, kw.bP)); bS = kw.bP; }
   k_bicg_init<<<G, B, 0, st>>>(n, r0, bS, kw.r, kw.rhat, kw.pg, xg, guess_nonzero, kw.partials, kw.counter,
-                               kw.dots_local, kw.sc, single, rtol, abstol);
+                               kw.dots_local, kw.sc, sarg(), rtol, abstol);
   UFE_LAUNCH_CHECK();
   UFE_TRY(allreduce_stage(st, comm, kw, ST_INIT, 2, rtol, abstol));
   int launched = 0, batch = (pc && single) ? 1 : 4;     // an exact block solve converges in the first (half) step
   while (true) {
     for (int b = 0; b < batch; b++, launched++) {
-      if (launched > 0) { k_bicg_p<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.pg, kw.sc); UFE_LAUNCH_CHECK(); }
-      UFE_TRY(sync_input(st, comm, halo, kw.pg, &pv, &use_pv));
-      UFE_TRY(apply_op<1>(st, S, pc, kw.pg, kw.v, kw.rhat, ST_A, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
+      int ep = 0;
+      if (launched > 0) { ep = sig(); k_bicg_p<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.pg, kw.sc, kw.counter, ep); UFE_LAUNCH_CHECK(); }
+      UFE_TRY(sync_input(st, comm, halo, kw.pg, &pv, &use_pv, ep));
+      UFE_TRY(apply_op<1>(st, S, pc, kw.pg, kw.v, kw.rhat, ST_A, kw, sarg(), rtol, abstol, use_pv ? &pv : nullptr));
       UFE_TRY(allreduce_stage(st, comm, kw, ST_A, 1, rtol, abstol));
+      ep = 0;
       if (pc) {
-        k_bicg_s_norm<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.partials, kw.counter, kw.dots_local, kw.sc, single, rtol, abstol);
+        k_bicg_s_norm<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.partials, kw.counter, kw.dots_local, kw.sc, sarg(), rtol, abstol);
         UFE_LAUNCH_CHECK();
         UFE_TRY(allreduce_stage(st, comm, kw, ST_S, 1, rtol, abstol));
         k_bicg_xhalf<<<G, B, 0, st>>>(n, r0, xg, kw.pg, kw.sc); UFE_LAUNCH_CHECK();
         k_half_ack<<<1, 1, 0, st>>>(kw.sc); UFE_LAUNCH_CHECK();
-      } else { k_bicg_s<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.sc); UFE_LAUNCH_CHECK(); }
-      UFE_TRY(sync_input(st, comm, halo, kw.sg, &pv, &use_pv));
-      UFE_TRY(apply_op<2>(st, S, pc, kw.sg, kw.t, nullptr, ST_B, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
+      } else { ep = sig(); k_bicg_s<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.sc, kw.counter, ep); UFE_LAUNCH_CHECK(); }
+      UFE_TRY(sync_input(st, comm, halo, kw.sg, &pv, &use_pv, ep));
+      UFE_TRY(apply_op<2>(st, S, pc, kw.sg, kw.t, nullptr, ST_B, kw, sarg(), rtol, abstol, use_pv ? &pv : nullptr));
       UFE_TRY(allreduce_stage(st, comm, kw, ST_B, 2, rtol, abstol));
       k_bicg_xr<<<G, B, 0, st>>>(n, r0, xg, kw.pg, kw.sg, kw.t, kw.rhat, kw.r, kw.partials, kw.counter,
-                                 kw.dots_local, kw.sc, single, rtol, abstol);
+                                 kw.dots_local, kw.sc, sarg(), rtol, abstol);
       UFE_LAUNCH_CHECK();
       UFE_TRY(allreduce_stage(st, comm, kw, ST_C, 2, rtol, abstol));
     }
@@ -752,6 +811,9 @@ static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const 
   const int G = UFE_RED_BLOCKS, B = UFE_RED_THREADS;
   const long long ldv = n;
   double *xg = S.x;
+  const bool peer = !single && comm.peer.on && halo;
+  auto sarg = [&]() { return single ? 1 : (peer ? -(int)(++comm.peer.red_epoch) : 0); };
+  auto sig = [&]() { return peer ? (int)(++comm.peer.halo_epoch) : 0; };
   if (reset) { k_sc_reset<<<1, 1, 0, st>>>(kw.sc, maxits, abstol); UFE_LAUNCH_CHECK(); }
   const double *bS = S.bS;
   if (pc) { UFE_TRY(ufe_pclu_apply(st, pc, S.bS, kw.bP)); bS = kw.bP; }
@@ -764,20 +826,21 @@ static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const 
       UFE_TRY(apply_op<0>(st, S, pc, xg, kw.w, nullptr, 0, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
     }
     k_gm_resid<<<G, B, 0, st>>>(n, r0, bS, kw.w, xg, have_ax, (first && !guess_nonzero) ? 1 : 0, kw.partials,
-                                kw.counter, kw.dots_local, kw.sc, kw.gm, single, rtol, abstol);
+                                kw.counter, kw.dots_local, kw.sc, kw.gm, sarg(), rtol, abstol);
     UFE_LAUNCH_CHECK();
     UFE_TRY(allreduce_stage(st, comm, kw, ST_GM_INIT, 2, rtol, abstol));
     first = false;
     for (int j = 0; j < GM_RESTART; j++) {
-      k_gm_scale<<<G, B, 0, st>>>(n, r0, kw.w, kw.Vb + (size_t)j * ldv, kw.pg, kw.sc, kw.gm, j); UFE_LAUNCH_CHECK();
-      UFE_TRY(sync_input(st, comm, halo, kw.pg, &pv, &use_pv));
+      const int ep = sig();
+      k_gm_scale<<<G, B, 0, st>>>(n, r0, kw.w, kw.Vb + (size_t)j * ldv, kw.pg, kw.sc, kw.gm, j, kw.counter, ep); UFE_LAUNCH_CHECK();
+      UFE_TRY(sync_input(st, comm, halo, kw.pg, &pv, &use_pv, ep));
       UFE_TRY(apply_op<0>(st, S, pc, kw.pg, kw.w, nullptr, 0, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
       for (int i0 = 0; i0 <= j; i0 += 8) {
         const int cnt = (j + 1 - i0) < 8 ? (j + 1 - i0) : 8;
         k_gm_mdot<8><<<G, B, 0, st>>>(n, kw.Vb, ldv, kw.w, i0, cnt, kw.partials, kw.counter, kw.dots_local, kw.sc);
         UFE_LAUNCH_CHECK();
       }
-      if (!single && comm.peer.on) {
+      if (peer) {
         UFE_TRY(peer_reduce(st, comm, kw, -1, j + 1, kw.dots_local, rtol, abstol));     // sums straight into hcol
       } else {
         if (!single) {
@@ -788,11 +851,9 @@ static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const 
         UFE_LAUNCH_CHECK();
       }
       k_gm_update<<<G, B, 0, st>>>(n, kw.Vb, ldv, kw.w, j, kw.partials, kw.counter, kw.dots_local + 40, kw.sc,
-                                   kw.gm, single, rtol, abstol);
+                                   kw.gm, sarg(), rtol, abstol);
       UFE_LAUNCH_CHECK();
-      if (!single && comm.peer.on) {
-        UFE_TRY(peer_reduce(st, comm, kw, ST_GM_NORM, 1, kw.dots_local + 40, rtol, abstol));
-      } else if (!single) {
+      if (!single && !peer) {
         UFE_NCCL(ncclAllReduce(kw.dots_local + 40, kw.dots_local + 40, 1, ncclDouble, ncclSum, comm.nccl, st));
         g_launch_count++;
         k_post<<<1, 1, 0, st>>>(ST_GM_NORM, kw.sc, kw.gm, kw.dots_local + 40, 1, rtol, abstol); UFE_LAUNCH_CHECK();
