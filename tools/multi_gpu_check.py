@@ -25,24 +25,41 @@ def rel(a, b, ref):
     return np.linalg.norm(a - b) / np.linalg.norm(ref), np.abs(a - b).max() / np.abs(ref).max()
 
 ok = True
-for name, (mesh, C, ice) in (('ISMIP-HOM A', experiments.ISMIP_HOM('A', 160e3, 41)), ('ISMIP-HOM C', experiments.ISMIP_HOM('C', 160e3, 31)),
-                             ('MISMIP+ 8km', experiments.MISMIPplus(8e3))):
+cases = []
+for pc_name, meth in (('auto', 'bicgstab'), ('bjacobi2', 'bicgstab'), ('bjacobi2', 'gmres'), ('auto', 'gmres')):
+    cases.append(('ISMIP-HOM A', experiments.ISMIP_HOM('A', 160e3, 41), pc_name, meth))
+cases.append(('ISMIP-HOM C', experiments.ISMIP_HOM('C', 160e3, 31), 'auto', 'bicgstab'))
+cases.append(('MISMIP+ 8km', experiments.MISMIPplus(8e3), 'auto', 'bicgstab'))
+cases.append(('MISMIP+ 8km strip-only', experiments.MISMIPplus(8e3), 'bjacobi_lu', 'bicgstab'))
+oracle_cache = {}
+for name, (mesh, C, ice), pc_name, meth in cases:
     C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
+    C.b200_krylov_pc, C.b200_krylov_method = pc_name, meth
+    C.b200_krylov_pc_strip_only = name.endswith('strip-only')
     if name.startswith('MISMIP'): C.visc_it_nit = 8
     S = diva.initialise_DIVA_solver(mesh, C, make_comm())
     t = time.time(); info = S.solve_DIVA(ice); wall = time.time() - t
+    sec = S.calc_secondary_velocities()
     own = S.ownership()
     if rank == 0:
         import oracle as O
-        O.build(); O.calc_all_matrix_operators_mesh(mesh)
-        D = O.new_DIVA_state(mesh); nv, _ = O.solve_DIVA(mesh, ice, C, D, 'direct')
+        O.build()
+        key = name.split(' strip')[0]
+        if key not in oracle_cache:
+            O.calc_all_matrix_operators_mesh(mesh)
+            D = O.new_DIVA_state(mesh); nv, _ = O.solve_DIVA(mesh, ice, C, D, 'direct')
+            oracle_cache[key] = (D, nv, mesh)
+        D, nv, mesh0 = oracle_cache[key]
         ref = np.concatenate([D['u_vav_b'], D['v_vav_b']])
         ru, rv = rel(S.u_vav_b, D['u_vav_b'], ref), rel(S.v_vav_b, D['v_vav_b'], ref)
         r3 = np.abs(S.u_3D_b - D['u_3D_b']).max() / np.abs(D['u_3D_b']).max()
-        good = max(ru + rv) < 1e-6 and abs(info.n_visc_its - nv) <= 1 and r3 < 1e-6
+        want = O.calc_secondary_velocities(mesh0, S.u_3D_b, S.v_3D_b)
+        rs = max(np.abs(sec[k] - w).max() / max(np.abs(w).max(), 1e-300) for k, w in want.items())
+        good = max(ru + rv) < 1e-6 and abs(info.n_visc_its - nv) <= 1 and r3 < 1e-6 and rs < 1e-12
         ok &= good
-        print(f'{name}: ranks {world} own {own} Picard {info.n_visc_its} (oracle {nv}) Krylov {info.n_Axb_its} flags {info.flags} '
-              f'u {ru} v {rv} u3D {r3:.2e} wall {wall:.3f}s {"OK" if good else "MISMATCH"}', flush=True)
+        print(f'{name} [{meth}+{pc_name}]: ranks {world} comm {"peer" if info.reserved else "nccl"} Picard {info.n_visc_its} (oracle {nv}) '
+              f'Krylov {info.n_Axb_its} flags {info.flags} u {ru[1]:.2e} v {rv[1]:.2e} u3D {r3:.2e} secondary {rs:.1e} wall {wall:.3f}s '
+              f'{"OK" if good else "MISMATCH"}', flush=True)
     S.close()
 dist.barrier()
 if rank == 0:
