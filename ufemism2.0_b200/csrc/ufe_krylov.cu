@@ -13,8 +13,13 @@
 // has set `done`, the remaining kernels of a batch return immediately, so the solution
 // and the reported iteration count are exactly those of the converged iteration.
 // Dot products are reduced in a fixed order (per-block partials summed by the last block)
-// => bitwise reproducible run to run.  Multi-GPU: one ncclAllReduce per reduction stage
-// on the batched scalars, halo exchange of the SpMV input before each MatMult.
+// => bitwise reproducible run to run.  Multi-GPU (PeerComm, ufe_internal.cuh): the SpMV reads the
+// halo entries of its input vector in place from the owners' IPC-mapped buffers, and the last
+// block of every reducing kernel exchanges the partial sums with all peers by P2P stores and sums
+// them in rank order -- no collective launch inside an iteration.  Without peer access the same
+// loop runs over NCCL (ncclSend/Recv halo ranges, one ncclAllReduce per reduction stage).
+// An explicit left preconditioner (ufe_pclu.cu) can be plugged in: the operator becomes
+// M^-1 A and BiCGStab gains a half-step exit.
 #include "ufe_internal.cuh"
 #include "ufe_reduce.cuh"
 
