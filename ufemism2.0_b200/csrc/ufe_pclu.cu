@@ -148,11 +148,15 @@ __global__ void k_pad_identity(int n_loc, int g, int K, double *__restrict__ D) 
 // Items whose A or B operand does not exist (no neighbour on that side) are skipped.
 // ------------------------------------------------------------------------------------
 // tile = (16 MI) x (16 NI); MI x NI register micro-tile per thread (rows ty + 16 p, columns tx + 16 q)
+// `pair`: two independent products per item in one launch (blockIdx.z & 1 selects the triple)
+struct GemmOps { Opnd A, B, C; };
 template <int MI, int NI>
 __global__ void __launch_bounds__(256)
-k_bgemm(int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha, double beta) {
+k_bgemm(int g, int K, int s, int kept, GemmOps o0, GemmOps o1, int pair, double alpha, double beta) {
   constexpr int TMv = 16 * MI, TNv = 16 * NI, BROWS = 256 / TNv;     // B rows staged per pass
-  const int z = blockIdx.z, node = (2 * z + 1 + kept) * s - 1;
+  const int z = pair ? (int)blockIdx.z >> 1 : (int)blockIdx.z, node = (2 * z + 1 + kept) * s - 1;
+  const GemmOps &o = (pair && (blockIdx.z & 1)) ? o1 : o0;
+  const Opnd &A = o.A, &B = o.B, &C = o.C;
   const long long ia = opnd_block(A, node, z, K), ib = opnd_block(B, node, z, K), ic = opnd_block(C, node, z, K);
   if (ia < 0 || ib < 0 || ic < 0) return;
   const size_t gg = (size_t)g * g;
@@ -207,14 +211,21 @@ k_bgemm(int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha, dou
 }
 
 // picks the tile so that small batches (upper reduction levels) still fill the GPU
+static void launch_bgemm2(cudaStream_t st, int items, int g, int K, int s, int kept, const GemmOps &o0, const GemmOps &o1, int pair,
+                          double alpha, double beta) {
+  if (items <= 0) return;
+  const int nz = pair ? 2 * items : items;
+  const long long big = (long long)nz * ((g + 127) / 128) * (g / 64), mid = (long long)nz * (g / 64) * (g / 64);
+  if (big >= 296) k_bgemm<8, 4><<<dim3(g / 64, (g + 127) / 128, nz), 256, 0, st>>>(g, K, s, kept, o0, o1, pair, alpha, beta);
+  else if (mid >= 296) k_bgemm<4, 4><<<dim3(g / 64, g / 64, nz), 256, 0, st>>>(g, K, s, kept, o0, o1, pair, alpha, beta);
+  else k_bgemm<2, 2><<<dim3(g / 32, g / 32, nz), 256, 0, st>>>(g, K, s, kept, o0, o1, pair, alpha, beta);
+  g_launch_count++;
+}
+// picks the tile so that small batches (upper reduction levels) still fill the GPU
 static void launch_bgemm(cudaStream_t st, int items, int g, int K, int s, int kept, Opnd A, Opnd B, Opnd C, double alpha,
                          double beta) {
-  if (items <= 0) return;
-  const long long big = (long long)items * ((g + 127) / 128) * (g / 64), mid = (long long)items * (g / 64) * (g / 64);
-  if (big >= 296) k_bgemm<8, 4><<<dim3(g / 64, (g + 127) / 128, items), 256, 0, st>>>(g, K, s, kept, A, B, C, alpha, beta);
-  else if (mid >= 296) k_bgemm<4, 4><<<dim3(g / 64, g / 64, items), 256, 0, st>>>(g, K, s, kept, A, B, C, alpha, beta);
-  else k_bgemm<2, 2><<<dim3(g / 32, g / 32, items), 256, 0, st>>>(g, K, s, kept, A, B, C, alpha, beta);
-  g_launch_count++;
+  const GemmOps o{A, B, C};
+  launch_bgemm2(st, items, g, K, s, kept, o, o, 0, alpha, beta);
 }
 
 // zero the blocks of a level's items (for outputs whose producing GEMM may be skipped)
@@ -526,8 +537,7 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
     g_launch_count += 3 * nbk;
     const Opnd Dn{pc->D, 0, 0}, Pn{pc->Pm, 0, 0}, Qn{pc->Qm, 0, 0};
     const Opnd Le{pc->LS, 2, lv.base}, Ue{pc->US, 2, lv.base};               // this level, eliminated (position 2z)
-    launch_bgemm(st, lv.nE, g, K, s, 0, Dn, Le, Pn, 1.0, 0.0);
-    launch_bgemm(st, lv.nE, g, K, s, 0, Dn, Ue, Qn, 1.0, 0.0);
+    launch_bgemm2(st, lv.nE, g, K, s, 0, GemmOps{Dn, Le, Pn}, GemmOps{Dn, Ue, Qn}, 1, 1.0, 0.0);     // P = Dinv L, Q = Dinv U
     if (lv.nK > 0) {
       const int nbase = pc->lev[l + 1].base;
       const Opnd Lk{pc->LS, 2, lv.base + 1}, Uk{pc->US, 2, lv.base + 1};     // this level, kept (position 2z+1)
@@ -535,9 +545,8 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
       const Opnd L2n{pc->LS, 1, nbase}, U2n{pc->US, 1, nbase};               // next level (position z)
       launch_bgemm(st, lv.nK, g, K, s, 1, Lk, Qa, Dn, -1.0, 1.0);       // D_i -= L_i Q_a
       launch_bgemm(st, lv.nK, g, K, s, 1, Uk, Pb, Dn, -1.0, 1.0);       // D_i -= U_i P_b
-      launch_bgemm(st, lv.nK, g, K, s, 1, Lk, Pa, L2n, -1.0, 0.0);      // L_i' = -L_i P_a
       k_bzero<<<dim3(32, 1, lv.nK), 256, 0, st>>>(g, K, s, 1, U2n);     // right neighbour may not exist
-      launch_bgemm(st, lv.nK, g, K, s, 1, Uk, Qb, U2n, -1.0, 0.0);      // U_i' = -U_i Q_b
+      launch_bgemm2(st, lv.nK, g, K, s, 1, GemmOps{Lk, Pa, L2n}, GemmOps{Uk, Qb, U2n}, 1, -1.0, 0.0);   // L_i' = -L_i P_a, U_i' = -U_i Q_b
       g_launch_count += 1;
     }
     if (cudaGetLastError() != cudaSuccess) { ufe_set_error("bjacobi_lu factorisation launch failed"); return UFE_ERR_CUDA; }
