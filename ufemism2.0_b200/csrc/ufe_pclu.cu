@@ -242,48 +242,52 @@ __global__ void k_bzero(int g, int K, int s, int kept, Opnd C) {
 // For pivot block P:  Ipp = inv(A_PP);  A_PJ <- Ipp A_PJ (J != P);  A_IJ <- A_IJ - A_IP A_PJ
 // (I,J != P);  A_IP <- -A_IP Ipp;  A_PP <- Ipp.
 // ------------------------------------------------------------------------------------
-// pivot block inverse, one WARP per eliminated node: ipp <- inv(A_PP).  Lane l holds row l of
-// [S | I] in registers (fully unrolled, no dynamic register indexing); at step p the pivot lane is
-// the unused lane with the largest |S[.][p]| (partial pivoting without moving rows), its scaled
-// row is broadcast by shuffles and eliminated from every other lane.  Row p of the inverse ends
-// up in the lane that was the pivot of step p.
-__global__ void __launch_bounds__(32)
-k_gjb_pivot(int g, int s, int b, const double *__restrict__ D, double *__restrict__ ipp) {
-  const int z = blockIdx.z, node = (2 * z + 1) * s - 1, lane = threadIdx.x;
-  const double *A = D + (size_t)node * g * g + (size_t)(b * NB + lane) * g + b * NB;
-  double S[NB], I2[NB];
-#pragma unroll
-  for (int j = 0; j < NB; j++) { S[j] = A[j]; I2[j] = (j == lane) ? 1.0 : 0.0; }
-  bool used = false;
-  int myp = 0;                                   // the step this lane was the pivot of
-#pragma unroll
+// 32 x 32 inverse in shared memory by 1024 threads (i, j): Gauss-Jordan on [S | I2] with partial
+// pivoting tracked as a row permutation (no physical swaps, three barriers per pivot).  On return
+// Ip = S^-1.  The inverse is unique, so the pivoting leaves no trace outside this routine.
+__device__ __forceinline__ void invert32(double (*S)[NB + 1], double (*I2)[NB + 1], double (*Ip)[NB + 1], int *perm,
+                                         int i, int j) {
+  I2[i][j] = (i == j) ? 1.0 : 0.0;
+  if (i == 0) perm[j] = j;
+  __syncthreads();
   for (int p = 0; p < NB; p++) {
-    double v = used ? -1.0 : fabs(S[p]);
-    int r = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
-      const int r2 = __shfl_xor_sync(0xffffffffu, r, o);
-      if (v2 > v || (v2 == v && r2 < r)) { v = v2; r = r2; }
+    if (i == 0) {                       // warp 0: arg max over logical rows r >= p of |S[perm[r]][p]|
+      double v = (j >= p) ? fabs(S[perm[j]][p]) : -1.0;
+      int r = j;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int r2 = __shfl_xor_sync(0xffffffffu, r, o);
+        if (v2 > v || (v2 == v && r2 < r)) { v = v2; r = r2; }
+      }
+      if (j == 0) { const int t = perm[p]; perm[p] = perm[r]; perm[r] = t; }
     }
-    const int pl = r;                            // pivot lane (same value in every lane)
-    double piv = __shfl_sync(0xffffffffu, S[p], pl);
+    __syncthreads();
+    const int P = perm[p];              // physical pivot row
+    double piv = S[P][p];
     if (fabs(piv) < 1e-13) piv = piv < 0.0 ? -1e-13 : 1e-13;      // static perturbation
     const double d = 1.0 / piv;
-    const double f = S[p];
-    const bool me = lane == pl;
-    if (me) { used = true; myp = p; }
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-      const double sp = __shfl_sync(0xffffffffu, S[j], pl) * d;
-      const double ip = __shfl_sync(0xffffffffu, I2[j], pl) * d;
-      if (me) { S[j] = sp; I2[j] = ip; }
-      else { S[j] -= f * sp; I2[j] -= f * ip; }
-    }
+    const double f = S[i][p];
+    const double sp = S[P][j] * d, ip = I2[P][j] * d;
+    __syncthreads();
+    if (i == P) { S[i][j] = sp; I2[i][j] = ip; }
+    else { S[i][j] -= f * sp; I2[i][j] -= f * ip; }
+    __syncthreads();
   }
-  double *out = ipp + (size_t)z * NB * NB + (size_t)myp * NB;
-#pragma unroll
-  for (int j = 0; j < NB; j++) out[j] = I2[j];
+  Ip[i][j] = I2[perm[i]][j];
+  __syncthreads();
+}
+
+// pivot block inverse, one CTA per eliminated node: ipp <- inv(A_PP)
+__global__ void __launch_bounds__(1024)
+k_gjb_pivot(int g, int s, int b, const double *__restrict__ D, double *__restrict__ ipp) {
+  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
+  __shared__ double W1[NB][NB + 1], W2[NB][NB + 1], Ip[NB][NB + 1];
+  __shared__ int perm[NB];
+  const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
+  W1[i][j] = D[(size_t)node * g * g + (size_t)(b * NB + i) * g + b * NB + j];
+  __syncthreads();
+  invert32(W1, W2, Ip, perm, i, j);
+  ipp[(size_t)z * NB * NB + i * NB + j] = Ip[i][j];
 }
 
 // Panel step for pivot block b:  y = 0: row panel tile (P, J = blockIdx.x): A_PJ <- Ipp A_PJ;
@@ -530,7 +534,7 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
     const int s = lv.s;
     // eliminated nodes: Dinv (in place), P = Dinv L, Q = Dinv U
     for (int b = 0; b < nbk; b++) {
-      k_gjb_pivot<<<dim3(1, 1, lv.nE), 32, 0, st>>>(g, s, b, pc->D, pc->ipp);
+      k_gjb_pivot<<<dim3(1, 1, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp);
       k_gjb_panel<<<dim3(nbk, 2, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp, pc->colbuf);
       k_gjb_update<<<dim3(nt, nt, lv.nE), 256, 0, st>>>(g, s, b, pc->D, pc->colbuf, pc->ipp);
     }
