@@ -277,7 +277,9 @@ __device__ __forceinline__ void invert32(double (*S)[NB + 1], double (*I2)[NB + 
   __syncthreads();
 }
 
-// pivot block inverse, one CTA per eliminated node: ipp <- inv(A_PP)
+// pivot block inverse, one CTA per eliminated node: ipp <- inv(A_PP).  (Measured alternatives: a
+// single warp holding the rows in registers with shuffle broadcasts, 71 us; a single warp on shared
+// memory, 47 us; this 1024-thread version, three barriers per pivot: fastest of the three.)
 __global__ void __launch_bounds__(1024)
 k_gjb_pivot(int g, int s, int b, const double *__restrict__ D, double *__restrict__ ipp) {
   const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
