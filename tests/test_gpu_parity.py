@@ -501,3 +501,53 @@ def test_two_rank_nccl_solve_if_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "multi_gpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_prescribed_velocity_BC_through_solve_DIVA(oracle):
+    """solve_DIVA with the optional BC_prescr_* arguments (DIVA_main.f90:137-152): prescribed rows get
+    a unit diagonal and the prescribed value; the pattern cache is rebuilt when the mask changes."""
+    mesh, C, ice = experiments.MISMIPplus(8e3)
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C.visc_it_nit = 3
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
+    rng = np.random.default_rng(4)
+    mask = (mesh.TriGC[:, 0] < 100e3).astype(np.int32)
+    bu, bv = 5.0 + rng.random(mesh.nTri), rng.random(mesh.nTri) - 0.5
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        for use_bc in (True, False, True):
+            for k in S.STATE_FIELDS_B:
+                getattr(S, k)[:] = 0
+            S.eta_3D_b[:] = 0
+            D = oracle.new_DIVA_state(mesh)
+            if use_bc:
+                info = S.solve_DIVA(ice, BC_prescr_mask_b=mask, BC_prescr_u_b=bu, BC_prescr_v_b=bv)
+                nv, _ = oracle.solve_DIVA(mesh, ice, C, D, "direct", bc_mask=mask, bc_u=bu, bc_v=bv)
+            else:
+                info = S.solve_DIVA(ice)
+                nv, _ = oracle.solve_DIVA(mesh, ice, C, D, "direct")
+            assert info.n_visc_its == nv
+            _check_uv(S, D)
+    finally:
+        S.close()
+
+
+def test_error_paths_on_device():
+    mesh, C, ice = experiments.ISMIP_HOM("A", 80e3, 9)
+    C2 = copy.copy(C)
+    C2.choice_ice_rheology_Glen = "Huybrechts1992"
+    S = diva.initialise_DIVA_solver(mesh, C2)
+    try:
+        bad = copy.copy(ice)
+        bad.Ti = None
+        with pytest.raises(UfeError):               # Huybrechts1992 needs Ti
+            S.solve_DIVA(bad)
+        with pytest.raises(UfeError):               # no assembled matrix before the first solve
+            S.get_stiffness_matrix()
+    finally:
+        S.close()
+    with pytest.raises(UfeError):                   # nz outside [2, 32]
+        m2 = copy.copy(mesh)
+        m2.nz = 40
+        m2.zeta = np.linspace(0.0, 1.0, 40)
+        diva.initialise_DIVA_solver(m2, C)
