@@ -148,6 +148,14 @@ __global__ void k_gm_sethcol(const KrylovScalars *sc, double *gm, const double *
 
 // finish a reduction stage inside the producing kernel (single GPU) or leave the local
 // partial sums in dots_local for the all-reduce (multi GPU)
+// Bounded spin on a flag another GPU writes: a rank that died must not hang the others' GPUs.
+// ~2^26 polls of a local volatile word (tens of seconds); returns false on time-out.
+__device__ __forceinline__ bool peer_wait(const volatile int *flag, int epoch) {
+  for (long long spins = 0; spins < (1LL << 26); spins++)
+    if (*flag >= epoch) return true;
+  return false;
+}
+
 // `single`:  > 0 one rank: finish the stage here;  == 0 several ranks over NCCL: leave the local
 // partial sums in dots_local for the all-reduce;  < 0 several ranks with peer memory, epoch =
 // -single: the last block stores its partial sums into every rank's slot (NVLink P2P), waits
@@ -172,10 +180,10 @@ __device__ __forceinline__ void finish_stage(double (&acc)[NV], int stage, doubl
         __threadfence_system();
         *reinterpret_cast<volatile int *>(pd->flags[t] + P + par * P + me) = epoch;
         const volatile int *mine = reinterpret_cast<const volatile int *>(pd->flags[me] + P + par * P + t);
-        while (*mine < epoch) {}
+        if (!peer_wait(mine, epoch)) { sc->reason = -9; sc->done = 1; }
       }
       __syncthreads();
-      if (t == 0) {
+      if (t == 0 && sc->reason != -9) {
         __threadfence_system();
         const volatile double *src = pd->dots[me] + (size_t)par * P * UFE_PEER_DOTS;
         for (int i = 0; i < NV; i++) { double sum = 0.0; for (int q = 0; q < P; q++) sum += src[(size_t)q * UFE_PEER_DOTS + i]; sc->dots[i] = sum; }
@@ -283,10 +291,10 @@ __global__ void k_peer_reduce(int P, int me, int epoch, int nd, int stage, PeerF
   }
   if (t < P) {
     const volatile int *mine = reinterpret_cast<const volatile int *>(fp.f[me] + P + par * P + t);
-    while (*mine < epoch) {}
+    if (!peer_wait(mine, epoch)) { sc->reason = -9; sc->done = 1; }
   }
   __syncthreads();
-  if (t == 0) {
+  if (t == 0 && sc->reason != -9) {
     __threadfence_system();
     const volatile double *src = dp.d[me] + (size_t)par * P * UFE_PEER_DOTS;
     if (stage < 0) {
@@ -314,7 +322,9 @@ k_kspmv_bell(int nt_loc, int t0, int nslices, const int *__restrict__ bell_off, 
              KrylovScalars *sc, double *gm, int single, double rtol, double abstol, PeerView peer) {
   if (sc->done) return;
   if (PEER) {       // wait until every rank has published this input vector (flags are in own memory)
-    if ((int)threadIdx.x < peer.P && (int)threadIdx.x != peer.me) while (peer.flags[threadIdx.x] < peer.epoch) {}
+    if ((int)threadIdx.x < peer.P && (int)threadIdx.x != peer.me && !peer_wait(peer.flags + threadIdx.x, peer.epoch)) {
+      sc->reason = -9; sc->done = 1;      // peer time-out: stop the solve, the host reports it
+    }
     __syncthreads();
   }
   const int own_lo = PEER ? peer.bounds[peer.me] : 0, own_hi = PEER ? peer.bounds[peer.me + 1] : 0x7fffffff;
@@ -891,6 +901,7 @@ int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Co
     }
   }
   const int reason = kw.sc_host->reason;
+  if (reason == -9) { ufe_set_error("peer-memory synchronisation timed out (another rank stopped?)"); return UFE_ERR_CUDA; }
   if (reason == -3) fl |= UFE_FLAG_KRYLOV_MAXIT;
   if (reason == -4 || reason == -5) fl |= UFE_FLAG_KRYLOV_DIVERGED;
   if (n_its) *n_its = kw.sc_host->its;
