@@ -251,17 +251,23 @@ __device__ __forceinline__ void invert32(double (*S)[NB + 1], double (*I2)[NB + 
   if (i == 0) perm[j] = j;
   __syncthreads();
   for (int p = 0; p < NB; p++) {
-    if (i == 0) {                       // warp 0: arg max over logical rows r >= p of |S[perm[r]][p]|
-      double v = (j >= p) ? fabs(S[perm[j]][p]) : -1.0;
-      int r = j;
-      for (int o = 16; o > 0; o >>= 1) {
-        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
-        const int r2 = __shfl_xor_sync(0xffffffffu, r, o);
-        if (v2 > v || (v2 == v && r2 < r)) { v = v2; r = r2; }
+    // threshold pivoting: the matrix is Jacobi-scaled (unit diagonal), so the natural pivot is
+    // almost always of order one; the arg-max search (one warp, ~40 % of a step) and its barrier
+    // are only paid when it is not.  The test reads one shared value, so it is uniform.
+    if (fabs(S[perm[p]][p]) < 0.05) {
+      __syncthreads();                   // everybody has evaluated the test before perm changes
+      if (i == 0) {                      // warp 0: arg max over logical rows r >= p of |S[perm[r]][p]|
+        double v = (j >= p) ? fabs(S[perm[j]][p]) : -1.0;
+        int r = j;
+        for (int o = 16; o > 0; o >>= 1) {
+          const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+          const int r2 = __shfl_xor_sync(0xffffffffu, r, o);
+          if (v2 > v || (v2 == v && r2 < r)) { v = v2; r = r2; }
+        }
+        if (j == 0) { const int t = perm[p]; perm[p] = perm[r]; perm[r] = t; }
       }
-      if (j == 0) { const int t = perm[p]; perm[p] = perm[r]; perm[r] = t; }
+      __syncthreads();
     }
-    __syncthreads();
     const int P = perm[p];              // physical pivot row
     double piv = S[P][p];
     if (fabs(piv) < 1e-13) piv = piv < 0.0 ? -1e-13 : 1e-13;      // static perturbation
