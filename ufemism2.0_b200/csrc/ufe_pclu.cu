@@ -329,6 +329,41 @@ k_gjb_panel(int g, int s, int b, double *__restrict__ D, const double *__restric
   }
 }
 
+// The same panel step with the pivot-block inverse folded in: every CTA inverts A_PP itself.
+// Redundant work, but on the small upper levels (a handful of nodes) the GPU is idle anyway and
+// it removes a serial launch per panel; used when the whole grid is resident at once.
+__global__ void __launch_bounds__(1024)
+k_gjb_panel_inv(int g, int s, int b, double *__restrict__ D, double *__restrict__ ipp, double *__restrict__ colbuf) {
+  const int z = blockIdx.z, node = (2 * z + 1) * s - 1;
+  __shared__ double X[NB][NB + 1], Ip[NB][NB + 1], W1[NB][NB + 1], W2[NB][NB + 1];
+  __shared__ int perm[NB];
+  const int j = threadIdx.x & 31, i = threadIdx.x >> 5, q = blockIdx.x;
+  if (blockIdx.y == 1 && q == b) return;
+  double *A = D + (size_t)node * g * g;
+  W1[i][j] = A[(size_t)(b * NB + i) * g + b * NB + j];     // A_PP is not written in this kernel
+  __syncthreads();
+  invert32(W1, W2, Ip, perm, i, j);
+  if (blockIdx.y == 0) {
+    if (q == b) { ipp[(size_t)z * NB * NB + i * NB + j] = Ip[i][j]; return; }   // the update kernel copies it into place
+    double *T = A + (size_t)(b * NB) * g + q * NB;             // tile (P, J=q)
+    X[i][j] = T[(size_t)i * g + j];
+    __syncthreads();
+    double sum = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < NB; k++) sum += Ip[i][k] * X[k][j];
+    T[(size_t)i * g + j] = sum;
+  } else {
+    double *T = A + (size_t)(q * NB) * g + b * NB;             // tile (I=q, P)
+    X[i][j] = T[(size_t)i * g + j];
+    colbuf[((size_t)z * g + q * NB + i) * NB + j] = X[i][j];   // old A_IP for the trailing update
+    __syncthreads();
+    double sum = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < NB; k++) sum += X[i][k] * Ip[k][j];
+    T[(size_t)i * g + j] = -sum;
+  }
+}
+
 // trailing update, 64 x 64 tile per CTA (256 threads, 4 x 4 micro-tile), inner dimension 32
 __global__ void __launch_bounds__(256)
 k_gjb_update(int g, int s, int b, double *__restrict__ D, const double *__restrict__ colbuf,
@@ -542,11 +577,16 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
     const int s = lv.s;
     // eliminated nodes: Dinv (in place), P = Dinv L, Q = Dinv U
     for (int b = 0; b < nbk; b++) {
-      k_gjb_pivot<<<dim3(1, 1, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp);
-      k_gjb_panel<<<dim3(nbk, 2, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp, pc->colbuf);
+      if (2 * nbk * lv.nE <= 148) {          // small level: one wave of CTAs, fold the pivot inverse into the panel step
+        k_gjb_panel_inv<<<dim3(nbk, 2, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp, pc->colbuf);
+        g_launch_count += 2;
+      } else {
+        k_gjb_pivot<<<dim3(1, 1, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp);
+        k_gjb_panel<<<dim3(nbk, 2, lv.nE), 1024, 0, st>>>(g, s, b, pc->D, pc->ipp, pc->colbuf);
+        g_launch_count += 3;
+      }
       k_gjb_update<<<dim3(nt, nt, lv.nE), 256, 0, st>>>(g, s, b, pc->D, pc->colbuf, pc->ipp);
     }
-    g_launch_count += 3 * nbk;
     const Opnd Dn{pc->D, 0, 0}, Pn{pc->Pm, 0, 0}, Qn{pc->Qm, 0, 0};
     const Opnd Le{pc->LS, 2, lv.base}, Ue{pc->US, 2, lv.base};               // this level, eliminated (position 2z)
     launch_bgemm2(st, lv.nE, g, K, s, 0, GemmOps{Dn, Le, Pn}, GemmOps{Dn, Ue, Qn}, 1, 1.0, 0.0);     // P = Dinv L, Q = Dinv U
