@@ -183,3 +183,24 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+REF = "/root/reference"
+PATH_KEYS = [f.name for f in __import__("dataclasses").fields(config.Config) if not f.name.startswith("b200_")]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("cfg_file, make", [
+    ("config-files/benchmarks/MISMIP+/config_MISMIPplus_2km_spinup.cfg", lambda: experiments.MISMIPplus(8e3)[1]),
+    ("config-files/config_MISMIP_8km_spinup_for_scaling.cfg", lambda: experiments.MISMIP_8km(64e3)[1]),
+])
+def test_workload_configs_equal_the_reference_cfg_files(cfg_file, make):
+    """The named workloads hard-code the solver keys of the reference's own .cfg files (the files are
+    not available on the GPU box); here, where they are, every key the path reads must agree."""
+    want = config.Config.from_namelist(os.path.join(REF, cfg_file))
+    got = make()
+    skip = {"choice_initial_velocity", "nz", "choice_zeta_grid", "zeta_irregular_log_R",
+            "refgeo_idealised_SSA_icestream_Hi", "refgeo_idealised_SSA_icestream_dhdx", "refgeo_idealised_SSA_icestream_L",
+            "refgeo_idealised_SSA_icestream_m", "refgeo_idealised_ISMIP_HOM_L", "choice_idealised_sliding_law"}
+    diffs = {k: (getattr(got, k), getattr(want, k)) for k in PATH_KEYS if k not in skip and getattr(got, k) != getattr(want, k)}
+    assert not diffs, diffs
