@@ -256,6 +256,62 @@ int ufe_diva_reset_state(ufe_handle *h);
  * averaged velocities on the b- and a-grid, u_3D / v_3D on the a-grid, absolute values, R_shear. */
 int ufe_calc_secondary_velocities(ufe_handle *h, ufe_secondary_velocities *out);
 
+/* ---- ice-thickness rates of change (conservation of mass) ----------------
+ * The caller's other PETSc call site (conservation_of_mass_semiimplicit.f90:161) and the explicit
+ * scheme it builds on, on the same handle / device as the velocity solve, so that u_vav_b, v_vav_b
+ * can stay resident between solve_DIVA and the thickness update of the predictor-corrector step. */
+enum { UFE_BC_H_INFINITE = 1, UFE_BC_H_ZERO = 2 };   /* C%BC_H_*: 'infinite' | 'zero' */
+
+/* type_mesh members (src/UPSY/types/mesh_types.f90) read by calc_ice_flux_divergence_matrix_upwind
+ * (conservation_of_mass_utilities.f90:21-131) and map_velocities_from_b_to_c_2D
+ * (map_velocities_to_c_grid.f90:17-69), as built by construct_mesh_edges (edges/mesh_edges.f90:19-194),
+ * calc_Voronoi_cell_areas, calc_connection_widths, calc_connection_lengths (mesh_secondary.f90:137-366). */
+typedef struct ufe_mesh_edges {
+  int32_t nE;
+  const int32_t *VE;                   /* (nV,nC_mem) edge of connection ci */
+  const int32_t *ETri;                 /* (nE,2) [til, tir], 0 = none */
+  const double *A;                     /* (nV) Voronoi cell areas */
+  const double *Cw, *D_x, *D_y, *D;    /* (nV,nC_mem) */
+} ufe_mesh_edges;
+
+typedef struct ufe_thickness_config {
+  double dHi_semiimplicit_fs;          /* model_configuration.f90:356 */
+  double dHi_PETSc_rtol, dHi_PETSc_abstol;  /* :357-358 */
+  int32_t BC_H[4];                     /* north, east, south, west (:361-364), UFE_BC_H_* */
+  double dt_ice_max, dt_ice_min;       /* :391-392 */
+  double Hi_min;                       /* :437 */
+  int32_t krylov_method, krylov_maxits;/* extensions as in ufe_config (reference: PETSc GMRES(30), 10000) */
+} ufe_thickness_config;
+
+/* dummy arguments of calc_dHi_dt_explicit / calc_dHi_dt_semiimplicit
+ * (conservation_of_mass_explicit.f90:23-72, conservation_of_mass_semiimplicit.f90:24-98).  All (nV)
+ * unless noted, full-length.  mask_noice is a Fortran LOGICAL passed as int32. */
+typedef struct ufe_thickness_fields {
+  const double *Hi, *Hb, *SL;
+  const double *u_vav_b, *v_vav_b;     /* (nTri); both NULL = the device-resident velocities of the handle's
+                                          most recent solve_DIVA / solve_SSA */
+  const double *SMB, *BMB, *LMB, *fraction_margin, *dHi_dt_target;
+  const int32_t *mask_noice;
+  const int32_t *BC_prescr_mask;       /* optional pair, NULL = absent */
+  const double *BC_prescr_Hi;
+  double *AMB, *dHi_dt, *Hi_tplusdt, *divQ;   /* out; any may be NULL (not copied back) */
+} ufe_thickness_fields;
+
+/* upload the edge / Voronoi data once per mesh (the handle must come from ufe_diva_create on the same mesh) */
+int ufe_mesh_set_edges(ufe_handle *h, const ufe_mesh_edges *edges);
+/* replaces calc_dHi_dt_explicit (conservation_of_mass_explicit.f90:23-138); dt inout (flux-limited) */
+int ufe_calc_dHi_dt_explicit(ufe_handle *h, const ufe_thickness_config *cfg, ufe_thickness_fields *f, double *dt);
+/* replaces calc_dHi_dt_semiimplicit (conservation_of_mass_semiimplicit.f90:24-173); dt is not changed
+ * there.  n_Axb_its: Krylov iterations of the (1 + dt f_s M_divQ) solve; flags: UFE_FLAG_KRYLOV_*.
+ * The Krylov solve starts from x0 = 0 like the reference's (KSP default; its 'initial guess'
+ * Hi + dt*dHi_dt is never handed to PETSc as non-zero, petsc_basic.f90:99-128). */
+int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_config *cfg, ufe_thickness_fields *f, double dt,
+                                 int32_t *n_Axb_its, int32_t *flags);
+/* which = 0: M_divQ of the most recent call; 1: the stiffness matrix AA and load vector bb of the most
+ * recent semi-implicit call.  Reference CSR layout (row vi = [vi, C(vi,1..nC)]).  Query sizes with ind == NULL. */
+int ufe_get_thickness_csr(ufe_handle *h, int32_t which, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind,
+                          double *val, double *bb);
+
 /* L1 -- replaces solve_SSA_DIVA_linearised (solve_linearised_SSA_DIVA.f90:23-178; call
  * sites DIVA_main.f90:189-192, SSA_main.f90:178-181).  Full-length (nTri) arrays.
  * u_b, v_b inout; u_b_prev, v_b_prev out (the gathered previous solution). */

@@ -633,3 +633,333 @@ def calc_secondary_velocities(mesh, u_3D_b, v_3D_b):
         o[f"uabs_{k}"] = np.sqrt(o[f"u_{k}"] ** 2 + o[f"v_{k}"] ** 2)                 # :233-237
     o["R_shear"] = (o["uabs_base"] + 0.1) / (o["uabs_surf"] + 0.1)                    # :240-242
     return o
+
+
+# --------------------------------------------------------------------------------------
+# ice-thickness rates of change (conservation of mass)
+#   src/UPSY/mesh/edges/mesh_edges.f90, mesh_utilities.f90:72-372, mesh_secondary.f90:137-366,
+#   src/UFEMISM/ice_dynamics/utilities/map_velocities_to_c_grid.f90:17-69,
+#   src/UFEMISM/ice_dynamics/conservation_of_mass/*.f90
+# Loop-for-loop restatements (small meshes only).
+# --------------------------------------------------------------------------------------
+seawater_density = 1028.0   # src/UPSY/basic/parameters.f90
+
+
+def ice_surface_elevation(Hi, Hb, SL):
+    """ice_geometry_basics.f90:28-41"""
+    return Hi + max(SL - ice_density / seawater_density * Hi, Hb)
+
+
+def Hi_from_Hb_Hs_and_SL(Hb, Hs, SL):
+    """ice_geometry_basics.f90:58-82"""
+    Hi_float = max(0.0, (SL - Hb) * (seawater_density / ice_density))
+    Hs_float = Hb + Hi_float
+    if Hs > Hs_float:
+        return Hs - Hb
+    return min(Hi_float, (Hs - SL) / (1.0 - (ice_density / seawater_density)))
+
+
+def _circumcenter(p, q, r):
+    """plane_geometry.f90:282-309: intersection of the perpendicular bisectors of pq and qr."""
+    # line through two points as a x + b y = c (line_from_points), then its perpendicular bisector
+    def bisector(p, q):
+        a, b = q[1] - p[1], p[0] - q[0]
+        m = ((p[0] + q[0]) / 2.0, (p[1] + q[1]) / 2.0)
+        c = -b * m[0] + a * m[1]
+        return -b, a, c
+    a, b, c = bisector(p, q)
+    e, f, g = bisector(q, r)
+    d = a * f - e * b
+    if d == 0.0:
+        return np.array([1e30, 1e30])
+    return np.array([(f * c - b * g) / d, (a * g - e * c) / d])
+
+
+def construct_mesh_edges(mesh):
+    """edges/mesh_edges.f90:19-194 (+ edge_border_index :196-228).  Returns dict VE, EV, ETri, EBI, nE."""
+    nV = mesh.nV
+    C, nC, iTri, niTri, Tri, VBI = mesh.C, mesh.nC, mesh.iTri, mesh.niTri, mesh.Tri, mesh.VBI
+    nE = int(nC.sum()) // 2
+    VE = np.zeros((nV, mesh.nC_mem), dtype=np.int32, order="F")
+    EV = np.zeros((nE, 4), dtype=np.int32, order="F")
+    ETri = np.zeros((nE, 2), dtype=np.int32, order="F")
+    EBI = np.zeros(nE, dtype=np.int32)
+
+    def border_index(vi, vj):
+        a, b = VBI[vi - 1], VBI[vj - 1]
+        if a == 0 or b == 0:
+            return 0
+        for code, grp in ((1, (8, 1, 2)), (3, (2, 3, 4)), (5, (4, 5, 6)), (7, (6, 7, 8))):
+            if a in grp and b in grp:
+                return code
+        return 0
+
+    ei = 0
+    for vi in range(1, nV + 1):
+        for ci in range(1, nC[vi - 1] + 1):
+            vj = int(C[vi - 1, ci - 1])
+            if VE[vi - 1, ci - 1] > 0:
+                continue
+            ei += 1
+            VE[vi - 1, ci - 1] = ei
+            for cj in range(1, nC[vj - 1] + 1):
+                if C[vj - 1, cj - 1] == vi:
+                    VE[vj - 1, cj - 1] = ei
+                    break
+            EBI[ei - 1] = border_index(vi, vj)
+            vil = til = vir = tir = 0
+            for iti in range(niTri[vi - 1]):
+                ti = int(iTri[vi - 1, iti])
+                for n1 in range(3):
+                    n2, n3 = (n1 + 1) % 3, (n1 + 2) % 3
+                    if Tri[ti - 1, n1] == vi and Tri[ti - 1, n2] == vj:
+                        til, vil = ti, int(Tri[ti - 1, n3])
+                    if Tri[ti - 1, n1] == vj and Tri[ti - 1, n2] == vi:
+                        tir, vir = ti, int(Tri[ti - 1, n3])
+            EV[ei - 1] = (vi, vj, vil, vir)
+            ETri[ei - 1] = (til, tir)
+    assert ei == nE
+    return dict(nE=nE, VE=VE, EV=EV, ETri=ETri, EBI=EBI)
+
+
+def calc_Voronoi_cell(mesh, Tricc, vi, dx):
+    """mesh_utilities.f90:72-303; returns the list of points spanning the cell of vertex vi (1-based)."""
+    C, nC, iTri, niTri, Tri, VBI = mesh.C, mesh.nC, mesh.iTri, mesh.niTri, mesh.Tri, mesh.VBI
+    vb = int(VBI[vi - 1])
+    if vb == 0:                                            # calc_Voronoi_cell_free :105-167
+        return [Tricc[int(iTri[vi - 1, k]) - 1].copy() for k in range(niTri[vi - 1])]
+    Vor = []
+    for ci in range(2, nC[vi - 1] + 1):                    # calc_Voronoi_cell_border :169-303
+        vj = int(C[vi - 1, ci - 1])
+        ti = 0
+        for iti in range(niTri[vi - 1]):
+            tj = int(iTri[vi - 1, iti])
+            for n in range(3):
+                if Tri[tj - 1, n] == vj and Tri[tj - 1, (n + 1) % 3] == vi:
+                    ti = tj
+                    break
+            if ti > 0:
+                break
+        assert ti > 0
+        Vor.append(Tricc[ti - 1].copy())
+    f = Vor[0]
+    first = {1: [f[0], mesh.ymax + dx], 2: [f[0], mesh.ymax + dx], 3: [mesh.xmax + dx, f[1]], 4: [mesh.xmax + dx, f[1]],
+             5: [f[0], mesh.ymin - dx], 6: [f[0], mesh.ymin - dx], 7: [mesh.xmin - dx, f[1]], 8: [mesh.xmin - dx, f[1]]}[vb]
+    Vor.insert(0, np.array(first))
+    l = Vor[-1]
+    last = {2: [mesh.xmax + dx, l[1]], 3: [mesh.xmax + dx, l[1]], 4: [l[0], mesh.ymin - dx], 5: [l[0], mesh.ymin - dx],
+            6: [mesh.xmin - dx, l[1]], 7: [mesh.xmin - dx, l[1]], 8: [l[0], mesh.ymax + dx], 1: [l[0], mesh.ymax + dx]}[vb]
+    Vor.append(np.array(last))
+    corner = {2: [mesh.xmax + dx, mesh.ymax + dx], 4: [mesh.xmax + dx, mesh.ymin - dx],
+              6: [mesh.xmin - dx, mesh.ymin - dx], 8: [mesh.xmin - dx, mesh.ymax + dx]}.get(vb)
+    if corner is not None:
+        Vor.append(np.array(corner))
+    return Vor
+
+
+def calc_mesh_edges_oracle(mesh):
+    """Edges + Voronoi areas (mesh_secondary.f90:137-186) + Cw (:246-298, find_shared_Voronoi_boundary
+    mesh_utilities.f90:305-372; circumcentres inside the domain, so crop_line_to_domain is the identity)
+    + D_x, D_y, D (:300-366)."""
+    E = construct_mesh_edges(mesh)
+    V = mesh.V
+    Tricc = np.array([_circumcenter(V[t[0] - 1], V[t[1] - 1], V[t[2] - 1]) for t in mesh.Tri])
+    A = np.zeros(mesh.nV)
+    for vi in range(1, mesh.nV + 1):
+        Vor = calc_Voronoi_cell(mesh, Tricc, vi, 0.0)
+        n = len(Vor)
+        for k in range(n):
+            p, q = Vor[(k + 1) % n] - V[vi - 1], Vor[k] - V[vi - 1]
+            A[vi - 1] += abs(p[0] * q[1] - p[1] * q[0]) / 2.0
+    dx = ((mesh.xmax - mesh.xmin) + (mesh.ymax - mesh.ymin)) / 100.0
+    Cw = np.zeros((mesh.nV, mesh.nC_mem), order="F")
+    D_x, D_y, D = np.zeros_like(Cw), np.zeros_like(Cw), np.zeros_like(Cw)
+    for vi in range(1, mesh.nV + 1):
+        for ci in range(1, mesh.nC[vi - 1] + 1):
+            ei = int(E["VE"][vi - 1, ci - 1])
+            til, tir = (int(t) for t in E["ETri"][ei - 1])
+            ebi = int(E["EBI"][ei - 1])
+            if ebi == 0:
+                p, q = Tricc[til - 1], Tricc[tir - 1]
+            else:
+                ti = til if til > 0 else tir
+                p = Tricc[ti - 1].copy()
+                q = {1: [p[0], mesh.ymax + dx], 3: [mesh.xmax + dx, p[1]], 5: [p[0], mesh.ymin - dx],
+                     7: [mesh.xmin - dx, p[1]]}[ebi]
+                q = np.array(q)
+                p[0] = min(mesh.xmax, max(mesh.xmin, p[0]))
+                p[1] = min(mesh.ymax, max(mesh.ymin, p[1]))
+            Cw[vi - 1, ci - 1] = np.hypot(p[0] - q[0], p[1] - q[1])
+            vj = int(mesh.C[vi - 1, ci - 1])
+            D_x[vi - 1, ci - 1] = V[vj - 1, 0] - V[vi - 1, 0]
+            D_y[vi - 1, ci - 1] = V[vj - 1, 1] - V[vi - 1, 1]
+            D[vi - 1, ci - 1] = np.sqrt(D_x[vi - 1, ci - 1] ** 2 + D_y[vi - 1, ci - 1] ** 2)
+    E.update(Tricc=Tricc, A=A, Cw=Cw, D_x=D_x, D_y=D_y, D=D)
+    return E
+
+
+def map_velocities_from_b_to_c_2D(E, u_b, v_b):
+    """map_velocities_to_c_grid.f90:17-69"""
+    nE = E["nE"]
+    u_c, v_c = np.zeros(nE), np.zeros(nE)
+    for ei in range(nE):
+        til, tir = int(E["ETri"][ei, 0]), int(E["ETri"][ei, 1])
+        if til == 0 and tir > 0:
+            u_c[ei], v_c[ei] = u_b[tir - 1], v_b[tir - 1]
+        elif tir == 0 and til > 0:
+            u_c[ei], v_c[ei] = u_b[til - 1], v_b[til - 1]
+        elif til > 0 and tir > 0:
+            u_c[ei] = (u_b[til - 1] + u_b[tir - 1]) / 2.0
+            v_c[ei] = (v_b[til - 1] + v_b[tir - 1]) / 2.0
+        else:
+            raise RuntimeError("something is seriously wrong with the ETri array of this mesh!")
+    return u_c, v_c
+
+
+def calc_ice_flux_divergence_matrix_upwind(mesh, E, u_vav_b, v_vav_b, fraction_margin) -> CSR:
+    """conservation_of_mass_utilities.f90:21-131: row vi = [vi, C(vi,1..nC)]."""
+    u_c, v_c = map_velocities_from_b_to_c_2D(E, u_vav_b, v_vav_b)
+    nV = mesh.nV
+    ptr = np.ones(nV + 1, dtype=np.int32)
+    ind, val = [], []
+    for vi in range(1, nV + 1):
+        n = int(mesh.nC[vi - 1])
+        cM = np.zeros(n + 1)
+        for ci in range(1, n + 1):
+            ei = int(E["VE"][vi - 1, ci - 1])
+            vj = int(mesh.C[vi - 1, ci - 1])
+            A_i = E["A"][vi - 1]
+            L_c = E["Cw"][vi - 1, ci - 1]
+            u_perp = (u_c[ei - 1] * E["D_x"][vi - 1, ci - 1] / E["D"][vi - 1, ci - 1]
+                      + v_c[ei - 1] * E["D_y"][vi - 1, ci - 1] / E["D"][vi - 1, ci - 1])
+            if fraction_margin[vi - 1] >= 1.0:
+                cM[0] = cM[0] + L_c * max(0.0, u_perp) / A_i
+            if fraction_margin[vj - 1] >= 1.0:
+                cM[ci] = L_c * min(0.0, u_perp) / A_i
+        ind.append(vi); val.append(cM[0])
+        for ci in range(1, n + 1):
+            ind.append(int(mesh.C[vi - 1, ci - 1])); val.append(cM[ci])
+        ptr[vi] = len(ind) + 1
+    return CSR(nV, nV, 1, nV, ptr, np.array(ind, dtype=np.int32), np.array(val, dtype=np.float64))
+
+
+def _BC_H(C, vbi):
+    return {1: C.BC_H_north, 2: C.BC_H_north, 3: C.BC_H_east, 4: C.BC_H_east, 5: C.BC_H_south, 6: C.BC_H_south,
+            7: C.BC_H_west, 8: C.BC_H_west}[int(vbi)]
+
+
+def apply_ice_thickness_BC_explicit(mesh, C, mask_noice, Hb, SL, Hi_tplusdt):
+    """conservation_of_mass_explicit.f90:140-282 (in place on Hi_tplusdt)."""
+    nV = mesh.nV
+    Hs = np.array([ice_surface_elevation(Hi_tplusdt[i], Hb[i], SL[i]) for i in range(nV)])
+    Hs_tot = Hs.copy()                                                         # gather_to_all :163
+    n_int = np.zeros(nV, dtype=np.int64)                                       # calc_n_interior_neighbours, utilities :205-233
+    for vi in range(nV):
+        for ci in range(mesh.nC[vi]):
+            vj = int(mesh.C[vi, ci]) - 1
+            if mesh.VBI[vj] == 0 and not mask_noice[vj]:
+                n_int[vi] += 1
+    for second in (False, True):
+        if second:
+            Hs_tot = Hs.copy()                                                 # gather again :233
+        for vi in range(nV):
+            if mesh.VBI[vi] == 0:
+                continue
+            bc = _BC_H(C, mesh.VBI[vi])
+            if bc == "zero":
+                Hi_tplusdt[vi] = 0.0
+            elif bc == "infinite":
+                if (not second) and n_int[vi] > 0:
+                    s = 0.0
+                    for ci in range(mesh.nC[vi]):
+                        vj = int(mesh.C[vi, ci]) - 1
+                        if mesh.VBI[vj] == 0 and not mask_noice[vj]:
+                            s += Hs_tot[vj]
+                    Hs[vi] = max(Hb[vi], s / float(n_int[vi]))
+                    Hi_tplusdt[vi] = Hi_from_Hb_Hs_and_SL(Hb[vi], Hs[vi], SL[vi])
+                elif second and n_int[vi] == 0:
+                    s = 0.0
+                    for ci in range(mesh.nC[vi]):
+                        s += Hs_tot[int(mesh.C[vi, ci]) - 1]
+                    Hs[vi] = max(Hb[vi], s / float(mesh.nC[vi]))
+                    Hi_tplusdt[vi] = Hi_from_Hb_Hs_and_SL(Hb[vi], Hs[vi], SL[vi])
+            else:
+                raise ValueError(f'unknown BC_H "{bc}"')
+    return Hi_tplusdt
+
+
+def calc_flux_limited_timestep(C, Hi, dHi_dt):
+    """conservation_of_mass_utilities.f90:155-203 (including its max(dHi_dt, 1e-9) as written)."""
+    dt_lim = np.full(Hi.shape, C.dt_ice_max)
+    m = (Hi > C.Hi_min) & (dHi_dt < 0.0)
+    dt_lim[m] = Hi[m] / np.maximum(dHi_dt[m], 1e-9)
+    return max(C.dt_ice_min, float(dt_lim.min()))
+
+
+def calc_dHi_dt_explicit(mesh, E, C, f, dt):
+    """conservation_of_mass_explicit.f90:23-138.  f: dict of fields (Hi, Hb, SL, u_vav_b, v_vav_b, SMB, BMB, LMB,
+    fraction_margin, mask_noice, dHi_dt_target, optional BC_prescr_mask / BC_prescr_Hi).
+    Returns dict(dt, dHi_dt, Hi_tplusdt, divQ, AMB, M_divQ)."""
+    M = calc_ice_flux_divergence_matrix_upwind(mesh, E, f["u_vav_b"], f["v_vav_b"], f["fraction_margin"])
+    Hi = f["Hi"]
+    divQ = spmv(M, Hi)
+    dHi_dt = -divQ + f["fraction_margin"] * (f["SMB"] + f["BMB"] - f["dHi_dt_target"]) + f["LMB"]
+    AMB = dHi_dt.copy()
+    dt = min(dt, calc_flux_limited_timestep(C, Hi, dHi_dt))
+    Hi_tp = np.maximum(0.0, Hi + dHi_dt * dt)
+    apply_ice_thickness_BC_explicit(mesh, C, f["mask_noice"], f["Hb"], f["SL"], Hi_tp)
+    if f.get("BC_prescr_mask") is not None:
+        m = f["BC_prescr_mask"] == 1
+        Hi_tp[m] = np.maximum(0.0, f["BC_prescr_Hi"][m])
+    Hi_tp[f["mask_noice"].astype(bool)] = 0.0
+    dHi_dt = (Hi_tp - Hi) / dt
+    AMB = dHi_dt - AMB
+    return dict(dt=dt, dHi_dt=dHi_dt, Hi_tplusdt=Hi_tp, divQ=divQ, AMB=AMB, M_divQ=M)
+
+
+def calc_dHi_dt_semiimplicit(mesh, E, C, f, dt, linear_solver="direct"):
+    """conservation_of_mass_semiimplicit.f90:24-173 (+ BC rows :175-313).
+    Returns dict(dHi_dt, Hi_tplusdt, divQ, AMB, AA, bb, n_Axb_its)."""
+    ex = calc_dHi_dt_explicit(mesh, E, C, f, dt)                               # :111-115 (dt itself is not changed)
+    Hi_ex = ex["Hi_tplusdt"]
+    M = ex["M_divQ"]                                                           # :118 (same matrix)
+    Hi = f["Hi"]
+    divQ = spmv(M, Hi)
+    fs = C.dHi_semiimplicit_fs
+    val = M.val * dt * fs                                                      # :131-134
+    nV = mesh.nV
+    for vi in range(1, nV + 1):                                                # :137-146
+        for k in range(M.ptr[vi - 1] - 1, M.ptr[vi] - 1):
+            if M.ind[k] == vi:
+                val[k] = val[k] + 1.0
+    fm = f["fraction_margin"]
+    bb = Hi - (dt * (1.0 - fs) * divQ) + np.maximum(-1.0 * Hi, dt * (fm * (f["SMB"] + f["BMB"] - f["dHi_dt_target"]) + f["LMB"]))   # :150-152
+    # boundary conditions :158, 175-313
+    apply_ice_thickness_BC_explicit(mesh, C, f["mask_noice"], f["Hb"], f["SL"], Hi_ex)     # :224
+
+    def identity_row(vi0, rhs):
+        k1, k2 = M.ptr[vi0] - 1, M.ptr[vi0 + 1] - 1
+        val[k1:k2] = 0.0
+        for k in range(k1, k2):
+            if M.ind[k] == vi0 + 1:
+                val[k] = 1.0
+        bb[vi0] = rhs
+    for vi0 in range(nV):
+        if mesh.VBI[vi0] > 0:
+            identity_row(vi0, Hi_ex[vi0])
+    if f.get("BC_prescr_mask") is not None:
+        for vi0 in range(nV):
+            if f["BC_prescr_mask"][vi0] == 1:
+                identity_row(vi0, f["BC_prescr_Hi"][vi0])
+    for vi0 in range(nV):
+        if f["mask_noice"][vi0]:
+            identity_row(vi0, 0.0)
+    AA = CSR(nV, nV, 1, nV, M.ptr, M.ind, val)
+    if linear_solver == "direct":
+        Hi_tp, its = direct_solve(AA, bb), 0
+    else:
+        Hi_tp, its, _, _ = ksp_solve(AA, bb, C.dHi_PETSc_rtol, C.dHi_PETSc_abstol)         # :161-162
+    AMB = (Hi_tp - Hi) / dt                                                    # :165
+    dHi_dt = (Hi_tp - Hi) / dt                                                 # :168
+    AMB = dHi_dt - AMB                                                         # :175
+    return dict(dHi_dt=dHi_dt, Hi_tplusdt=Hi_tp, divQ=divQ, AMB=AMB, AA=AA, bb=bb, n_Axb_its=its, explicit=ex)

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "ufe_diva.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(ufe_[a-z_0-9]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(ufe_[A-Za-z_0-9]+)\s*\(", hdr))
     assert len(declared) >= 18
     lib = capi.lib()
     for name in sorted(declared):
@@ -38,9 +38,10 @@ def test_struct_layouts_match_header():
     src = textwrap.dedent("""
         #include <stdio.h>
         #include "ufe_diva.h"
-        int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ufe_csr), sizeof(ufe_mesh),
+        int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ufe_csr), sizeof(ufe_mesh),
           sizeof(ufe_config), sizeof(ufe_ice_inputs), sizeof(ufe_diva_state), sizeof(ufe_ssa_state),
-          sizeof(ufe_solve_info), sizeof(ufe_comm)); return 0; }""")
+          sizeof(ufe_solve_info), sizeof(ufe_comm), sizeof(ufe_mesh_edges), sizeof(ufe_thickness_config),
+          sizeof(ufe_thickness_fields)); return 0; }""")
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
@@ -49,7 +50,8 @@ def test_struct_layouts_match_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = list(map(int, subprocess.check_output([exe]).split()))
     mirrors = [capi.ufe_csr, capi.ufe_mesh, capi.ufe_config, capi.ufe_ice_inputs, capi.ufe_diva_state,
-               capi.ufe_ssa_state, capi.ufe_solve_info, capi.ufe_comm]
+               capi.ufe_ssa_state, capi.ufe_solve_info, capi.ufe_comm, capi.ufe_mesh_edges, capi.ufe_thickness_config,
+               capi.ufe_thickness_fields]
     assert sizes == [ct.sizeof(m) for m in mirrors]
 
 

@@ -97,6 +97,27 @@ class ufe_secondary_velocities(ct.Structure):
     _fields_ = [(n, ct.c_void_p) for n in SECONDARY_FIELDS]
 
 
+class ufe_mesh_edges(ct.Structure):
+    _fields_ = [("nE", c_i32), ("VE", ct.c_void_p), ("ETri", ct.c_void_p), ("A", ct.c_void_p),
+                ("Cw", ct.c_void_p), ("D_x", ct.c_void_p), ("D_y", ct.c_void_p), ("D", ct.c_void_p)]
+
+
+class ufe_thickness_config(ct.Structure):
+    _fields_ = [("dHi_semiimplicit_fs", c_f64), ("dHi_PETSc_rtol", c_f64), ("dHi_PETSc_abstol", c_f64),
+                ("BC_H", c_i32 * 4), ("dt_ice_max", c_f64), ("dt_ice_min", c_f64), ("Hi_min", c_f64),
+                ("krylov_method", c_i32), ("krylov_maxits", c_i32)]
+
+
+THICKNESS_IN = ("Hi", "Hb", "SL", "u_vav_b", "v_vav_b", "SMB", "BMB", "LMB", "fraction_margin", "dHi_dt_target")
+THICKNESS_OUT = ("AMB", "dHi_dt", "Hi_tplusdt", "divQ")
+
+
+class ufe_thickness_fields(ct.Structure):
+    _fields_ = ([(n, ct.c_void_p) for n in THICKNESS_IN] +
+                [("mask_noice", ct.c_void_p), ("BC_prescr_mask", ct.c_void_p), ("BC_prescr_Hi", ct.c_void_p)] +
+                [(n, ct.c_void_p) for n in THICKNESS_OUT])
+
+
 class ufe_comm(ct.Structure):
     _fields_ = [("rank", c_i32), ("nranks", c_i32), ("device", c_i32), ("nccl_unique_id", ct.c_char_p)]
 
@@ -107,6 +128,7 @@ EXPORTS = [
     "ufe_diva_solve", "ufe_ssa_solve", "ufe_diva_upload", "ufe_diva_solve_resident",
     "ufe_diva_download", "ufe_diva_reset_state", "ufe_calc_secondary_velocities", "ufe_ssa_diva_linearised", "ufe_mesh_get_operator",
     "ufe_mesh_apply_operator", "ufe_get_stiffness_csr", "ufe_bench_spmv", "ufe_get_ownership",
+    "ufe_mesh_set_edges", "ufe_calc_dHi_dt_explicit", "ufe_calc_dHi_dt_semiimplicit", "ufe_get_thickness_csr",
 ]
 
 _lib = None

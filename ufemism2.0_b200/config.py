@@ -53,6 +53,17 @@ class Config:
     slid_beta_max: float = 1e20
     slid_delta_v: float = 1e-3
     Hi_min: float = 0.0                                   # :437
+    # ice thickness integration (:355-365, :391-392) -- read by calc_dHi_dt_explicit / _semiimplicit
+    choice_ice_integration_method: str = "semi-implicit"
+    dHi_semiimplicit_fs: float = 1.5
+    dHi_PETSc_rtol: float = 1e-8
+    dHi_PETSc_abstol: float = 1e-6
+    BC_H_west: str = "zero"
+    BC_H_east: str = "zero"
+    BC_H_south: str = "zero"
+    BC_H_north: str = "zero"
+    dt_ice_max: float = 10.0
+    dt_ice_min: float = 0.1
     # rheology (:590-601)
     choice_flow_law: str = "Glen"
     Glens_flow_law_exponent: float = 3.0
@@ -118,3 +129,4 @@ IDEALISED_SLIDING_CODES = {"": 0, "SSA_icestream": 1, "ISMIP-HOM_C": 2, "ISMIP-H
                            "ISMIP-HOM_F": 5}
 RHEOLOGY_CODES = {"uniform": 0, "Huybrechts1992": 1}
 ENH_CODES = {"separate": 0, "interp": 1}
+BC_H_CODES = {"infinite": 1, "zero": 2}

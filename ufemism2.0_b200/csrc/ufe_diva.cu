@@ -126,7 +126,18 @@ struct ufe_handle {
   cudaEvent_t ev[8];
   void *flush_buf = nullptr;
   size_t flush_bytes = 0;
+  struct ThicknessState *thk = nullptr;        // ice-thickness path (ufe_thickness.cu), created by ufe_mesh_set_edges
 };
+
+// ufe_thickness.cu reaches the mesh, the stream and the resident velocities through this view
+struct ThicknessState;
+void ufe_thickness_free(ThicknessState *t);
+int ufe_handle_thickness_view(ufe_handle *h, DevMesh **dm, cudaStream_t *st, int *nranks, int *device,
+                              double **u_vav_b, double **v_vav_b, ThicknessState ***slot) {
+  *dm = &h->dm; *st = h->st; *nranks = h->comm.nranks; *device = h->device;
+  *u_vav_b = h->F.u_vav_b; *v_vav_b = h->F.v_vav_b; *slot = &h->thk;
+  return UFE_OK;
+}
 
 static ClosureParams make_params(const ufe_handle *h, double eps_sq_0_applied) {
   ClosureParams P;
@@ -363,6 +374,7 @@ extern "C" int ufe_diva_destroy(ufe_handle *h) {
   if (h->sec_alloc) { double **sp = reinterpret_cast<double **>(&h->sec); for (size_t i = 0; i < sizeof(SecondaryFields) / sizeof(double *); i++) cudaFree(sp[i]); }
   ufe_krylov_free(h->kw);
   ufe_pclu_free(h->pclu);
+  ufe_thickness_free(h->thk);
   for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->comm.nccl) ncclCommDestroy(h->comm.nccl);
   if (h->st) cudaStreamDestroy(h->st);

@@ -9,6 +9,7 @@ the C ABI (include/ufe_diva.h):
   multiply_CSR_matrix_with_vector_1D/_2D              CSR_matrix_vector_multiplication.f90:198,336
   map_a_b_2D/3D, ddx_a_b_2D, ... , ddy_b_a_2D          mesh_disc_apply_operators.f90:121-431
   partition_list                                      mpi_distributed_memory.f90:42
+  calc_dHi_dt_explicit / calc_dHi_dt_semiimplicit     conservation_of_mass_explicit.f90:23 ; _semiimplicit.f90:24
 
 ``crash(...)`` in the reference becomes ``UfeError``; the "viscosity iteration failed to
 converge" warning becomes ``info.flags & PICARD_MAXIT``.
@@ -22,7 +23,7 @@ import numpy as np
 
 from . import capi
 from .capi import UfeError, check, vp
-from .config import (BC_CODES, ENH_CODES, IDEALISED_SLIDING_CODES, RHEOLOGY_CODES, SLIDING_CODES, Config)
+from .config import (BC_CODES, BC_H_CODES, ENH_CODES, IDEALISED_SLIDING_CODES, RHEOLOGY_CODES, SLIDING_CODES, Config)
 from .mesh_types import Mesh
 
 PICARD_MAXIT, KRYLOV_MAXIT, KRYLOV_DIVERGED = 1, 2, 4
@@ -303,6 +304,84 @@ class DIVASolver:
             setattr(st, n, vp(out[n]))
         check(capi.lib().ufe_calc_secondary_velocities(self._h, ct.byref(st)))
         return out
+
+    # ---- ice-thickness rates of change
+    def set_mesh_edges(self, edges):
+        """Upload mesh%VE, ETri, A, Cw, D_x, D_y, D (``mesh_types.MeshEdges``) once per mesh."""
+        e = capi.ufe_mesh_edges()
+        e.nE = edges.nE
+        keep = []
+        for n, dt in (("VE", np.int32), ("ETri", np.int32), ("A", np.float64), ("Cw", np.float64),
+                      ("D_x", np.float64), ("D_y", np.float64), ("D", np.float64)):
+            a = np.asfortranarray(getattr(edges, n), dtype=dt)
+            keep.append(a)
+            setattr(e, n, vp(a))
+        check(capi.lib().ufe_mesh_set_edges(self._h, ct.byref(e)))
+
+    def _thickness_structs(self, fields: dict):
+        C = self.C
+        cfg = capi.ufe_thickness_config()
+        cfg.dHi_semiimplicit_fs, cfg.dHi_PETSc_rtol, cfg.dHi_PETSc_abstol = C.dHi_semiimplicit_fs, C.dHi_PETSc_rtol, C.dHi_PETSc_abstol
+        for i, side in enumerate(("north", "east", "south", "west")):
+            cfg.BC_H[i] = _code(BC_H_CODES, getattr(C, "BC_H_" + side), "BC_H")
+        cfg.dt_ice_max, cfg.dt_ice_min, cfg.Hi_min = C.dt_ice_max, C.dt_ice_min, C.Hi_min
+        cfg.krylov_method = _code(KRYLOV_METHODS, C.b200_krylov_method, "b200_krylov_method")
+        cfg.krylov_maxits = C.b200_krylov_maxits
+        f = capi.ufe_thickness_fields()
+        keep, out = [], {}
+        for n in capi.THICKNESS_IN:
+            a = fields.get(n)
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                keep.append(a)
+                setattr(f, n, vp(a))
+        a = np.ascontiguousarray(fields["mask_noice"], dtype=np.int32)
+        keep.append(a)
+        f.mask_noice = vp(a)
+        if fields.get("BC_prescr_mask") is not None:
+            a = np.ascontiguousarray(fields["BC_prescr_mask"], dtype=np.int32)
+            keep.append(a)
+            f.BC_prescr_mask = vp(a)
+        if fields.get("BC_prescr_Hi") is not None:
+            a = np.ascontiguousarray(fields["BC_prescr_Hi"], dtype=np.float64)
+            keep.append(a)
+            f.BC_prescr_Hi = vp(a)
+        for n in capi.THICKNESS_OUT:
+            out[n] = np.zeros(self.mesh.nV)
+            setattr(f, n, vp(out[n]))
+        return cfg, f, keep, out
+
+    def calc_dHi_dt_explicit(self, fields: dict, dt: float) -> dict:
+        """calc_dHi_dt_explicit(mesh, Hi, Hb, SL, u_vav_b, v_vav_b, SMB, BMB, LMB, AMB, fraction_margin, mask_noice,
+        dt, dHi_dt, Hi_tplusdt, divQ, dHi_dt_target [, BC_prescr_mask, BC_prescr_Hi])
+        (conservation_of_mass_explicit.f90:23).  ``fields`` holds the in-arguments by name; u_vav_b / v_vav_b may be
+        left out to use the resident result of the last velocity solve.  Returns the out-arguments + ``dt``."""
+        cfg, f, keep, out = self._thickness_structs(fields)
+        d = ct.c_double(dt)
+        check(capi.lib().ufe_calc_dHi_dt_explicit(self._h, ct.byref(cfg), ct.byref(f), ct.byref(d)))
+        out["dt"] = d.value
+        return out
+
+    def calc_dHi_dt_semiimplicit(self, fields: dict, dt: float) -> dict:
+        """calc_dHi_dt_semiimplicit (conservation_of_mass_semiimplicit.f90:24).  Returns the out-arguments,
+        ``n_Axb_its`` and ``flags``."""
+        cfg, f, keep, out = self._thickness_structs(fields)
+        its, fl = ct.c_int32(), ct.c_int32()
+        check(capi.lib().ufe_calc_dHi_dt_semiimplicit(self._h, ct.byref(cfg), ct.byref(f), ct.c_double(dt),
+                                                      ct.byref(its), ct.byref(fl)))
+        out["n_Axb_its"], out["flags"] = its.value, fl.value
+        return out
+
+    def get_thickness_matrix(self, which="M_divQ"):
+        """M_divQ of the most recent call, or (AA, bb) of the most recent semi-implicit call."""
+        w = {"M_divQ": 0, "AA": 1}[which]
+        m_loc, nnz = ct.c_int32(), ct.c_int32()
+        check(capi.lib().ufe_get_thickness_csr(self._h, w, ct.byref(m_loc), ct.byref(nnz), None, None, None, None))
+        ptr = np.zeros(m_loc.value + 1, dtype=np.int32)
+        ind, val, bb = np.zeros(nnz.value, dtype=np.int32), np.zeros(nnz.value), np.zeros(m_loc.value)
+        check(capi.lib().ufe_get_thickness_csr(self._h, w, ct.byref(m_loc), ct.byref(nnz), vp(ptr), vp(ind), vp(val), vp(bb)))
+        A = CSRMatrix(self.mesh.nV, self.mesh.nV, 1, self.mesh.nV, ptr, ind, val)
+        return A if w == 0 else (A, bb)
 
     # ---- L1
     def solve_SSA_DIVA_linearised(self, u_b, v_b, N_b, dN_dx_b, dN_dy_b, basal_friction_coefficient_b,

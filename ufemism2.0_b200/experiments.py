@@ -73,7 +73,8 @@ def MISMIP_8km(h=8e3, seed=synthetic.SEED):
     C = Config(visc_it_norm_dUV_tol=5e-5, visc_it_nit=50, visc_it_relax=0.4,
                stress_balance_PETSc_rtol=1e-4, stress_balance_PETSc_abstol=1e-3,
                choice_sliding_law="Zoet-Iverson", choice_ice_rheology_Glen="uniform",
-               uniform_Glens_flow_factor=1e-16, Hi_min=0.1)
+               uniform_Glens_flow_factor=1e-16, Hi_min=0.1,
+               dHi_semiimplicit_fs=1.5, dHi_PETSc_rtol=1e-8, dHi_PETSc_abstol=1e-4, dt_ice_max=10.0, dt_ice_min=0.2)
     return mesh, C, ice
 
 
@@ -91,7 +92,9 @@ def MISMIPplus(h=2e3, seed=synthetic.SEED, calving_front=None):
                choice_sliding_law="Schoof2005", choice_ice_rheology_Glen="uniform",
                uniform_Glens_flow_factor=1.4280330398280316e-17,
                BC_u_west="zero", BC_u_east="infinite", BC_u_south="infinite", BC_u_north="infinite",
-               BC_v_west="zero", BC_v_east="zero", BC_v_south="zero", BC_v_north="zero")
+               BC_v_west="zero", BC_v_east="zero", BC_v_south="zero", BC_v_north="zero",
+               dHi_semiimplicit_fs=1.5, dHi_PETSc_rtol=1e-8, dHi_PETSc_abstol=1e-6, dt_ice_max=10.0, dt_ice_min=0.5,
+               BC_H_west="infinite", BC_H_east="zero", BC_H_south="infinite", BC_H_north="infinite")
     return mesh, C, ice
 
 

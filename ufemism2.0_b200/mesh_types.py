@@ -178,3 +178,164 @@ def dummy_mesh_5(xmin, xmax, ymin, ymax, nz=12) -> Mesh:
     Tri = np.array([[1, 2, 5], [2, 3, 5], [3, 4, 5], [4, 1, 5]], dtype=np.int32)
     VBI = np.array([6, 4, 2, 8, 0], dtype=np.int32)
     return build_mesh_from_triangles(V, Tri, VBI, xmin, xmax, ymin, ymax, nz=nz)
+
+
+# --------------------------------------------------------------------------------------
+# secondary data read by the ice-thickness path: edges (c-grid),
+# Voronoi cell areas, shared Voronoi boundary lengths, connection vectors
+# --------------------------------------------------------------------------------------
+@dataclass
+class MeshEdges:
+    """``type_mesh`` members read by ``calc_ice_flux_divergence_matrix_upwind``
+    (conservation_of_mass_utilities.f90:21-131) and ``map_velocities_from_b_to_c_2D``
+    (map_velocities_to_c_grid.f90:17-69); all Fortran-ordered, 1-based, 0 = none."""
+
+    nE: int
+    VE: np.ndarray      # (nV,nC_mem) i32: edge of connection ci
+    EV: np.ndarray      # (nE,4) i32: [vi, vj, vl, vr]
+    ETri: np.ndarray    # (nE,2) i32: [til, tir]
+    EBI: np.ndarray     # (nE,) i32
+    Tricc: np.ndarray   # (nTri,2) f64 circumcentres
+    A: np.ndarray       # (nV,) f64 Voronoi cell areas
+    Cw: np.ndarray      # (nV,nC_mem) f64 shared Voronoi boundary lengths
+    D_x: np.ndarray     # (nV,nC_mem) f64
+    D_y: np.ndarray
+    D: np.ndarray
+
+
+def _circumcentres(V, T0):
+    """Circumcentre of every triangle (plane_geometry.f90:282-309 computes the same point as the
+    intersection of two perpendicular bisectors)."""
+    p, q, r = V[T0[:, 0]], V[T0[:, 1]], V[T0[:, 2]]
+    ax, ay = q[:, 0] - p[:, 0], q[:, 1] - p[:, 1]
+    bx, by = r[:, 0] - p[:, 0], r[:, 1] - p[:, 1]
+    d = 2.0 * (ax * by - ay * bx)
+    a2, b2 = ax * ax + ay * ay, bx * bx + by * by
+    cx = p[:, 0] + (by * a2 - ay * b2) / d
+    cy = p[:, 1] + (ax * b2 - bx * a2) / d
+    return np.asfortranarray(np.stack([cx, cy], axis=1))
+
+
+def calc_mesh_edges(mesh: Mesh) -> MeshEdges:
+    """Vectorised ``construct_mesh_edges`` (edges/mesh_edges.f90:19-194), ``calc_Voronoi_cell_areas``,
+    ``calc_connection_widths``, ``calc_connection_lengths`` (mesh_secondary.f90:137-186, 246-366) for
+    the synthetic meshes.  Uses the ordering conventions of C / iTri (iTri(vi,k) lies between
+    C(vi,k) and C(vi,k+1)) instead of the reference's searches; tests/test_thickness.py checks it against a loop-for-loop
+    restatement of those routines."""
+    nV, nTri, ncm = mesh.nV, mesh.nTri, mesh.nC_mem
+    C, nC, iTri, niTri, VBI = mesh.C, mesh.nC.astype(np.int64), mesh.iTri, mesh.niTri.astype(np.int64), mesh.VBI
+    V = mesh.V
+    T0 = mesh.Tri.astype(np.int64) - 1
+    Tricc = _circumcentres(V, T0)
+    tol = 1e-9 * max(mesh.xmax - mesh.xmin, mesh.ymax - mesh.ymin)
+    if (Tricc[:, 0].min() < mesh.xmin - tol or Tricc[:, 0].max() > mesh.xmax + tol or
+            Tricc[:, 1].min() < mesh.ymin - tol or Tricc[:, 1].max() > mesh.ymax + tol):
+        # mesh_utilities.f90:150-153 crashes on such a mesh
+        raise ValueError("found triangle circumcentre outside the mesh domain")
+    np.clip(Tricc[:, 0], mesh.xmin, mesh.xmax, out=Tricc[:, 0])
+    np.clip(Tricc[:, 1], mesh.ymin, mesh.ymax, out=Tricc[:, 1])
+
+    wmax = int(nC.max())
+    ci = np.arange(wmax, dtype=np.int64)[None, :]
+    valid = ci < nC[:, None]
+    vi_of = np.broadcast_to(np.arange(nV, dtype=np.int64)[:, None], (nV, wmax))
+    vj = C[:, :wmax].astype(np.int64) - 1
+    border = (VBI > 0)[:, None]
+
+    # --- edges: numbered in the order (vi ascending, ci ascending) of their first visit, which is
+    # from the lower-numbered end vertex
+    first = valid & (vj > vi_of)
+    fi, fc = np.nonzero(first)                       # row-major = (vi, ci) lexicographic
+    nE = fi.size
+    if nE != int(nC.sum()) // 2:
+        raise ValueError("inconsistent connectivity: sum(nC)/2 != number of edges")
+    VE = np.zeros((nV, ncm), dtype=np.int32, order="F")
+    VE[fi, fc] = np.arange(1, nE + 1, dtype=np.int32)
+    # the same edge seen from vj: find cj with C(vj,cj) == vi
+    a, b = fi, vj[fi, fc]
+    hit = (C[b, :wmax].astype(np.int64) - 1 == a[:, None]) & valid[b]
+    cj = hit.argmax(axis=1)
+    if not hit.any(axis=1).all():
+        raise ValueError("asymmetric connectivity list")
+    VE[b, cj] = VE[fi, fc]
+
+    # left / right triangles and opposite vertices of vi -> vj, seen from vi
+    nCi, isb = nC[fi], border[fi, 0]
+    left_k = fc                                      # iTri(vi,ci) lies left of vi -> C(vi,ci)
+    has_left = left_k < niTri[fi]
+    til = np.where(has_left, iTri[fi, np.minimum(left_k, ncm - 1)], 0).astype(np.int32)
+    vil = np.where(has_left, C[fi, (fc + 1) % np.maximum(nCi, 1)], 0).astype(np.int32)
+    right_k = np.where(isb, fc - 1, (fc - 1) % np.maximum(nCi, 1))
+    has_right = right_k >= 0
+    tir = np.where(has_right, iTri[fi, np.maximum(right_k, 0)], 0).astype(np.int32)
+    vir = np.where(has_right, C[fi, np.maximum(right_k, 0)], 0).astype(np.int32)
+    EV = np.asfortranarray(np.stack([a + 1, b + 1, vil, vir], axis=1).astype(np.int32))
+    ETri = np.asfortranarray(np.stack([til, tir], axis=1).astype(np.int32))
+
+    # edge border index (mesh_edges.f90:196-228)
+    ba, bb_ = VBI[a], VBI[b]
+    EBI = np.zeros(nE, dtype=np.int32)
+    for code, group in ((1, (8, 1, 2)), (3, (2, 3, 4)), (5, (4, 5, 6)), (7, (6, 7, 8))):
+        m = (EBI == 0) & (ba > 0) & (bb_ > 0) & np.isin(ba, group) & np.isin(bb_, group)
+        EBI[m] = code
+
+    # --- connection vectors
+    D_x = np.zeros((nV, ncm), order="F"); D_y = np.zeros((nV, ncm), order="F"); D = np.zeros((nV, ncm), order="F")
+    vjc = np.where(valid, vj, 0)
+    dx_ = np.where(valid, V[vjc, 0] - V[:, 0][:, None], 0.0)
+    dy_ = np.where(valid, V[vjc, 1] - V[:, 1][:, None], 0.0)
+    D_x[:, :wmax], D_y[:, :wmax] = dx_, dy_
+    D[:, :wmax] = np.sqrt(dx_ ** 2 + dy_ ** 2)
+
+    # --- shared Voronoi boundary lengths per edge (find_shared_Voronoi_boundary, mesh_utilities.f90:305-372)
+    ddom = ((mesh.xmax - mesh.xmin) + (mesh.ymax - mesh.ymin)) / 100.0
+    cw_e = np.zeros(nE)
+    inner = EBI == 0
+    if (inner & ((til == 0) | (tir == 0))).any():
+        raise ValueError("non-border edge with a single adjacent triangle")
+    cw_e[inner] = np.hypot(*(Tricc[til[inner] - 1] - Tricc[tir[inner] - 1]).T)
+    bt = np.where(til > 0, til, tir)[~inner] - 1
+    cc1 = Tricc[bt]
+    cc2 = cc1.copy()
+    eb = EBI[~inner]
+    cc2[eb == 1, 1] = mesh.ymax + ddom
+    cc2[eb == 3, 0] = mesh.xmax + ddom
+    cc2[eb == 5, 1] = mesh.ymin - ddom
+    cc2[eb == 7, 0] = mesh.xmin - ddom
+    cw_e[~inner] = np.hypot(*(cc1 - cc2).T)
+    Cw = np.zeros((nV, ncm), order="F")
+    Cw[:, :wmax] = np.where(valid, cw_e[np.maximum(VE[:, :wmax].astype(np.int64) - 1, 0)], 0.0)
+
+    # --- Voronoi cell areas (calc_Voronoi_cell with dx = 0, mesh_utilities.f90:72-303)
+    wt = int(niTri.max())
+    kt = np.arange(wt, dtype=np.int64)[None, :]
+    tv = kt < niTri[:, None]
+    tcc = Tricc[np.maximum(iTri[:, :wt].astype(np.int64) - 1, 0)]          # (nV, wt, 2)
+    rel = np.where(tv[:, :, None], tcc - V[:, None, :], 0.0)
+    # polygon points relative to the vertex: [first projection] + circumcentres + [last projection]
+    P = np.zeros((nV, wt + 2, 2))
+    P[:, 1:wt + 1] = rel
+    bidx = np.nonzero(VBI > 0)[0]
+    if bidx.size:
+        vb = VBI[bidx]
+        firstp = rel[bidx, 0].copy()
+        lastp = rel[bidx, niTri[bidx] - 1].copy()
+        Vb = V[bidx]
+        for codes, axis, lim in (((1, 2), 1, mesh.ymax), ((3, 4), 0, mesh.xmax), ((5, 6), 1, mesh.ymin), ((7, 8), 0, mesh.xmin)):
+            m = np.isin(vb, codes)
+            firstp[m, axis] = lim - Vb[m, axis]
+        for codes, axis, lim in (((2, 3), 0, mesh.xmax), ((4, 5), 1, mesh.ymin), ((6, 7), 0, mesh.xmin), ((8, 1), 1, mesh.ymax)):
+            m = np.isin(vb, codes)
+            lastp[m, axis] = lim - Vb[m, axis]
+        P[bidx, 0] = firstp
+        # the last projection goes right after the last circumcentre; later slots stay at the vertex
+        # itself (zero vector), which adds nothing to the cross products, like the corner points do
+        P[bidx, niTri[bidx] + 1] = lastp
+    # free vertices: close the polygon (slot 0 = last circumcentre so that pair (0,1) is the wrap-around)
+    fidx = np.nonzero(VBI == 0)[0]
+    P[fidx, 0] = rel[fidx, niTri[fidx] - 1]
+    cross = P[:, 1:, 0] * P[:, :-1, 1] - P[:, 1:, 1] * P[:, :-1, 0]
+    A = np.abs(cross).sum(axis=1) / 2.0
+
+    return MeshEdges(nE=nE, VE=VE, EV=EV, ETri=ETri, EBI=EBI, Tricc=Tricc, A=np.ascontiguousarray(A), Cw=Cw,
+                     D_x=D_x, D_y=D_y, D=D)

@@ -27,9 +27,12 @@ pi = 3.141592653589793       # parameters.f90:44
 SEED = 20261017
 
 
-def lattice_mesh(xmin, xmax, ymin, ymax, nx, ny, jitter=0.2, seed=SEED, nz=12) -> Mesh:
+def lattice_mesh(xmin, xmax, ymin, ymax, nx, ny, jitter=0.2, seed=SEED, nz=12, delaunay=False) -> Mesh:
     """nx x ny lattice, alternating cell diagonals, interior vertices jittered by
-    ``jitter*h*U(-1,1)`` (PCG64), vertices and triangles sorted by x (centroid x)."""
+    ``jitter*h*U(-1,1)`` (PCG64), vertices and triangles sorted by x (centroid x).
+    ``delaunay=True`` re-triangulates the jittered points (scipy.spatial.Delaunay) so that the
+    Voronoi dual the ice-thickness path reads (cell areas, shared boundary lengths) is a proper
+    tessellation, as it is on the reference's own (Delaunay-refined) meshes."""
     assert nx >= 3 and ny >= 3
     dx = (xmax - xmin) / (nx - 1)
     dy = (ymax - ymin) / (ny - 1)
@@ -68,6 +71,15 @@ def lattice_mesh(xmin, xmax, ymin, ymax, nx, ny, jitter=0.2, seed=SEED, nz=12) -
     Tri0 = np.concatenate([t1, t2], axis=0)
     V = np.stack([x.ravel(), y.ravel()], axis=1)
     VBI = VBI.ravel()
+    if delaunay:
+        from scipy.spatial import Delaunay
+        Tri0 = Delaunay(V).simplices.astype(np.int64)
+        p, q, r = V[Tri0[:, 0]], V[Tri0[:, 1]], V[Tri0[:, 2]]
+        area2 = (q[:, 0] - p[:, 0]) * (r[:, 1] - p[:, 1]) - (q[:, 1] - p[:, 1]) * (r[:, 0] - p[:, 0])
+        Tri0 = Tri0[np.abs(area2) > 1e-9 * dx * dy]              # slivers between collinear border points
+        area2 = area2[np.abs(area2) > 1e-9 * dx * dy]
+        cw = area2 < 0
+        Tri0[cw] = Tri0[cw][:, [0, 2, 1]]                         # counter-clockwise
 
     # x-sort vertices (mesh_contiguous_domains.f90:45-138)
     vperm = np.argsort(V[:, 0], kind="stable")
