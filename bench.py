@@ -345,6 +345,34 @@ def main():
                                       "launch-latency-bound at this size")
     roofline = roofline_small
     krylov_iteration = other_kernels = None
+
+    # ---------------- the thickness update that follows the velocity solve ----
+    def thickness_leg(solver, msh, Cfg, geo, reps=5):
+        """calc_dHi_dt_semiimplicit on the velocities the last solve left on the device (single rank)."""
+        from ufemism2_0_b200 import mesh_types
+        try:
+            solver.set_mesh_edges(mesh_types.calc_mesh_edges(msh))
+        except ValueError as e:
+            return {"skipped": str(e)}
+        n = msh.nV
+        f = dict(Hi=geo.Hi, Hb=geo.Hb, SL=geo.SL, SMB=np.full(n, 0.3), BMB=np.zeros(n), LMB=np.zeros(n),
+                 fraction_margin=np.ones(n), mask_noice=np.zeros(n, dtype=np.int32), dHi_dt_target=np.zeros(n))
+        out, t = None, []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            out = solver.calc_dHi_dt_semiimplicit(f, 1.0)
+            t.append(time.perf_counter() - t0)
+        tm = solver.thickness_timing()
+        dq = tm.pop("divq_algorithmic_bytes")
+        return {"what": "calc_dHi_dt_semiimplicit, dt = 1 yr, f_s = %g, rtol %g, host buffers in and out" % (Cfg.dHi_semiimplicit_fs, Cfg.dHi_PETSc_rtol),
+                "nV": n, "wall_ms_per_call": 1e3 * float(np.mean(t[1:])), "n_Axb_its": out["n_Axb_its"], "flags": out["flags"],
+                "device_ms": tm, "k_thk_divq": {"algorithmic_bytes": dq, "achieved_GBs": dq / (tm["ms_divq"] * 1e-3) / 1e9,
+                                                  "frac": dq / (tm["ms_divq"] * 1e-3) / 1e9 / peak,
+                                                  "note": "includes the 1-thread init kernel launched before it"}}
+
+    thickness = thickness_large = None
+    if world == 1:
+        thickness = thickness_leg(S, mesh, C, ice)
     if not args.no_large_roofline:
         # the configuration the north_star quotes the SpMV roofline on: ~1 M vertices, N ~ 4 M unknowns,
         # ~76 M non-zeros, partitioned over the ranks; one truncated Picard iteration assembles the matrix
@@ -397,6 +425,8 @@ def main():
                                 "algorithmic_bytes_per_iteration": it_bytes, "achieved": it_bytes / (it_ms * 1e-3) / 1e9,
                                 "unit": "GB/s", "frac": it_bytes / (it_ms * 1e-3) / 1e9 / peak,
                                 "note": "per rank, same mesh as `roofline`; includes the host polls between iteration batches"}
+        if world == 1:
+            thickness_large = thickness_leg(SL, meshL, CL, iceL, reps=2)
         SL.close()
         del meshL, iceL
     if rank != 0:
@@ -422,7 +452,8 @@ def main():
         "comm": ("single GPU" if world == 1 else ("peer memory (IPC/NVLink) inside the Krylov loop, NCCL outside" if last.reserved else "NCCL")),
         "e2e": e2e, "warm": warm, "gpu_launches": int(sum(i.gpu_launches for i in infos)),
         "roofline": roofline, "roofline_bench_workload": roofline_small, "krylov_iteration": krylov_iteration,
-        "other_kernels_large_mesh": other_kernels, "clocks": clocks,
+        "other_kernels_large_mesh": other_kernels, "thickness_update": thickness,
+        "thickness_update_large_mesh": thickness_large, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_leg(mesh, C, ice, args.cpu_seconds, n_visc_full=last.n_visc_its)

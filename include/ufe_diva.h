@@ -311,6 +311,11 @@ int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_config *cfg,
  * recent semi-implicit call.  Reference CSR layout (row vi = [vi, C(vi,1..nC)]).  Query sizes with ind == NULL. */
 int ufe_get_thickness_csr(ufe_handle *h, int32_t which, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind,
                           double *val, double *bb);
+/* device time (CUDA events on the handle's stream) of the most recent thickness call, milliseconds:
+ * ms[0] inputs host->device, [1] k_thk_divq (M_divQ, divQ, explicit dH/dt, time-step limit), [2] rest of the explicit
+ * scheme + border BCs + system assembly, [3] Krylov solve, [4] finishing kernel, [5] outputs device->host; and the
+ * algorithmic bytes of one k_thk_divq launch (104 B per connection + 96 B per vertex). */
+int ufe_get_thickness_timing(ufe_handle *h, double ms[6], double *divq_algorithmic_bytes);
 
 /* L1 -- replaces solve_SSA_DIVA_linearised (solve_linearised_SSA_DIVA.f90:23-178; call
  * sites DIVA_main.f90:189-192, SSA_main.f90:178-181).  Full-length (nTri) arrays.

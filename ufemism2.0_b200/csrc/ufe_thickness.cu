@@ -36,6 +36,8 @@ struct ThicknessState {
   DevSystem S;                           // AA (val), B*AA (valS), bb, bS, x
   KrylovWork kw;
   bool kw_alloc = false, have_system = false, have_M = false;
+  cudaEvent_t ev[7] = {};                // start | inputs up | M_divQ + divQ | explicit scheme + system | Krylov | finish | outputs down
+  float ms[6] = {0, 0, 0, 0, 0, 0};      // device time of those six intervals for the most recent call
 };
 
 // accessors implemented in ufe_diva.cu
@@ -59,6 +61,7 @@ void ufe_thickness_free(ThicknessState *t) {
                   t->S.valS, t->S.bb, t->S.bS, t->S.x};
   for (double *p : dl) cudaFree(p);
   cudaFree(t->dtlim);
+  for (cudaEvent_t e : t->ev) if (e) cudaEventDestroy(e);
   if (t->kw_alloc) ufe_krylov_free(t->kw);
   delete t;
 }
@@ -375,6 +378,7 @@ extern "C" int ufe_mesh_set_edges(ufe_handle *h, const ufe_mesh_edges *e) {
   UFE_TRY(talloc(&t->dtlim, 1)); UFE_TRY(talloc(&t->dt_dev, 1));
   UFE_TRY(talloc(&t->Mval, (size_t)t->nnz)); UFE_TRY(talloc(&t->S.val, (size_t)t->nnz)); UFE_TRY(talloc(&t->S.valS, (size_t)t->nnz));
   UFE_TRY(talloc(&t->S.ind, (size_t)t->nnz));
+  for (cudaEvent_t &e : t->ev) UFE_CUDA(cudaEventCreate(&e));
   t->S.N = nV; t->S.m_loc = nV; t->S.r1 = 1; t->S.nnz = t->nnz; t->S.jmin = 1; t->S.jmax = nV;
   k_thk_pattern<<<ufe_div_up(nV, 256), 256, 0, c.st>>>(nV, ncm, c.dm->C, c.dm->nC, t->S.ptr, t->S.ind);
   UFE_LAUNCH_CHECK();
@@ -409,6 +413,7 @@ static int thk_check(const ufe_thickness_config *cfg, const ufe_thickness_fields
 static int thk_upload(const ThkCtx &c, const ufe_thickness_fields *f, const double **u, const double **v) {
   ThicknessState *t = c.t;
   const size_t nb = sizeof(double) * (size_t)t->nV;
+  UFE_CUDA(cudaEventRecord(t->ev[0], c.st));
   const double *src[] = {f->Hi, f->Hb, f->SL, f->SMB, f->BMB, f->LMB, f->fraction_margin, f->dHi_dt_target};
   double *dst[] = {t->Hi, t->Hb, t->SL, t->SMB, t->BMB, t->LMB, t->fm, t->target};
   for (int i = 0; i < 8; i++) UFE_CUDA(cudaMemcpyAsync(dst[i], src[i], nb, cudaMemcpyHostToDevice, c.st));
@@ -424,6 +429,7 @@ static int thk_upload(const ThkCtx &c, const ufe_thickness_fields *f, const doub
   } else {
     *u = c.u_res; *v = c.v_res;
   }
+  UFE_CUDA(cudaEventRecord(t->ev[1], c.st));
   return UFE_OK;
 }
 
@@ -434,7 +440,9 @@ static int thk_download(const ThkCtx &c, ufe_thickness_fields *f) {
   if (f->dHi_dt) UFE_CUDA(cudaMemcpyAsync(f->dHi_dt, t->dHi_dt, nb, cudaMemcpyDeviceToHost, c.st));
   if (f->Hi_tplusdt) UFE_CUDA(cudaMemcpyAsync(f->Hi_tplusdt, t->Hi_tp, nb, cudaMemcpyDeviceToHost, c.st));
   if (f->divQ) UFE_CUDA(cudaMemcpyAsync(f->divQ, t->divQ, nb, cudaMemcpyDeviceToHost, c.st));
+  UFE_CUDA(cudaEventRecord(t->ev[6], c.st));
   UFE_CUDA(cudaStreamSynchronize(c.st));
+  for (int i = 0; i < 6; i++) UFE_CUDA(cudaEventElapsedTime(&t->ms[i], t->ev[i], t->ev[i + 1]));
   return UFE_OK;
 }
 
@@ -463,6 +471,7 @@ static int thk_explicit_resident(const ThkCtx &c, const ufe_thickness_config *cf
   k_thk_divq<<<g, 256, 0, c.st>>>(thk_mesh(c), u, v, t->fm, t->Hi, t->SMB, t->BMB, t->LMB, t->target, cfg->Hi_min,
                                   t->Mval, t->divQ, t->dHi_dt, t->AMB, t->dtlim);
   UFE_LAUNCH_CHECK();
+  UFE_CUDA(cudaEventRecord(t->ev[2], c.st));
   t->have_M = true;
   k_thk_hs<<<g, 256, 0, c.st>>>(nV, 0, dt_in, cfg->dt_ice_min, t->dtlim, t->dt_dev, t->Hi, t->dHi_dt, t->Hb, t->SL,
                                 t->Hi_tp, t->Hs0);
@@ -482,6 +491,7 @@ extern "C" int ufe_calc_dHi_dt_explicit(ufe_handle *h, const ufe_thickness_confi
   const double *u, *v;
   UFE_TRY(thk_upload(c, f, &u, &v));
   UFE_TRY(thk_explicit_resident(c, cfg, f, u, v, *dt));
+  for (int i = 3; i <= 5; i++) UFE_CUDA(cudaEventRecord(c.t->ev[i], c.st));
   UFE_CUDA(cudaMemcpyAsync(dt, c.t->dt_dev, sizeof(double), cudaMemcpyDeviceToHost, c.st));
   return thk_download(c, f);
 }
@@ -509,6 +519,7 @@ extern "C" int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_c
                                     cfg->dHi_semiimplicit_fs, t->Mval, t->Hi, t->divQ, t->fm, t->SMB, t->BMB, t->LMB,
                                     t->target, t->Hi_tp, t->S.val, t->S.valS, t->S.bb, t->S.bS);
   UFE_LAUNCH_CHECK();
+  UFE_CUDA(cudaEventRecord(t->ev[3], c.st));
   t->have_system = true;
   if (!t->kw_alloc) { UFE_TRY(ufe_krylov_alloc(t->kw, nV, nV, true)); t->kw_alloc = true; }
   Comm comm;
@@ -517,8 +528,10 @@ extern "C" int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_c
                          cfg->krylov_maxits > 0 ? cfg->krylov_maxits : 10000, 0, &its, &fl));
   if (n_Axb_its) *n_Axb_its = its;
   if (flags) *flags = fl;
+  UFE_CUDA(cudaEventRecord(t->ev[4], c.st));
   k_thk_finish_semi<<<g, 256, 0, c.st>>>(nV, dt, t->S.x, t->Hi, t->Hi_tp, t->dHi_dt, t->AMB);
   UFE_LAUNCH_CHECK();
+  UFE_CUDA(cudaEventRecord(t->ev[5], c.st));
   return thk_download(c, f);
 }
 
@@ -537,5 +550,16 @@ extern "C" int ufe_get_thickness_csr(ufe_handle *h, int32_t which, int32_t *m_lo
   UFE_CUDA(cudaMemcpy(ind, t->S.ind, sizeof(int) * (size_t)t->nnz, cudaMemcpyDeviceToHost));
   if (val) UFE_CUDA(cudaMemcpy(val, which == 0 ? t->Mval : t->S.val, sizeof(double) * (size_t)t->nnz, cudaMemcpyDeviceToHost));
   if (bb && which == 1) UFE_CUDA(cudaMemcpy(bb, t->S.bb, sizeof(double) * (size_t)t->nV, cudaMemcpyDeviceToHost));
+  return UFE_OK;
+}
+
+extern "C" int ufe_get_thickness_timing(ufe_handle *h, double ms[6], double *divq_algorithmic_bytes) {
+  ThkCtx c;
+  UFE_TRY(thk_ctx(h, c, true));
+  if (!ms) { ufe_set_error("null argument"); return UFE_ERR_INVALID; }
+  for (int i = 0; i < 6; i++) ms[i] = c.t->ms[i];
+  // k_thk_divq: per connection VE 4 + C 4 + ETri 8 + (u,v) of two triangles 32 + Cw,D_x,D_y,D 32 + fraction_margin, Hi
+  // gathers 16 + val out 8 = 104 B; per vertex ptr 4 + nC 4 + A 8 + 6 fields in 48 + diagonal 8 + 3 fields out 24 = 96 B
+  if (divq_algorithmic_bytes) *divq_algorithmic_bytes = 104.0 * (c.t->nnz - c.t->nV) + 96.0 * c.t->nV;
   return UFE_OK;
 }

@@ -383,6 +383,14 @@ class DIVASolver:
         A = CSRMatrix(self.mesh.nV, self.mesh.nV, 1, self.mesh.nV, ptr, ind, val)
         return A if w == 0 else (A, bb)
 
+    def thickness_timing(self) -> dict:
+        """Device-time split (ms) of the most recent thickness call + algorithmic bytes of k_thk_divq."""
+        ms = (ct.c_double * 6)()
+        by = ct.c_double()
+        check(capi.lib().ufe_get_thickness_timing(self._h, ms, ct.byref(by)))
+        keys = ("ms_h2d", "ms_divq", "ms_explicit_and_system", "ms_krylov", "ms_finish", "ms_d2h")
+        return dict(zip(keys, list(ms)), divq_algorithmic_bytes=by.value)
+
     # ---- L1
     def solve_SSA_DIVA_linearised(self, u_b, v_b, N_b, dN_dx_b, dN_dy_b, basal_friction_coefficient_b,
                                   tau_dx_b, tau_dy_b, PETSc_rtol, PETSc_abstol, BC_prescr_mask_b=None,

@@ -83,6 +83,26 @@ module diva_gpu_bindings
     type(c_ptr)        :: nccl_unique_id
   end type ufe_comm
 
+  ! ---- ice-thickness path (SURVEY.md 8f rank 2) -------------------------------------------------
+  ! type_mesh members read by calc_ice_flux_divergence_matrix_upwind / map_velocities_from_b_to_c_2D
+  type, bind(C) :: ufe_mesh_edges
+    integer(c_int32_t) :: nE
+    type(c_ptr)        :: VE, ETri, A, Cw, D_x, D_y, D      ! c_loc( mesh%VE), c_loc( mesh%ETri), ...
+  end type ufe_mesh_edges
+
+  type, bind(C) :: ufe_thickness_config
+    real(c_double)     :: dHi_semiimplicit_fs, dHi_PETSc_rtol, dHi_PETSc_abstol
+    integer(c_int32_t) :: BC_H(4)                           ! north, east, south, west: 1 'infinite', 2 'zero'
+    real(c_double)     :: dt_ice_max, dt_ice_min, Hi_min
+    integer(c_int32_t) :: krylov_method, krylov_maxits
+  end type ufe_thickness_config
+
+  type, bind(C) :: ufe_thickness_fields
+    type(c_ptr) :: Hi, Hb, SL, u_vav_b, v_vav_b, SMB, BMB, LMB, fraction_margin, dHi_dt_target
+    type(c_ptr) :: mask_noice, BC_prescr_mask, BC_prescr_Hi
+    type(c_ptr) :: AMB, dHi_dt, Hi_tplusdt, divQ
+  end type ufe_thickness_fields
+
   interface
 
     function ufe_last_error_string() bind(C, name='ufe_last_error_string') result(s)
@@ -172,6 +192,33 @@ module diva_gpu_bindings
       integer(c_int32_t), intent(out)   :: n_Axb_its
       type(c_ptr),        value         :: BC_prescr_mask_b, BC_prescr_u_b, BC_prescr_v_b   ! c_null_ptr when absent
     end function ufe_ssa_diva_linearised
+
+    ! upload mesh%VE, ETri, A, Cw, D_x, D_y, D once per mesh
+    integer(c_int) function ufe_mesh_set_edges( handle, edges) bind(C, name='ufe_mesh_set_edges')
+      import :: c_int, c_ptr, ufe_mesh_edges
+      type(c_ptr),          value      :: handle
+      type(ufe_mesh_edges), intent(in) :: edges
+    end function ufe_mesh_set_edges
+
+    ! replaces calc_dHi_dt_explicit (conservation_of_mass_explicit.f90:23-138)
+    integer(c_int) function ufe_calc_dHi_dt_explicit( handle, cfg, fields, dt) bind(C, name='ufe_calc_dHi_dt_explicit')
+      import :: c_int, c_ptr, c_double, ufe_thickness_config, ufe_thickness_fields
+      type(c_ptr),                value         :: handle
+      type(ufe_thickness_config), intent(in)    :: cfg
+      type(ufe_thickness_fields), intent(inout) :: fields
+      real(c_double),             intent(inout) :: dt
+    end function ufe_calc_dHi_dt_explicit
+
+    ! replaces calc_dHi_dt_semiimplicit (conservation_of_mass_semiimplicit.f90:24-173)
+    integer(c_int) function ufe_calc_dHi_dt_semiimplicit( handle, cfg, fields, dt, n_Axb_its, flags) &
+        bind(C, name='ufe_calc_dHi_dt_semiimplicit')
+      import :: c_int, c_int32_t, c_ptr, c_double, ufe_thickness_config, ufe_thickness_fields
+      type(c_ptr),                value         :: handle
+      type(ufe_thickness_config), intent(in)    :: cfg
+      type(ufe_thickness_fields), intent(inout) :: fields
+      real(c_double),             value         :: dt
+      integer(c_int32_t),         intent(out)   :: n_Axb_its, flags
+    end function ufe_calc_dHi_dt_semiimplicit
 
   end interface
 
