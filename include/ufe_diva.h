@@ -311,6 +311,21 @@ int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_config *cfg,
  * recent semi-implicit call.  Reference CSR layout (row vi = [vi, C(vi,1..nC)]).  Query sizes with ind == NULL. */
 int ufe_get_thickness_csr(ufe_handle *h, int32_t which, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind,
                           double *val, double *bb);
+/* ---- SURVEY.md 8(f) rank 1, last part: replaces calc_vertical_velocities
+ * (src/UFEMISM/ice_dynamics/conservation_of_mass/vertical_velocities.f90:18-210), called after dHi_dt is known.
+ * Reads the device-resident u_3D_b / v_3D_b of the most recent solve_DIVA and ice%u_3D / v_3D of the
+ * ufe_calc_secondary_velocities call that followed it; needs ufe_mesh_set_edges.  All (nV) unless noted. */
+typedef struct ufe_vertical_velocity_inputs {
+  const double *Hi, *Hib, *dHb_dt, *dHi_dt, *BMB;
+  const int32_t *mask_grounded_ice, *mask_floating_ice;
+  const double *dzeta_dx_ak, *dzeta_dy_ak, *dzeta_dz_ak;    /* (nV,nz), calc_zeta_gradients (zeta_gradients.f90:129-131) */
+} ufe_vertical_velocity_inputs;
+int ufe_calc_vertical_velocities(ufe_handle *h, const ufe_vertical_velocity_inputs *in, double *w_3D /* (nV,nz) out */);
+/* mesh%M_ddx_a_a (which = 0) / M_ddy_a_a (1), calc_matrix_operators_mesh_a_a
+ * (mesh_disc_calc_matrix_operators_2D.f90:60-196), as built on the device.  Query sizes with ind == NULL. */
+int ufe_mesh_get_operator_a_a(ufe_handle *h, int32_t which, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind,
+                              double *val);
+
 /* device time (CUDA events on the handle's stream) of the most recent thickness call, milliseconds:
  * ms[0] inputs host->device, [1] k_thk_divq (M_divQ, divQ, explicit dH/dt, time-step limit), [2] rest of the explicit
  * scheme + border BCs + system assembly, [3] Krylov solve, [4] finishing kernel, [5] outputs device->host; and the

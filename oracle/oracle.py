@@ -963,3 +963,110 @@ def calc_dHi_dt_semiimplicit(mesh, E, C, f, dt, linear_solver="direct"):
     dHi_dt = (Hi_tp - Hi) / dt                                                 # :168
     AMB = dHi_dt - AMB                                                         # :175
     return dict(dHi_dt=dHi_dt, Hi_tplusdt=Hi_tp, divQ=divQ, AMB=AMB, AA=AA, bb=bb, n_Axb_its=its, explicit=ex)
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY.md 8f rank 1 (remaining part): calc_vertical_velocities
+#   src/UFEMISM/ice_dynamics/conservation_of_mass/vertical_velocities.f90:18-210
+#   operators ddx_a_a / ddy_a_a: mesh_disc_calc_matrix_operators_2D.f90:60-196,
+#   calc_shape_functions_2D_reg_1st_order shape_functions.f90:140-216
+# --------------------------------------------------------------------------------------
+def calc_matrix_operators_mesh_a_a(mesh):
+    """M_ddx_a_a, M_ddy_a_a (shared pattern: row vi = [vi, neighbourhood in flood-fill order])."""
+    nV, V = mesh.nV, mesh.V
+    q = 1.5
+    ptr = np.ones(nV + 1, dtype=np.int32)
+    ind, vx, vy = [], [], []
+
+    def extend(stack):                                       # extend_group_single_iteration_a, mesh_utilities.f90:1856-1894
+        for i in range(len(stack)):
+            vi = stack[i]
+            for ci in range(mesh.nC[vi - 1]):
+                vj = int(mesh.C[vi - 1, ci])
+                if vj not in stack:
+                    stack.append(vj)
+
+    for vi in range(1, nV + 1):
+        x, y = V[vi - 1]
+        stack = [vi]
+        while len(stack) - 1 < 2:                            # n_neighbours_min = 2 (:90)
+            extend(stack)
+        while True:
+            nb = [vj for vj in stack if vj != vi]
+            dx = np.array([V[vj - 1, 0] - x for vj in nb])
+            dy = np.array([V[vj - 1, 1] - y for vj in nb])
+            w = 1.0 / (np.sqrt(dx * dx + dy * dy) ** q)
+            A = np.zeros((2, 2))
+            for c in range(len(nb)):
+                A[0, 0] += w[c] ** 2 * dx[c] * dx[c]
+                A[0, 1] += w[c] ** 2 * dx[c] * dy[c]
+                A[1, 0] += w[c] ** 2 * dy[c] * dx[c]
+                A[1, 1] += w[c] ** 2 * dy[c] * dy[c]
+            det = A[0, 0] * A[1, 1] - A[0, 1] * A[1, 0]
+            if abs(det) < np.finfo(float).tiny:
+                extend(stack)
+                continue
+            M = np.array([[A[1, 1] / det, -A[0, 1] / det], [-A[1, 0] / det, A[0, 0] / det]])
+            Nfx = w ** 2 * ((M[0, 0] * dx) + (M[0, 1] * dy))
+            Nfy = w ** 2 * ((M[1, 0] * dx) + (M[1, 1] * dy))
+            break
+        sx = 0.0
+        sy = 0.0
+        for c in range(len(nb)):                             # sum() in array order
+            sx += Nfx[c]
+            sy += Nfy[c]
+        ind.append(vi); vx.append(-sx); vy.append(-sy)
+        for c, vj in enumerate(nb):
+            ind.append(vj); vx.append(Nfx[c]); vy.append(Nfy[c])
+        ptr[vi] = len(ind) + 1
+    ind = np.array(ind, dtype=np.int32)
+    return (CSR(nV, nV, 1, nV, ptr, ind, np.array(vx)), CSR(nV, nV, 1, nV, ptr, ind, np.array(vy)))
+
+
+def calc_vertical_velocities(mesh, E, ice, u_3D_b, v_3D_b, u_3D, v_3D, BMB):
+    """vertical_velocities.f90:18-210.  ice: dict with Hi, Hib, dHb_dt, dHi_dt, mask_grounded_ice, mask_floating_ice,
+    dzeta_dx_ak, dzeta_dy_ak, dzeta_dz_ak.  Returns w_3D (nV,nz)."""
+    nV, nz, zeta, V = mesh.nV, mesh.nz, mesh.zeta, mesh.V
+    Mx, My = calc_matrix_operators_mesh_a_a(mesh)
+    dHib_dx, dHib_dy = spmv(Mx, ice["Hib"]), spmv(My, ice["Hib"])                      # :113-114
+    nE = E["nE"]
+    u_c, v_c = np.zeros((nE, nz)), np.zeros((nE, nz))
+    for k in range(nz):                                                                # map_velocities_from_b_to_c_3D
+        u_c[:, k], v_c[:, k] = map_velocities_from_b_to_c_2D(E, u_3D_b[:, k], v_3D_b[:, k])
+    w = np.zeros((nV, nz), order="F")
+    for vi in range(nV):
+        gr, fl = bool(ice["mask_grounded_ice"][vi]), bool(ice["mask_floating_ice"][vi])
+        if gr:
+            dHib_dt = ice["dHb_dt"][vi]
+        elif fl:
+            dHib_dt = -ice["dHi_dt"][vi] * ice_density / seawater_density
+        else:
+            dHib_dt = 0.0
+        if not (gr or fl):
+            continue
+        w[vi, nz - 1] = (u_3D[vi, nz - 1] * dHib_dx[vi]) + (v_3D[vi, nz - 1] * dHib_dy[vi]) + dHib_dt + min(0.0, BMB[vi])
+        if ice["Hi"][vi] < 10.0:
+            w[vi, :] = w[vi, nz - 1]
+            continue
+        for ks in range(nz - 2, -1, -1):
+            dzeta = zeta[ks + 1] - zeta[ks]
+            cint = 0.0
+            for ci in range(mesh.nC[vi]):
+                vj = int(mesh.C[vi, ci]) - 1
+                ei = int(E["VE"][vi, ci]) - 1
+                u_ks = 0.5 * (u_c[ei, ks] + u_c[ei, ks + 1])
+                v_ks = 0.5 * (v_c[ei, ks] + v_c[ei, ks + 1])
+                dS = E["Cw"][vi, ci]
+                n0, n1 = V[vj, 0] - V[vi, 0], V[vj, 1] - V[vi, 1]
+                nn = np.sqrt(n0 * n0 + n1 * n1)
+                n0, n1 = n0 / nn, n1 / nn
+                cint = cint + (u_ks * n0 + v_ks * n1) * dS
+            grad_uv = cint / E["A"][vi]
+            du = (u_3D[vi, ks + 1] - u_3D[vi, ks]) / dzeta
+            dv = (v_3D[vi, ks + 1] - v_3D[vi, ks]) / dzeta
+            zx = 0.5 * (ice["dzeta_dx_ak"][vi, ks] + ice["dzeta_dx_ak"][vi, ks + 1])
+            zy = 0.5 * (ice["dzeta_dy_ak"][vi, ks] + ice["dzeta_dy_ak"][vi, ks + 1])
+            zz = 0.5 * (ice["dzeta_dz_ak"][vi, ks] + ice["dzeta_dz_ak"][vi, ks + 1])
+            dw = -1.0 / zz * (grad_uv + zx * du + zy * dv)
+            w[vi, ks] = w[vi, ks + 1] - dzeta * dw
+    return w

@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
         int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ufe_csr), sizeof(ufe_mesh),
           sizeof(ufe_config), sizeof(ufe_ice_inputs), sizeof(ufe_diva_state), sizeof(ufe_ssa_state),
           sizeof(ufe_solve_info), sizeof(ufe_comm), sizeof(ufe_mesh_edges), sizeof(ufe_thickness_config),
-          sizeof(ufe_thickness_fields)); return 0; }""")
+          sizeof(ufe_thickness_fields)); printf("%zu\\n", sizeof(ufe_vertical_velocity_inputs)); return 0; }""")
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
@@ -51,7 +51,7 @@ def test_struct_layouts_match_header():
         sizes = list(map(int, subprocess.check_output([exe]).split()))
     mirrors = [capi.ufe_csr, capi.ufe_mesh, capi.ufe_config, capi.ufe_ice_inputs, capi.ufe_diva_state,
                capi.ufe_ssa_state, capi.ufe_solve_info, capi.ufe_comm, capi.ufe_mesh_edges, capi.ufe_thickness_config,
-               capi.ufe_thickness_fields]
+               capi.ufe_thickness_fields, capi.ufe_vertical_velocity_inputs]
     assert sizes == [ct.sizeof(m) for m in mirrors]
 
 

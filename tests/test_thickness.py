@@ -336,3 +336,97 @@ def test_gpu_thickness_error_paths():
     with pytest.raises(diva.UfeError, match="unknown BC_H"):
         S.calc_dHi_dt_explicit(f, 1.0)
     S.close()
+
+
+# ------------------------------------------------------------------------------------------
+# calc_vertical_velocities (last part)
+# ------------------------------------------------------------------------------------------
+def _zeta_gradients(oracle, mesh, Hi, Hs):
+    """dzeta_dx_ak, dzeta_dy_ak, dzeta_dz_ak as calc_zeta_gradients defines them (zeta_gradients.f90:91-131)."""
+    Mx, My = oracle.calc_matrix_operators_mesh_a_a(mesh)
+    H = np.maximum(0.1, Hi)
+    dHi_dx, dHi_dy = oracle.spmv(Mx, Hi), oracle.spmv(My, Hi)
+    dHs_dx, dHs_dy = oracle.spmv(Mx, Hs), oracle.spmv(My, Hs)
+    z = mesh.zeta[None, :]
+    zx = (1.0 / H)[:, None] * (dHs_dx[:, None] - z * dHi_dx[:, None])
+    zy = (1.0 / H)[:, None] * (dHs_dy[:, None] - z * dHi_dy[:, None])
+    zz = np.repeat((-1.0 / H)[:, None], mesh.nz, axis=1)
+    return np.asfortranarray(zx), np.asfortranarray(zy), np.asfortranarray(zz)
+
+
+def test_oracle_a_a_operators_are_exact_on_linear_functions(oracle):
+    """ct_discretisation_mapping_derivatives.f90: first-order operators reproduce the gradient of a linear function."""
+    mesh = _mesh(15, 11)
+    Mx, My = oracle.calc_matrix_operators_mesh_a_a(mesh)
+    f = 3.0 + 2e-4 * mesh.V[:, 0] - 5e-5 * mesh.V[:, 1]
+    assert np.abs(oracle.spmv(Mx, f) - 2e-4).max() < 1e-15 and np.abs(oracle.spmv(My, f) + 5e-5).max() < 1e-15
+    # row vi starts with vi, then its neighbours in C order (one flood-fill sweep is enough: n_neighbours_min = 2)
+    for vi in (0, mesh.nV // 3, mesh.nV - 1):
+        k0, k1 = Mx.ptr[vi] - 1, Mx.ptr[vi + 1] - 1
+        assert Mx.ind[k0] == vi + 1 and np.array_equal(Mx.ind[k0 + 1:k1], mesh.C[vi, : mesh.nC[vi]])
+
+
+def test_oracle_vertical_velocities_uniform_slab_known_answer(oracle):
+    """Incompressibility on a flat slab (derivation in vertical_velocities.f90:23-63): u = u0 x, v = u0 y at every depth,
+    H uniform, flat fixed base  =>  w(zeta) = -2 u0 H (1 - zeta)."""
+    mesh = _mesh(17, 13)
+    E = mesh_types.calc_mesh_edges(mesh)
+    nV, nT, nz = mesh.nV, mesh.nTri, mesh.nz
+    u0, H = 1e-3, 800.0
+    u3b = np.asfortranarray(np.repeat((u0 * E.Tricc[:, 0])[:, None], nz, axis=1))
+    v3b = np.asfortranarray(np.repeat((u0 * E.Tricc[:, 1])[:, None], nz, axis=1))
+    u3 = np.asfortranarray(np.repeat((u0 * mesh.V[:, 0])[:, None], nz, axis=1))
+    v3 = np.asfortranarray(np.repeat((u0 * mesh.V[:, 1])[:, None], nz, axis=1))
+    ice = dict(Hi=np.full(nV, H), Hib=np.full(nV, -50.0), dHb_dt=np.zeros(nV), dHi_dt=np.zeros(nV),
+               mask_grounded_ice=np.ones(nV, dtype=np.int32), mask_floating_ice=np.zeros(nV, dtype=np.int32),
+               dzeta_dx_ak=np.zeros((nV, nz), order="F"), dzeta_dy_ak=np.zeros((nV, nz), order="F"),
+               dzeta_dz_ak=np.full((nV, nz), -1.0 / H, order="F"))
+    w = oracle.calc_vertical_velocities(mesh, _edges_dict(E), ice, u3b, v3b, u3, v3, np.zeros(nV))
+    inner = _interior(mesh)
+    want = -2.0 * u0 * H * (1.0 - mesh.zeta)[None, :]
+    assert np.abs(w[inner] - want).max() < 1e-11
+    # thin ice: no stretching (:149-152); no ice: no velocity (:131-134)
+    ice["Hi"][5] = 5.0
+    ice["mask_grounded_ice"][7] = 0
+    w = oracle.calc_vertical_velocities(mesh, _edges_dict(E), ice, u3b, v3b, u3, v3, np.full(nV, -0.3))
+    assert (w[5] == w[5, -1]).all() and (w[7] == 0.0).all() and abs(w[9, -1] + 0.3) < 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_a_a_operators_match_oracle(oracle):
+    mesh = _mesh(31, 23, jitter=0.3)
+    S = _solver(mesh, config.Config())
+    S.set_mesh_edges(mesh_types.calc_mesh_edges(mesh))
+    Mx, My = oracle.calc_matrix_operators_mesh_a_a(mesh)
+    for which, want in (("ddx", Mx), ("ddy", My)):
+        got = S.get_operator_a_a(which)
+        assert np.array_equal(got.ptr, want.ptr) and np.array_equal(got.ind, want.ind)      # bit-exact pattern
+        assert _relmax(got.val, want.val) < 1e-11
+    S.close()
+
+
+@pytest.mark.gpu
+def test_gpu_vertical_velocities_match_oracle(oracle):
+    """solve_DIVA -> calc_secondary_velocities -> calc_vertical_velocities, all on the resident fields."""
+    mesh, C, ice = experiments.MISMIPplus(8e3)
+    E = mesh_types.calc_mesh_edges(mesh)
+    S = diva.initialise_DIVA_solver(mesh, C)
+    S.solve_DIVA(ice)
+    S.set_mesh_edges(E)
+    nV, nz = mesh.nV, mesh.nz
+    rng = np.random.default_rng(2)
+    zx, zy, zz = _zeta_gradients(oracle, mesh, ice.Hi, ice.Hs)
+    vin = dict(Hi=ice.Hi, Hib=ice.Hib, dHb_dt=0.01 * rng.standard_normal(nV), dHi_dt=0.5 * rng.standard_normal(nV),
+               BMB=rng.standard_normal(nV), mask_grounded_ice=ice.mask_grounded_ice, mask_floating_ice=ice.mask_floating_ice,
+               dzeta_dx_ak=zx, dzeta_dy_ak=zy, dzeta_dz_ak=zz)
+    with pytest.raises(diva.UfeError, match="ufe_calc_secondary_velocities"):
+        S.calc_vertical_velocities(vin)
+    sec = S.calc_secondary_velocities()
+    w = S.calc_vertical_velocities(vin)
+    want = oracle.calc_vertical_velocities(mesh, _edges_dict(E), vin, S.u_3D_b, S.v_3D_b, sec["u_3D"], sec["v_3D"], vin["BMB"])
+    assert np.isfinite(w).all() and np.abs(want).max() > 0.0
+    assert _relmax(w, want) < 1e-10
+    # thin / ice-free vertices follow the special cases
+    noice = (np.asarray(ice.mask_grounded_ice) == 0) & (np.asarray(ice.mask_floating_ice) == 0)
+    assert (w[noice] == 0.0).all()
+    S.close()

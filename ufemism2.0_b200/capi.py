@@ -118,6 +118,14 @@ class ufe_thickness_fields(ct.Structure):
                 [(n, ct.c_void_p) for n in THICKNESS_OUT])
 
 
+VERTICAL_IN = ("Hi", "Hib", "dHb_dt", "dHi_dt", "BMB", "mask_grounded_ice", "mask_floating_ice",
+               "dzeta_dx_ak", "dzeta_dy_ak", "dzeta_dz_ak")
+
+
+class ufe_vertical_velocity_inputs(ct.Structure):
+    _fields_ = [(n, ct.c_void_p) for n in VERTICAL_IN]
+
+
 class ufe_comm(ct.Structure):
     _fields_ = [("rank", c_i32), ("nranks", c_i32), ("device", c_i32), ("nccl_unique_id", ct.c_char_p)]
 
@@ -129,7 +137,7 @@ EXPORTS = [
     "ufe_diva_download", "ufe_diva_reset_state", "ufe_calc_secondary_velocities", "ufe_ssa_diva_linearised", "ufe_mesh_get_operator",
     "ufe_mesh_apply_operator", "ufe_get_stiffness_csr", "ufe_bench_spmv", "ufe_get_ownership",
     "ufe_mesh_set_edges", "ufe_calc_dHi_dt_explicit", "ufe_calc_dHi_dt_semiimplicit", "ufe_get_thickness_csr",
-    "ufe_get_thickness_timing",
+    "ufe_get_thickness_timing", "ufe_calc_vertical_velocities", "ufe_mesh_get_operator_a_a",
 ]
 
 _lib = None

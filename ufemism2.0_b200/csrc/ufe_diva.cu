@@ -114,7 +114,7 @@ struct ufe_handle {
   KrylovWork kw;
   double *sym = nullptr;                       // symmetric peer buffer (several ranks): owns S.x, kw.pg, kw.sg
   SecondaryFields sec;                         // calc_secondary_velocities outputs (allocated on first use)
-  bool sec_alloc = false;
+  bool sec_alloc = false, sec_current = false;
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
   int pc_used = -1;                            // resolved preconditioner for the cached pattern (-1 = undecided)
   int pc_age = -1, pc_last_its = 0;            // bjacobi_lu reuse: solves since the last factorisation (-1 = never), its of the last solve
@@ -132,10 +132,18 @@ struct ufe_handle {
 // ufe_thickness.cu reaches the mesh, the stream and the resident velocities through this view
 struct ThicknessState;
 void ufe_thickness_free(ThicknessState *t);
-int ufe_handle_thickness_view(ufe_handle *h, DevMesh **dm, cudaStream_t *st, int *nranks, int *device,
-                              double **u_vav_b, double **v_vav_b, ThicknessState ***slot) {
-  *dm = &h->dm; *st = h->st; *nranks = h->comm.nranks; *device = h->device;
-  *u_vav_b = h->F.u_vav_b; *v_vav_b = h->F.v_vav_b; *slot = &h->thk;
+struct ThkHandleView {
+  DevMesh *dm; cudaStream_t st; int nranks, device;
+  double *u_vav_b, *v_vav_b, *u_3D_b, *v_3D_b, *u_3D, *v_3D;   // u_3D / v_3D: nullptr until calc_secondary_velocities ran
+  bool sec_current;                                             // ... for the most recent solve
+  ThicknessState **slot;
+};
+int ufe_handle_thickness_view(ufe_handle *h, ThkHandleView *v) {
+  v->dm = &h->dm; v->st = h->st; v->nranks = h->comm.nranks; v->device = h->device;
+  v->u_vav_b = h->F.u_vav_b; v->v_vav_b = h->F.v_vav_b; v->u_3D_b = h->F.u_3D_b; v->v_3D_b = h->F.v_3D_b;
+  v->u_3D = h->sec_alloc ? h->sec.u_3D : nullptr; v->v_3D = h->sec_alloc ? h->sec.v_3D : nullptr;
+  v->sec_current = h->sec_current;
+  v->slot = &h->thk;
   return UFE_OK;
 }
 
@@ -738,6 +746,7 @@ static int picard_resident(ufe_handle *h, int is_diva, ufe_solve_info *info) {
   DivaFields &F = h->F;
   memset(info, 0, sizeof *info);
   const int64_t launches0 = g_launch_count;
+  h->sec_current = false;
   cudaEventRecord(h->ev[0], h->st);
   if (!h->grounded_ice_exists) {           // DIVA_main.f90:123-134
     const size_t nT = nTri;
@@ -997,6 +1006,7 @@ extern "C" int ufe_calc_secondary_velocities(ufe_handle *h, ufe_secondary_veloci
   D2H(out->u_vav, O.u_vav, nV); D2H(out->v_vav, O.v_vav, nV); D2H(out->uabs_vav, O.uabs_vav, nV);
   D2H(out->R_shear, O.R_shear, nV);
   UFE_CUDA(cudaStreamSynchronize(h->st));
+  h->sec_current = true;
   return UFE_OK;
 }
 

@@ -216,8 +216,35 @@ __device__ bool shape_reg_2nd(double x, double y, int n_c, const double *xc, con
   return true;
 }
 
+// regular 1st order (shape_functions.f90:140-216, 2x2 inverse matrix_algebra.f90:11-19, 110-131): Nfx[i], Nfy[i] of the
+// neighbours and the home point's Nfx_i, Nfy_i; returns false if singular
+__device__ bool shape_reg_1st(double x, double y, int n_c, const double *xc, const double *yc, double *Ni, double *Nfx,
+                              double *Nfy) {
+  double A00 = 0.0, A01 = 0.0, A10 = 0.0, A11 = 0.0;
+  for (int i = 0; i < n_c; i++) {
+    const double dx = xc[i] - x, dy = yc[i] - y;
+    const double w = 1.0 / pow(norm2_2(dx, dy), 1.5);
+    const double w2 = w * w;
+    A00 += w2 * dx * dx; A01 += w2 * dx * dy; A10 += w2 * dy * dx; A11 += w2 * dy * dy;
+  }
+  const double det = A00 * A11 - A01 * A10;
+  if (fabs(det) < DBL_MIN) return false;
+  const double M00 = A11 / det, M01 = -A01 / det, M10 = -A10 / det, M11 = A00 / det;
+  double sx = 0.0, sy = 0.0;
+  for (int i = 0; i < n_c; i++) {
+    const double dx = xc[i] - x, dy = yc[i] - y;
+    const double w = 1.0 / pow(norm2_2(dx, dy), 1.5);
+    const double w2 = w * w;
+    Nfx[i] = w2 * ((M00 * dx) + (M01 * dy));
+    Nfy[i] = w2 * ((M10 * dx) + (M11 * dy));
+    sx += Nfx[i]; sy += Nfy[i];
+  }
+  Ni[0] = -sx; Ni[1] = -sy;
+  return true;
+}
+
 // FAMILY 0: a_b (rows = triangles, cols = vertices), 1: b_a (rows = vertices, cols = triangles),
-// 2: b_b 2nd order.  PASS 0: count, PASS 1: fill.
+// 2: b_b 2nd order, 3: a_a (ddx, ddy; regular 1st order).  PASS 0: count, PASS 1: fill.
 template <int FAMILY, int PASS>
 __global__ void __launch_bounds__(128)
 k_build_operator(MeshView m, int row1, int m_loc, int *__restrict__ counts, const int *__restrict__ ptr,
@@ -239,12 +266,40 @@ k_build_operator(MeshView m, int row1, int m_loc, int *__restrict__ counts, cons
     const int nt = m.niTri[row - 1];
     for (int k = 0; k < nt; k++) stack[n++] = m.iTri[(size_t)k * m.nV + row - 1];
     while (n < 3) if (!extend_b(m, stack, n)) { atomicExch(err, 1); return; }
+  } else if (FAMILY == 3) {
+    x = m.V[row - 1]; y = m.V[(size_t)m.nV + row - 1];
+    stack[n++] = row;
+    while (n - 1 < 2) if (!extend_a(m, stack, n)) { atomicExch(err, 1); return; }
   } else {
     x = m.TriGC[row - 1]; y = m.TriGC[(size_t)m.nTri + row - 1];
     stack[n++] = row;
     while (n - 1 < 5) if (!extend_b(m, stack, n)) { atomicExch(err, 1); return; }
   }
-  if (FAMILY < 2) {
+  if (FAMILY == 3) {
+    double Nfx[UFE_STACK_MAX], Nfy[UFE_STACK_MAX], Ni[2];
+    int nc;
+    for (;;) {
+      nc = 0;
+      for (int i = 0; i < n; i++) {
+        const int id = stack[i];
+        if (id == row) continue;
+        xc[nc] = m.V[id - 1]; yc[nc] = m.V[(size_t)m.nV + id - 1]; nc++;
+      }
+      if (shape_reg_1st(x, y, nc, xc, yc, Ni, Nfx, Nfy)) break;
+      if (!extend_a(m, stack, n)) { atomicExch(err, 1); return; }
+    }
+    if (PASS == 0) { counts[r] = nc + 1; return; }
+    int k = ptr[r] - 1;
+    ind[k] = row; v0[k] = Ni[0]; v1[k] = Ni[1];
+    k++;
+    int c = 0;
+    for (int i = 0; i < n; i++) {
+      const int id = stack[i];
+      if (id == row) continue;
+      ind[k] = id; v0[k] = Nfx[c]; v1[k] = Nfy[c];
+      k++; c++;
+    }
+  } else if (FAMILY < 2) {
     double Nf[UFE_STACK_MAX], Nfx[UFE_STACK_MAX], Nfy[UFE_STACK_MAX];
     for (;;) {
       for (int i = 0; i < n; i++) {
@@ -316,7 +371,7 @@ int ufe_counts_to_ptr(cudaStream_t st, int m_loc, int *counts, int *ptr, int *nn
 
 template <int FAMILY>
 static int build_family(cudaStream_t st, const MeshView &mv, int row1, int m_loc, int m, int n, DevFamily &F) {
-  F.m_loc = m_loc; F.m = m; F.n = n; F.i1 = row1; F.nval = (FAMILY == 2) ? 5 : 3;
+  F.m_loc = m_loc; F.m = m; F.n = n; F.i1 = row1; F.nval = (FAMILY == 2) ? 5 : (FAMILY == 3 ? 2 : 3);
   int *counts = nullptr, *err = nullptr;
   UFE_CUDA(cudaMalloc(&counts, sizeof(int) * (m_loc > 0 ? m_loc : 1)));
   UFE_CUDA(cudaMalloc(&err, sizeof(int)));
@@ -343,6 +398,13 @@ static int build_family(cudaStream_t st, const MeshView &mv, int row1, int m_loc
   UFE_CUDA(cudaStreamSynchronize(st));
   cudaFree(counts); cudaFree(err);
   return UFE_OK;
+}
+
+// M_ddx_a_a / M_ddy_a_a (calc_matrix_operators_mesh_a_a, mesh_disc_calc_matrix_operators_2D.f90:60-196), all rows
+int ufe_build_operators_a_a(cudaStream_t st, const DevMesh &dm, DevFamily &F) {
+  UFE_TRY(ufe_operators_init_tables());
+  MeshView mv{dm.nV, dm.nTri, dm.nC_mem, dm.V, dm.TriGC, dm.Tri, dm.TriC, dm.C, dm.nC, dm.iTri, dm.niTri};
+  return build_family<3>(st, mv, 1, dm.nV, dm.nV, dm.nV, F);
 }
 
 int ufe_build_operators(cudaStream_t st, const DevMesh &dm, int vi1, int vi2, int ti1, int ti2, bool need[3],

@@ -36,13 +36,26 @@ struct ThicknessState {
   DevSystem S;                           // AA (val), B*AA (valS), bb, bS, x
   KrylovWork kw;
   bool kw_alloc = false, have_system = false, have_M = false;
+  // calc_vertical_velocities
+  DevFamily aa;                          // M_ddx_a_a, M_ddy_a_a (built on first use)
+  bool aa_built = false;
+  double *vv_in[5] = {};                 // Hib, dHb_dt, dHi_dt, BMB, Hi (nV)
+  double *vv_dz[3] = {};                 // dzeta_dx_ak, dzeta_dy_ak, dzeta_dz_ak (nV,nz)
+  double *w_3D = nullptr;                // (nV,nz)
+  int *vv_mask[2] = {};                  // mask_grounded_ice, mask_floating_ice
   cudaEvent_t ev[7] = {};                // start | inputs up | M_divQ + divQ | explicit scheme + system | Krylov | finish | outputs down
   float ms[6] = {0, 0, 0, 0, 0, 0};      // device time of those six intervals for the most recent call
 };
 
 // accessors implemented in ufe_diva.cu
-int ufe_handle_thickness_view(ufe_handle *h, DevMesh **dm, cudaStream_t *st, int *nranks, int *device,
-                              double **u_vav_b, double **v_vav_b, ThicknessState ***slot);
+struct ThkHandleView {
+  DevMesh *dm; cudaStream_t st; int nranks, device;
+  double *u_vav_b, *v_vav_b, *u_3D_b, *v_3D_b, *u_3D, *v_3D;
+  bool sec_current;
+  ThicknessState **slot;
+};
+int ufe_handle_thickness_view(ufe_handle *h, ThkHandleView *v);
+int ufe_build_operators_a_a(cudaStream_t st, const DevMesh &dm, DevFamily &F);
 
 template <typename T>
 static int talloc(T **p, size_t n) {
@@ -61,6 +74,10 @@ void ufe_thickness_free(ThicknessState *t) {
                   t->S.valS, t->S.bb, t->S.bS, t->S.x};
   for (double *p : dl) cudaFree(p);
   cudaFree(t->dtlim);
+  for (double *p : t->vv_in) cudaFree(p);
+  for (double *p : t->vv_dz) cudaFree(p);
+  for (int *p : t->vv_mask) cudaFree(p);
+  cudaFree(t->w_3D); cudaFree(t->aa.ptr); cudaFree(t->aa.ind); cudaFree(t->aa.val[0]); cudaFree(t->aa.val[1]);
   for (cudaEvent_t e : t->ev) if (e) cudaEventDestroy(e);
   if (t->kw_alloc) ufe_krylov_free(t->kw);
   delete t;
@@ -305,13 +322,15 @@ __global__ void k_thk_finish_semi(int nV, double dt, const double *__restrict__ 
 // ------------------------------------------------------------------------------------
 struct ThkCtx {
   ufe_handle *h; DevMesh *dm; cudaStream_t st; ThicknessState *t; double *u_res, *v_res;
+  ThkHandleView hv;
 };
 
 static int thk_ctx(ufe_handle *h, ThkCtx &c, bool need_state) {
   if (!h) { ufe_set_error("null handle"); return UFE_ERR_INVALID; }
-  int nranks = 1, device = 0;
-  ThicknessState **slot = nullptr;
-  UFE_TRY(ufe_handle_thickness_view(h, &c.dm, &c.st, &nranks, &device, &c.u_res, &c.v_res, &slot));
+  UFE_TRY(ufe_handle_thickness_view(h, &c.hv));
+  const int nranks = c.hv.nranks, device = c.hv.device;
+  ThicknessState **slot = c.hv.slot;
+  c.dm = c.hv.dm; c.st = c.hv.st; c.u_res = c.hv.u_vav_b; c.v_res = c.hv.v_vav_b;
   if (nranks != 1) {
     ufe_set_error("the ice-thickness path runs on a single-rank handle (nranks = %d)", nranks);
     return UFE_ERR_INVALID;
@@ -561,5 +580,170 @@ extern "C" int ufe_get_thickness_timing(ufe_handle *h, double ms[6], double *div
   // k_thk_divq: per connection VE 4 + C 4 + ETri 8 + (u,v) of two triangles 32 + Cw,D_x,D_y,D 32 + fraction_margin, Hi
   // gathers 16 + val out 8 = 104 B; per vertex ptr 4 + nC 4 + A 8 + 6 fields in 48 + diagonal 8 + 3 fields out 24 = 96 B
   if (divq_algorithmic_bytes) *divq_algorithmic_bytes = 104.0 * (c.t->nnz - c.t->nV) + 96.0 * c.t->nV;
+  return UFE_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// calc_vertical_velocities (vertical_velocities.f90:18-210): w from conservation of mass in each 3-D
+// Voronoi cell.  One thread per vertex; the loop over connections is the outer loop and the loop over
+// layers the inner one, which keeps the reference's summation order (connections 1..nC) for every
+// layer while each edge's geometry is read once.  3-D fields are (n, nz) column-major.
+// ------------------------------------------------------------------------------------
+template <int NZ>
+__global__ void __launch_bounds__(128)
+k_vertical_velocities(ThkMesh M, const double *__restrict__ V, const double *__restrict__ zeta, const int *__restrict__ aptr,
+                      const int *__restrict__ aind, const double *__restrict__ addx, const double *__restrict__ addy,
+                      const double *__restrict__ Hib, const double *__restrict__ dHb_dt, const double *__restrict__ dHi_dt,
+                      const double *__restrict__ BMB, const double *__restrict__ Hi, const int *__restrict__ mask_gr,
+                      const int *__restrict__ mask_fl, const double *__restrict__ zx, const double *__restrict__ zy,
+                      const double *__restrict__ zz, const double *__restrict__ u3b, const double *__restrict__ v3b,
+                      const double *__restrict__ u3, const double *__restrict__ v3, double *__restrict__ w) {
+  const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vi >= M.nV) return;
+  const size_t nV = M.nV, nT = M.nTri;
+  const bool gr = mask_gr[vi] != 0, fl = mask_fl[vi] != 0;
+  if (!(gr || fl)) {
+#pragma unroll
+    for (int k = 0; k < NZ; k++) w[k * nV + vi] = 0.0;
+    return;
+  }
+  double dHib_dt;
+  if (gr) dHib_dt = dHb_dt[vi];
+  else dHib_dt = -dHi_dt[vi] * THK_ICE_DENSITY / THK_SEAWATER_DENSITY;
+  // slopes of the ice base: rows of M_ddx_a_a / M_ddy_a_a
+  double sx = 0.0, sy = 0.0;
+  for (int k = aptr[vi] - 1; k < aptr[vi + 1] - 1; k++) {
+    const double hb = Hib[aind[k] - 1];
+    sx += addx[k] * hb; sy += addy[k] * hb;
+  }
+  const double wb = (u3[(NZ - 1) * nV + vi] * sx) + (v3[(NZ - 1) * nV + vi] * sy) + dHib_dt + fmin(0.0, BMB[vi]);
+  if (Hi[vi] < 10.0) {
+#pragma unroll
+    for (int k = 0; k < NZ; k++) w[k * nV + vi] = wb;
+    return;
+  }
+  double cint[NZ - 1];
+#pragma unroll
+  for (int k = 0; k < NZ - 1; k++) cint[k] = 0.0;
+  const int n = M.nC[vi];
+  const double x0 = V[vi], y0 = V[nV + vi];
+  for (int ci = 0; ci < n; ci++) {
+    const size_t o = (size_t)ci * nV + vi;
+    const int vj = M.C[o] - 1, ei = M.VE[o] - 1;
+    const int til = M.ETri[ei], tir = M.ETri[M.nE + ei];
+    const double dS = M.Cw[o];
+    double n0 = V[vj] - x0, n1 = V[nV + vj] - y0;
+    const double nn = sqrt(n0 * n0 + n1 * n1);
+    n0 = n0 / nn; n1 = n1 / nn;
+    double up = 0.0, vp = 0.0;     // edge velocity of the layer below (k+1), carried through the loop
+#pragma unroll
+    for (int k = NZ - 1; k >= 0; k--) {
+      double uc, vc;               // map_velocities_from_b_to_c_3D
+      if (til == 0) { uc = u3b[k * nT + tir - 1]; vc = v3b[k * nT + tir - 1]; }
+      else if (tir == 0) { uc = u3b[k * nT + til - 1]; vc = v3b[k * nT + til - 1]; }
+      else { uc = (u3b[k * nT + til - 1] + u3b[k * nT + tir - 1]) / 2.0; vc = (v3b[k * nT + til - 1] + v3b[k * nT + tir - 1]) / 2.0; }
+      if (k < NZ - 1) {
+        const double u_ks = 0.5 * (uc + up), v_ks = 0.5 * (vc + vp);
+        cint[k] = cint[k] + (u_ks * n0 + v_ks * n1) * dS;
+      }
+      up = uc; vp = vc;
+    }
+  }
+  const double A_i = M.A[vi];
+  double wk = wb;
+  w[(NZ - 1) * nV + vi] = wb;
+  double u_below = u3[(NZ - 1) * nV + vi], v_below = v3[(NZ - 1) * nV + vi];
+  double zx_b = zx[(NZ - 1) * nV + vi], zy_b = zy[(NZ - 1) * nV + vi], zz_b = zz[(NZ - 1) * nV + vi];
+#pragma unroll
+  for (int ks = NZ - 2; ks >= 0; ks--) {
+    const double dzeta = zeta[ks + 1] - zeta[ks];
+    const double grad_uv = cint[ks] / A_i;
+    const double u_k = u3[ks * nV + vi], v_k = v3[ks * nV + vi];
+    const double du = (u_below - u_k) / dzeta, dv = (v_below - v_k) / dzeta;
+    const double zx_k = zx[ks * nV + vi], zy_k = zy[ks * nV + vi], zz_k = zz[ks * nV + vi];
+    const double dzx = 0.5 * (zx_k + zx_b), dzy = 0.5 * (zy_k + zy_b), dzz = 0.5 * (zz_k + zz_b);
+    const double dw = -1.0 / dzz * (grad_uv + dzx * du + dzy * dv);
+    wk = wk - dzeta * dw;
+    w[ks * nV + vi] = wk;
+    u_below = u_k; v_below = v_k; zx_b = zx_k; zy_b = zy_k; zz_b = zz_k;
+  }
+}
+
+// first use: build M_ddx_a_a / M_ddy_a_a on the device and allocate the work fields
+static int thk_ensure_vv(const ThkCtx &c) {
+  ThicknessState *t = c.t;
+  if (t->aa_built) return UFE_OK;
+  const size_t nV = t->nV, nz = c.dm->nz;
+  UFE_TRY(ufe_build_operators_a_a(c.st, *c.dm, t->aa));
+  for (double *&p : t->vv_in) UFE_TRY(talloc(&p, nV));
+  for (double *&p : t->vv_dz) UFE_TRY(talloc(&p, nV * nz));
+  for (int *&p : t->vv_mask) UFE_TRY(talloc(&p, nV));
+  UFE_TRY(talloc(&t->w_3D, nV * nz));
+  t->aa_built = true;
+  return UFE_OK;
+}
+
+template <int NZ>
+static void launch_vv(const ThkCtx &c, const ThkMesh &M) {
+  ThicknessState *t = c.t;
+  k_vertical_velocities<NZ><<<ufe_div_up(M.nV, 128), 128, 0, c.st>>>(
+      M, c.dm->V, c.dm->zeta, t->aa.ptr, t->aa.ind, t->aa.val[0], t->aa.val[1], t->vv_in[0], t->vv_in[1], t->vv_in[2],
+      t->vv_in[3], t->vv_in[4], t->vv_mask[0], t->vv_mask[1], t->vv_dz[0], t->vv_dz[1], t->vv_dz[2], c.hv.u_3D_b, c.hv.v_3D_b,
+      c.hv.u_3D, c.hv.v_3D, t->w_3D);
+}
+
+extern "C" int ufe_calc_vertical_velocities(ufe_handle *h, const ufe_vertical_velocity_inputs *in, double *w_3D) {
+  ThkCtx c;
+  if (!in || !w_3D) { ufe_set_error("null argument"); return UFE_ERR_INVALID; }
+  if (!in->Hi || !in->Hib || !in->dHb_dt || !in->dHi_dt || !in->BMB || !in->mask_grounded_ice || !in->mask_floating_ice ||
+      !in->dzeta_dx_ak || !in->dzeta_dy_ak || !in->dzeta_dz_ak) {
+    ufe_set_error("ufe_vertical_velocity_inputs: a required input field is NULL"); return UFE_ERR_INVALID;
+  }
+  UFE_TRY(thk_ctx(h, c, true));
+  if (!c.hv.u_3D || !c.hv.sec_current) {
+    ufe_set_error("calc_vertical_velocities reads ice%%u_3D / v_3D: call ufe_calc_secondary_velocities after the velocity solve first");
+    return UFE_ERR_INVALID;
+  }
+  ThicknessState *t = c.t;
+  const size_t nV = t->nV, nz = c.dm->nz;
+  UFE_TRY(thk_ensure_vv(c));
+  const double *src[5] = {in->Hib, in->dHb_dt, in->dHi_dt, in->BMB, in->Hi};
+  for (int i = 0; i < 5; i++) UFE_CUDA(cudaMemcpyAsync(t->vv_in[i], src[i], 8 * nV, cudaMemcpyHostToDevice, c.st));
+  const double *dz[3] = {in->dzeta_dx_ak, in->dzeta_dy_ak, in->dzeta_dz_ak};
+  for (int i = 0; i < 3; i++) UFE_CUDA(cudaMemcpyAsync(t->vv_dz[i], dz[i], 8 * nV * nz, cudaMemcpyHostToDevice, c.st));
+  UFE_CUDA(cudaMemcpyAsync(t->vv_mask[0], in->mask_grounded_ice, 4 * nV, cudaMemcpyHostToDevice, c.st));
+  UFE_CUDA(cudaMemcpyAsync(t->vv_mask[1], in->mask_floating_ice, 4 * nV, cudaMemcpyHostToDevice, c.st));
+  const ThkMesh M = thk_mesh(c);
+  switch ((int)nz) {
+    case 4: launch_vv<4>(c, M); break;
+    case 8: launch_vv<8>(c, M); break;
+    case 10: launch_vv<10>(c, M); break;
+    case 12: launch_vv<12>(c, M); break;
+    case 16: launch_vv<16>(c, M); break;
+    case 20: launch_vv<20>(c, M); break;
+    case 24: launch_vv<24>(c, M); break;
+    case 32: launch_vv<32>(c, M); break;
+    default: ufe_set_error("calc_vertical_velocities: nz = %d is not instantiated (4, 8, 10, 12, 16, 20, 24, 32)", (int)nz); return UFE_ERR_INVALID;
+  }
+  UFE_LAUNCH_CHECK();
+  UFE_CUDA(cudaMemcpyAsync(w_3D, t->w_3D, 8 * nV * nz, cudaMemcpyDeviceToHost, c.st));
+  UFE_CUDA(cudaStreamSynchronize(c.st));
+  return UFE_OK;
+}
+
+// M_ddx_a_a / M_ddy_a_a as built on the device (which: 0 ddx, 1 ddy); query sizes with ind == NULL
+extern "C" int ufe_mesh_get_operator_a_a(ufe_handle *h, int32_t which, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind,
+                                         double *val) {
+  ThkCtx c;
+  UFE_TRY(thk_ctx(h, c, true));
+  ThicknessState *t = c.t;
+  if (which < 0 || which > 1) { ufe_set_error("bad operator id"); return UFE_ERR_INVALID; }
+  UFE_TRY(thk_ensure_vv(c));
+  if (m_loc) *m_loc = t->aa.m_loc;
+  if (nnz) *nnz = t->aa.nnz;
+  if (!ind) return UFE_OK;
+  if (ptr) UFE_CUDA(cudaMemcpy(ptr, t->aa.ptr, sizeof(int) * ((size_t)t->aa.m_loc + 1), cudaMemcpyDeviceToHost));
+  UFE_CUDA(cudaMemcpy(ind, t->aa.ind, sizeof(int) * (size_t)t->aa.nnz, cudaMemcpyDeviceToHost));
+  if (val) UFE_CUDA(cudaMemcpy(val, t->aa.val[which], sizeof(double) * (size_t)t->aa.nnz, cudaMemcpyDeviceToHost));
   return UFE_OK;
 }

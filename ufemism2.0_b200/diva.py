@@ -383,6 +383,30 @@ class DIVASolver:
         A = CSRMatrix(self.mesh.nV, self.mesh.nV, 1, self.mesh.nV, ptr, ind, val)
         return A if w == 0 else (A, bb)
 
+    def calc_vertical_velocities(self, ice: dict) -> np.ndarray:
+        """calc_vertical_velocities(mesh, ice, BMB) (vertical_velocities.f90:18): ``ice`` holds Hi, Hib, dHb_dt, dHi_dt,
+        BMB, mask_grounded_ice, mask_floating_ice, dzeta_dx_ak, dzeta_dy_ak, dzeta_dz_ak; the horizontal velocities are
+        the resident results of solve_DIVA + calc_secondary_velocities.  Returns ice%w_3D (nV,nz)."""
+        s = capi.ufe_vertical_velocity_inputs()
+        keep = []
+        for n in capi.VERTICAL_IN:
+            a = np.asfortranarray(ice[n], dtype=np.int32 if n.startswith("mask") else np.float64)
+            keep.append(a)
+            setattr(s, n, vp(a))
+        w = np.zeros((self.mesh.nV, self.mesh.nz), order="F")
+        check(capi.lib().ufe_calc_vertical_velocities(self._h, ct.byref(s), vp(w)))
+        return w
+
+    def get_operator_a_a(self, which: str) -> CSRMatrix:
+        """mesh%M_ddx_a_a / M_ddy_a_a as built on the device (needs set_mesh_edges)."""
+        w = {"ddx": 0, "ddy": 1}[which]
+        m_loc, nnz = ct.c_int32(), ct.c_int32()
+        check(capi.lib().ufe_mesh_get_operator_a_a(self._h, w, ct.byref(m_loc), ct.byref(nnz), None, None, None))
+        ptr = np.zeros(m_loc.value + 1, dtype=np.int32)
+        ind, val = np.zeros(nnz.value, dtype=np.int32), np.zeros(nnz.value)
+        check(capi.lib().ufe_mesh_get_operator_a_a(self._h, w, ct.byref(m_loc), ct.byref(nnz), vp(ptr), vp(ind), vp(val)))
+        return CSRMatrix(self.mesh.nV, self.mesh.nV, 1, self.mesh.nV, ptr, ind, val)
+
     def thickness_timing(self) -> dict:
         """Device-time split (ms) of the most recent thickness call + algorithmic bytes of k_thk_divq."""
         ms = (ct.c_double * 6)()

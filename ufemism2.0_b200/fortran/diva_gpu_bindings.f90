@@ -103,6 +103,12 @@ module diva_gpu_bindings
     type(c_ptr) :: AMB, dHi_dt, Hi_tplusdt, divQ
   end type ufe_thickness_fields
 
+  ! dummy arguments / type_ice_model members read by calc_vertical_velocities (vertical_velocities.f90:18-210)
+  type, bind(C) :: ufe_vertical_velocity_inputs
+    type(c_ptr) :: Hi, Hib, dHb_dt, dHi_dt, BMB, mask_grounded_ice, mask_floating_ice
+    type(c_ptr) :: dzeta_dx_ak, dzeta_dy_ak, dzeta_dz_ak
+  end type ufe_vertical_velocity_inputs
+
   interface
 
     function ufe_last_error_string() bind(C, name='ufe_last_error_string') result(s)
@@ -219,6 +225,14 @@ module diva_gpu_bindings
       real(c_double),             value         :: dt
       integer(c_int32_t),         intent(out)   :: n_Axb_its, flags
     end function ufe_calc_dHi_dt_semiimplicit
+
+    ! replaces calc_vertical_velocities (vertical_velocities.f90:18-210); w_3D (nV,nz) out
+    integer(c_int) function ufe_calc_vertical_velocities( handle, inputs, w_3D) bind(C, name='ufe_calc_vertical_velocities')
+      import :: c_int, c_ptr, c_double, ufe_vertical_velocity_inputs
+      type(c_ptr),                        value       :: handle
+      type(ufe_vertical_velocity_inputs), intent(in)  :: inputs
+      real(c_double),                     intent(out) :: w_3D(*)
+    end function ufe_calc_vertical_velocities
 
   end interface
 
