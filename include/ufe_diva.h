@@ -45,7 +45,8 @@ enum {
 enum {
   UFE_FLAG_PICARD_MAXIT = 1,  /* 'viscosity iteration failed to converge within N iterations' */
   UFE_FLAG_KRYLOV_MAXIT = 2,  /* a linear solve hit maxits (the reference never checks KSPGetConvergedReason) */
-  UFE_FLAG_KRYLOV_DIVERGED = 4
+  UFE_FLAG_KRYLOV_DIVERGED = 4,
+  UFE_FLAG_NEGATIVE_HI = 8    /* calc_dHi_dt: 'encountered negative values for Hi_tplusdt - time step too large?' */
 };
 
 /* ---- type_sparse_matrix_CSR_dp (src/UPSY/basic/CSR_sparse_matrix_type.f90:15-38) -- */
@@ -307,6 +308,13 @@ int ufe_calc_dHi_dt_explicit(ufe_handle *h, const ufe_thickness_config *cfg, ufe
  * Hi + dt*dHi_dt is never handed to PETSc as non-zero, petsc_basic.f90:99-128). */
 int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_config *cfg, ufe_thickness_fields *f, double dt,
                                  int32_t *n_Axb_its, int32_t *flags);
+/* replaces calc_dHi_dt (conservation_of_mass_main.f90:22-109), the entry the predictor-corrector scheme calls:
+ * dispatch on C%choice_ice_integration_method, then clip negative thicknesses (UFE_FLAG_NEGATIVE_HI in *flags
+ * where the reference warns), AMB = AMB + (Hi_tplusdt - Hi)/dt - dHi_dt, dHi_dt = (Hi_tplusdt - Hi)/dt.
+ * dt inout (only the explicit scheme changes it). */
+enum { UFE_THK_NONE = 0, UFE_THK_EXPLICIT = 1, UFE_THK_SEMI_IMPLICIT = 2 };   /* 'none' | 'explicit' | 'semi-implicit' */
+int ufe_calc_dHi_dt(ufe_handle *h, const ufe_thickness_config *cfg, int32_t choice_ice_integration_method,
+                    ufe_thickness_fields *f, double *dt, int32_t *n_Axb_its, int32_t *flags);
 /* which = 0: M_divQ of the most recent call; 1: the stiffness matrix AA and load vector bb of the most
  * recent semi-implicit call.  Reference CSR layout (row vi = [vi, C(vi,1..nC)]).  Query sizes with ind == NULL. */
 int ufe_get_thickness_csr(ufe_handle *h, int32_t which, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind,

@@ -965,6 +965,28 @@ def calc_dHi_dt_semiimplicit(mesh, E, C, f, dt, linear_solver="direct"):
     return dict(dHi_dt=dHi_dt, Hi_tplusdt=Hi_tp, divQ=divQ, AMB=AMB, AA=AA, bb=bb, n_Axb_its=its, explicit=ex)
 
 
+def calc_dHi_dt(mesh, E, C, f, dt, linear_solver="direct"):
+    """conservation_of_mass_main.f90:22-109.  Returns dict(dt, dHi_dt, Hi_tplusdt, divQ, AMB, found_negative_vals)."""
+    Hi = f["Hi"]
+    m = C.choice_ice_integration_method
+    if m == "none":
+        return dict(dt=dt, dHi_dt=np.zeros_like(Hi), Hi_tplusdt=Hi.copy(), divQ=None, AMB=np.zeros_like(Hi), found_negative_vals=False)
+    if m == "explicit":
+        r = calc_dHi_dt_explicit(mesh, E, C, f, dt)
+        dt = r["dt"]
+    elif m == "semi-implicit":
+        r = calc_dHi_dt_semiimplicit(mesh, E, C, f, dt, linear_solver)
+    else:
+        raise ValueError(f'unknown choice_ice_integration_method "{m}"!')
+    Hi_tp, AMB, dHi_dt = r["Hi_tplusdt"].copy(), r["AMB"], r["dHi_dt"]
+    neg = Hi_tp < 0.0
+    found = bool((neg & (Hi_tp < -0.1) & (Hi > C.Hi_min)).any())
+    Hi_tp[neg] = 0.0
+    AMB = AMB + (Hi_tp - Hi) / dt - dHi_dt
+    dHi_dt = (Hi_tp - Hi) / dt
+    return dict(dt=dt, dHi_dt=dHi_dt, Hi_tplusdt=Hi_tp, divQ=r["divQ"], AMB=AMB, found_negative_vals=found)
+
+
 # --------------------------------------------------------------------------------------
 # SURVEY.md 8f rank 1 (remaining part): calc_vertical_velocities
 #   src/UFEMISM/ice_dynamics/conservation_of_mass/vertical_velocities.f90:18-210

@@ -430,3 +430,52 @@ def test_gpu_vertical_velocities_match_oracle(oracle):
     noice = (np.asarray(ice.mask_grounded_ice) == 0) & (np.asarray(ice.mask_floating_ice) == 0)
     assert (w[noice] == 0.0).all()
     S.close()
+
+
+# ------------------------------------------------------------------------------------------
+# calc_dHi_dt: the dispatcher the predictor-corrector scheme calls (conservation_of_mass_main.f90:22-109)
+# ------------------------------------------------------------------------------------------
+def test_oracle_calc_dHi_dt_dispatch_and_clipping(oracle):
+    mesh = _mesh(15, 11)
+    E = mesh_types.calc_mesh_edges(mesh)
+    f = _random_case(mesh, E, seed=3)
+    f["SMB"] = f["SMB"] - 400.0 * (np.arange(mesh.nV) % 7 == 0)          # strong melt: the linear solve goes negative there
+    C = config.Config(choice_ice_integration_method="none")
+    r = oracle.calc_dHi_dt(mesh, _edges_dict(E), C, f, 2.0)
+    assert np.array_equal(r["Hi_tplusdt"], f["Hi"]) and not r["dHi_dt"].any()
+    C.choice_ice_integration_method = "semi-implicit"
+    r = oracle.calc_dHi_dt(mesh, _edges_dict(E), C, f, 5.0)
+    raw = oracle.calc_dHi_dt_semiimplicit(mesh, _edges_dict(E), C, f, 5.0)
+    assert (raw["Hi_tplusdt"] < -0.1).any() and r["found_negative_vals"] and (r["Hi_tplusdt"] >= 0.0).all()
+    assert np.allclose(r["AMB"], (r["Hi_tplusdt"] - raw["Hi_tplusdt"]) / 5.0)    # what the clipping added
+    C.choice_ice_integration_method = "bogus"
+    with pytest.raises(ValueError, match="unknown choice_ice_integration_method"):
+        oracle.calc_dHi_dt(mesh, _edges_dict(E), C, f, 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["none", "explicit", "semi-implicit"])
+def test_gpu_calc_dHi_dt_matches_oracle(oracle, method):
+    mesh = _mesh(33, 25)
+    E = mesh_types.calc_mesh_edges(mesh)
+    f = _random_case(mesh, E, seed=9)
+    f["SMB"] = f["SMB"] - 400.0 * (np.arange(mesh.nV) % 7 == 0)
+    C = config.Config(choice_ice_integration_method=method, BC_H_west="infinite", dt_ice_min=0.5)
+    want = oracle.calc_dHi_dt(mesh, _edges_dict(E), C, f, 5.0)
+    S = _solver(mesh, C)
+    S.set_mesh_edges(E)
+    got = S.calc_dHi_dt(f, 5.0)
+    assert got["dt"] == want["dt"]
+    assert bool(got["flags"] & 8) == want["found_negative_vals"]
+    tol = TOL_SOLVE if method == "semi-implicit" else TOL_VAL
+    assert _relmax(got["Hi_tplusdt"], want["Hi_tplusdt"]) < tol
+    assert np.abs(got["dHi_dt"] - want["dHi_dt"]).max() <= tol * max(np.abs(want["dHi_dt"]).max(), 1.0) * 10
+    assert np.abs(got["AMB"] - want["AMB"]).max() <= tol * max(np.abs(want["dHi_dt"]).max(), 1.0) * 10
+    if method != "none":
+        assert (got["Hi_tplusdt"] >= 0.0).all() and _relmax(got["divQ"], want["divQ"]) < TOL_VAL
+    if method == "semi-implicit":
+        assert want["found_negative_vals"]
+    S.C = config.Config(choice_ice_integration_method="implicit")
+    with pytest.raises(diva.UfeError, match="unknown choice_ice_integration_method"):
+        S.calc_dHi_dt(f, 1.0)
+    S.close()

@@ -136,7 +136,7 @@ EXPORTS = [
     "ufe_diva_solve", "ufe_ssa_solve", "ufe_diva_upload", "ufe_diva_solve_resident",
     "ufe_diva_download", "ufe_diva_reset_state", "ufe_calc_secondary_velocities", "ufe_ssa_diva_linearised", "ufe_mesh_get_operator",
     "ufe_mesh_apply_operator", "ufe_get_stiffness_csr", "ufe_bench_spmv", "ufe_get_ownership",
-    "ufe_mesh_set_edges", "ufe_calc_dHi_dt_explicit", "ufe_calc_dHi_dt_semiimplicit", "ufe_get_thickness_csr",
+    "ufe_mesh_set_edges", "ufe_calc_dHi_dt", "ufe_calc_dHi_dt_explicit", "ufe_calc_dHi_dt_semiimplicit", "ufe_get_thickness_csr",
     "ufe_get_thickness_timing", "ufe_calc_vertical_velocities", "ufe_mesh_get_operator_a_a",
 ]
 

@@ -130,3 +130,4 @@ IDEALISED_SLIDING_CODES = {"": 0, "SSA_icestream": 1, "ISMIP-HOM_C": 2, "ISMIP-H
 RHEOLOGY_CODES = {"uniform": 0, "Huybrechts1992": 1}
 ENH_CODES = {"separate": 0, "interp": 1}
 BC_H_CODES = {"infinite": 1, "zero": 2}
+ICE_INTEGRATION_CODES = {"none": 0, "explicit": 1, "semi-implicit": 2}

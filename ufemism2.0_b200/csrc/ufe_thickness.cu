@@ -43,6 +43,7 @@ struct ThicknessState {
   double *vv_dz[3] = {};                 // dzeta_dx_ak, dzeta_dy_ak, dzeta_dz_ak (nV,nz)
   double *w_3D = nullptr;                // (nV,nz)
   int *vv_mask[2] = {};                  // mask_grounded_ice, mask_floating_ice
+  int *found_negative = nullptr;         // calc_dHi_dt: Hi_tplusdt < -0.1 m somewhere
   cudaEvent_t ev[7] = {};                // start | inputs up | M_divQ + divQ | explicit scheme + system | Krylov | finish | outputs down
   float ms[6] = {0, 0, 0, 0, 0, 0};      // device time of those six intervals for the most recent call
 };
@@ -77,6 +78,7 @@ void ufe_thickness_free(ThicknessState *t) {
   for (double *p : t->vv_in) cudaFree(p);
   for (double *p : t->vv_dz) cudaFree(p);
   for (int *p : t->vv_mask) cudaFree(p);
+  cudaFree(t->found_negative);
   cudaFree(t->w_3D); cudaFree(t->aa.ptr); cudaFree(t->aa.ind); cudaFree(t->aa.val[0]); cudaFree(t->aa.val[1]);
   for (cudaEvent_t e : t->ev) if (e) cudaEventDestroy(e);
   if (t->kw_alloc) ufe_krylov_free(t->kw);
@@ -515,19 +517,11 @@ extern "C" int ufe_calc_dHi_dt_explicit(ufe_handle *h, const ufe_thickness_confi
   return thk_download(c, f);
 }
 
-extern "C" int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_config *cfg, ufe_thickness_fields *f,
-                                            double dt, int32_t *n_Axb_its, int32_t *flags) {
-  ThkCtx c;
-  UFE_TRY(thk_check(cfg, f));
-  if (!(dt > 0.0)) { ufe_set_error("dt must be positive"); return UFE_ERR_INVALID; }
-  if (cfg->krylov_method != UFE_KRYLOV_BICGSTAB && cfg->krylov_method != UFE_KRYLOV_GMRES) {
-    ufe_set_error("unknown krylov_method %d", cfg->krylov_method); return UFE_ERR_INVALID;
-  }
-  UFE_TRY(thk_ctx(h, c, true));
+// the semi-implicit scheme on resident inputs (everything but the host copies)
+static int thk_semi_resident(const ThkCtx &c, const ufe_thickness_config *cfg, const ufe_thickness_fields *f, const double *u,
+                             const double *v, double dt, int32_t *n_Axb_its, int32_t *flags) {
   ThicknessState *t = c.t;
   const int nV = t->nV, g = ufe_div_up(nV, 256);
-  const double *u, *v;
-  UFE_TRY(thk_upload(c, f, &u, &v));
   // the explicit solution first (:111-115): M_divQ, divQ and the border values Hi_tplusdt_ex
   UFE_TRY(thk_explicit_resident(c, cfg, f, u, v, dt));
   // apply_ice_thickness_BC_matrix_domain_border applies the explicit border BCs to Hi_tplusdt_ex once more (:224)
@@ -551,7 +545,94 @@ extern "C" int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_c
   k_thk_finish_semi<<<g, 256, 0, c.st>>>(nV, dt, t->S.x, t->Hi, t->Hi_tp, t->dHi_dt, t->AMB);
   UFE_LAUNCH_CHECK();
   UFE_CUDA(cudaEventRecord(t->ev[5], c.st));
+  return UFE_OK;
+}
+
+static int thk_check_semi(const ufe_thickness_config *cfg, double dt) {
+  if (!(dt > 0.0)) { ufe_set_error("dt must be positive"); return UFE_ERR_INVALID; }
+  if (cfg->krylov_method != UFE_KRYLOV_BICGSTAB && cfg->krylov_method != UFE_KRYLOV_GMRES) {
+    ufe_set_error("unknown krylov_method %d", cfg->krylov_method); return UFE_ERR_INVALID;
+  }
+  return UFE_OK;
+}
+
+extern "C" int ufe_calc_dHi_dt_semiimplicit(ufe_handle *h, const ufe_thickness_config *cfg, ufe_thickness_fields *f,
+                                            double dt, int32_t *n_Axb_its, int32_t *flags) {
+  ThkCtx c;
+  UFE_TRY(thk_check(cfg, f));
+  UFE_TRY(thk_check_semi(cfg, dt));
+  UFE_TRY(thk_ctx(h, c, true));
+  const double *u, *v;
+  UFE_TRY(thk_upload(c, f, &u, &v));
+  UFE_TRY(thk_semi_resident(c, cfg, f, u, v, dt, n_Axb_its, flags));
   return thk_download(c, f);
+}
+
+// calc_dHi_dt (conservation_of_mass_main.f90:22-109) after the scheme: clip negative thicknesses, flag values below
+// -0.1 m on ice thicker than Hi_min, AMB = AMB + (Hi_tplusdt - Hi)/dt - dHi_dt, dHi_dt = (Hi_tplusdt - Hi)/dt
+__global__ void k_thk_post(int nV, const double *dt_dev, double dt_host, double Hi_min, const double *__restrict__ Hi,
+                           double *__restrict__ Hi_tp, double *__restrict__ dHi_dt, double *__restrict__ AMB, int *found_negative) {
+  const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vi >= nV) return;
+  const double dt = dt_dev ? *dt_dev : dt_host;
+  double h = Hi_tp[vi];
+  if (h < 0.0) {
+    if (h < -0.1 && Hi[vi] > Hi_min) *found_negative = 1;
+    h = 0.0;
+    Hi_tp[vi] = h;
+  }
+  const double d = (h - Hi[vi]) / dt;
+  AMB[vi] = AMB[vi] + d - dHi_dt[vi];
+  dHi_dt[vi] = d;
+}
+
+extern "C" int ufe_calc_dHi_dt(ufe_handle *h, const ufe_thickness_config *cfg, int32_t choice_ice_integration_method,
+                               ufe_thickness_fields *f, double *dt, int32_t *n_Axb_its, int32_t *flags) {
+  ThkCtx c;
+  UFE_TRY(thk_check(cfg, f));
+  if (!dt) { ufe_set_error("null argument"); return UFE_ERR_INVALID; }
+  if (choice_ice_integration_method < UFE_THK_NONE || choice_ice_integration_method > UFE_THK_SEMI_IMPLICIT) {
+    ufe_set_error("unknown choice_ice_integration_method code %d!", choice_ice_integration_method);   // :62
+    return UFE_ERR_INVALID;
+  }
+  if (choice_ice_integration_method == UFE_THK_SEMI_IMPLICIT) UFE_TRY(thk_check_semi(cfg, *dt));
+  else if (!(*dt > 0.0)) { ufe_set_error("dt must be positive"); return UFE_ERR_INVALID; }
+  UFE_TRY(thk_ctx(h, c, true));
+  ThicknessState *t = c.t;
+  const int nV = t->nV, g = ufe_div_up(nV, 256);
+  if (n_Axb_its) *n_Axb_its = 0;
+  if (flags) *flags = 0;
+  const double *u, *v;
+  UFE_TRY(thk_upload(c, f, &u, &v));
+  if (choice_ice_integration_method == UFE_THK_NONE) {          // :64-68: unchanging geometry
+    const size_t nb = sizeof(double) * (size_t)nV;
+    UFE_CUDA(cudaMemcpyAsync(t->Hi_tp, t->Hi, nb, cudaMemcpyDeviceToDevice, c.st));
+    UFE_CUDA(cudaMemsetAsync(t->dHi_dt, 0, nb, c.st));
+    UFE_CUDA(cudaMemsetAsync(t->AMB, 0, nb, c.st));
+    for (int i = 2; i <= 5; i++) UFE_CUDA(cudaEventRecord(t->ev[i], c.st));
+    ufe_thickness_fields g2 = *f;
+    g2.divQ = nullptr;                                          // divQ is not computed on this branch
+    return thk_download(c, &g2);
+  }
+  if (!t->found_negative) UFE_TRY(talloc(&t->found_negative, 1));
+  UFE_CUDA(cudaMemsetAsync(t->found_negative, 0, sizeof(int), c.st));
+  const bool semi = choice_ice_integration_method == UFE_THK_SEMI_IMPLICIT;
+  if (semi) {
+    UFE_TRY(thk_semi_resident(c, cfg, f, u, v, *dt, n_Axb_its, flags));
+  } else {
+    UFE_TRY(thk_explicit_resident(c, cfg, f, u, v, *dt));
+    for (int i = 3; i <= 4; i++) UFE_CUDA(cudaEventRecord(t->ev[i], c.st));
+  }
+  k_thk_post<<<g, 256, 0, c.st>>>(nV, semi ? nullptr : t->dt_dev, *dt, cfg->Hi_min, t->Hi, t->Hi_tp, t->dHi_dt, t->AMB,
+                                  t->found_negative);
+  UFE_LAUNCH_CHECK();
+  UFE_CUDA(cudaEventRecord(t->ev[5], c.st));
+  int neg = 0;
+  if (!semi) UFE_CUDA(cudaMemcpyAsync(dt, t->dt_dev, sizeof(double), cudaMemcpyDeviceToHost, c.st));
+  UFE_CUDA(cudaMemcpyAsync(&neg, t->found_negative, sizeof(int), cudaMemcpyDeviceToHost, c.st));
+  UFE_TRY(thk_download(c, f));
+  if (neg && flags) *flags |= UFE_FLAG_NEGATIVE_HI;             // warning('encountered negative values for Hi_tplusdt ...') :91
+  return UFE_OK;
 }
 
 extern "C" int ufe_get_thickness_csr(ufe_handle *h, int32_t which, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind,

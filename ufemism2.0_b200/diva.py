@@ -23,7 +23,7 @@ import numpy as np
 
 from . import capi
 from .capi import UfeError, check, vp
-from .config import (BC_CODES, BC_H_CODES, ENH_CODES, IDEALISED_SLIDING_CODES, RHEOLOGY_CODES, SLIDING_CODES, Config)
+from .config import (BC_CODES, BC_H_CODES, ENH_CODES, ICE_INTEGRATION_CODES, IDEALISED_SLIDING_CODES, RHEOLOGY_CODES, SLIDING_CODES, Config)
 from .mesh_types import Mesh
 
 PICARD_MAXIT, KRYLOV_MAXIT, KRYLOV_DIVERGED = 1, 2, 4
@@ -350,6 +350,16 @@ class DIVASolver:
             out[n] = np.zeros(self.mesh.nV)
             setattr(f, n, vp(out[n]))
         return cfg, f, keep, out
+
+    def calc_dHi_dt(self, fields: dict, dt: float) -> dict:
+        """calc_dHi_dt (conservation_of_mass_main.f90:22): dispatch on C%choice_ice_integration_method, clip negative
+        thicknesses, final dHi_dt and AMB.  Returns the out-arguments + ``dt``, ``n_Axb_its``, ``flags``."""
+        cfg, f, keep, out = self._thickness_structs(fields)
+        method = _code(ICE_INTEGRATION_CODES, self.C.choice_ice_integration_method, "choice_ice_integration_method")
+        d, its, fl = ct.c_double(dt), ct.c_int32(), ct.c_int32()
+        check(capi.lib().ufe_calc_dHi_dt(self._h, ct.byref(cfg), method, ct.byref(f), ct.byref(d), ct.byref(its), ct.byref(fl)))
+        out["dt"], out["n_Axb_its"], out["flags"] = d.value, its.value, fl.value
+        return out
 
     def calc_dHi_dt_explicit(self, fields: dict, dt: float) -> dict:
         """calc_dHi_dt_explicit(mesh, Hi, Hb, SL, u_vav_b, v_vav_b, SMB, BMB, LMB, AMB, fraction_margin, mask_noice,

@@ -206,6 +206,17 @@ module diva_gpu_bindings
       type(ufe_mesh_edges), intent(in) :: edges
     end function ufe_mesh_set_edges
 
+    ! replaces calc_dHi_dt (conservation_of_mass_main.f90:22-109); method: 0 'none', 1 'explicit', 2 'semi-implicit'
+    integer(c_int) function ufe_calc_dHi_dt( handle, cfg, method, fields, dt, n_Axb_its, flags) bind(C, name='ufe_calc_dHi_dt')
+      import :: c_int, c_int32_t, c_ptr, c_double, ufe_thickness_config, ufe_thickness_fields
+      type(c_ptr),                value         :: handle
+      type(ufe_thickness_config), intent(in)    :: cfg
+      integer(c_int32_t),         value         :: method
+      type(ufe_thickness_fields), intent(inout) :: fields
+      real(c_double),             intent(inout) :: dt
+      integer(c_int32_t),         intent(out)   :: n_Axb_its, flags
+    end function ufe_calc_dHi_dt
+
     ! replaces calc_dHi_dt_explicit (conservation_of_mass_explicit.f90:23-138)
     integer(c_int) function ufe_calc_dHi_dt_explicit( handle, cfg, fields, dt) bind(C, name='ufe_calc_dHi_dt_explicit')
       import :: c_int, c_ptr, c_double, ufe_thickness_config, ufe_thickness_fields
