@@ -222,18 +222,14 @@ k_vertex_diva(int v0, int nv, int nV, int nTri, int nz_rt, ClosureParams P, DevF
   F.beta_eff_a[vi] = (P.sliding_law == UFE_SLID_NO_SLIDING) ? 1.0 / F2_surf : beta / (1.0 + beta * F2_surf);
 }
 
-// DIVA, b-grid: one thread per owned triangle
-template <int NZ>
-__global__ void __launch_bounds__(128)
-k_triangle_diva(int t0, int nt, int nV, int nTri, int nz_rt, ClosureParams P, DevFamilyView ab,
-                const double *__restrict__ fraction_gr_b, DivaFields F) {
-  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tl >= nt) return;
-  const int ti = t0 + tl;
-  const int nz = NZ > 0 ? NZ : nz_rt;
-  constexpr int NZA = NZ > 0 ? NZ : UFE_NZ_MAX;
+// rows with more than three entries (singular three-point fit -> widened neighbourhood): accumulate per layer.
+// Rare, so the per-layer accumulators live in local memory (rolled loops) and do not set the kernel's register count.
+template <int NZA>
+__device__ __noinline__ void k_triangle_diva_general(int tl, int ti, int nV, int nTri, int nz, const ClosureParams &P,
+                                                     const DevFamilyView &ab, const double *__restrict__ fraction_gr_b,
+                                                     const DivaFields &F) {
   double eb[NZA], f1[NZA], f2[NZA];
-#pragma unroll
+#pragma unroll 1
   for (int l = 0; l < NZA; l++) { eb[l] = 0.0; f1[l] = 0.0; f2[l] = 0.0; }
   double N_b = 0.0, dNx = 0.0, dNy = 0.0, beta_b = 0.0, beta_eff_b = 0.0;
   for (int k = ab.ptr[tl] - 1; k < ab.ptr[tl + 1] - 1; k++) {
@@ -243,7 +239,7 @@ k_triangle_diva(int t0, int nt, int nV, int nTri, int nz_rt, ClosureParams P, De
     N_b += wm * Na; dNx += wx * Na; dNy += wy * Na;
     beta_b += wm * F.beta_a[vj];
     beta_eff_b += wm * F.beta_eff_a[vj];
-#pragma unroll
+#pragma unroll 1
     for (int l = 0; l < NZA; l++) {
       if (l < nz) {
         eb[l] += wm * F.eta_3D_a[(size_t)l * nV + vj];
@@ -255,7 +251,7 @@ k_triangle_diva(int t0, int nt, int nV, int nTri, int nz_rt, ClosureParams P, De
   if (P.do_GL_subgrid_friction) beta_eff_b = beta_eff_b * pow(fraction_gr_b[ti], P.subgrid_exponent);
   F.N_b[ti] = N_b; F.dN_dx_b[ti] = dNx; F.dN_dy_b[ti] = dNy;
   F.beta_b[ti] = beta_b; F.beta_eff_b[ti] = beta_eff_b;
-#pragma unroll
+#pragma unroll 1
   for (int l = 0; l < NZA; l++) {
     if (l < nz) {
       F.eta_3D_b[(size_t)l * nTri + ti] = eb[l];
@@ -263,6 +259,56 @@ k_triangle_diva(int t0, int nt, int nV, int nTri, int nz_rt, ClosureParams P, De
       F.F2_3D_b[(size_t)l * nTri + ti] = f2[l];
     }
   }
+}
+
+
+// DIVA, b-grid: one thread per owned triangle
+template <int NZ>
+__global__ void __launch_bounds__(128)
+k_triangle_diva(int t0, int nt, int nV, int nTri, int nz_rt, ClosureParams P, DevFamilyView ab,
+                const double *__restrict__ fraction_gr_b, DivaFields F) {
+  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tl >= nt) return;
+  const int ti = t0 + tl;
+  const int nz = NZ > 0 ? NZ : nz_rt;
+  constexpr int NZA = NZ > 0 ? NZ : UFE_NZ_MAX;
+  const int k0 = ab.ptr[tl] - 1, k1 = ab.ptr[tl + 1] - 1;
+  if (k1 - k0 == 3) {
+    // the usual row (the triangle's own three vertices): weights and columns stay in registers and the layer loop
+    // is the outer one -- nine independent gathers per layer in flight, no per-layer accumulator arrays, so the
+    // kernel runs at twice the occupancy.  Same summation order as the general path: ((0 + w0 f0) + w1 f1) + w2 f2.
+    const int v0 = ab.ind[k0] - 1, v1 = ab.ind[k0 + 1] - 1, v2 = ab.ind[k0 + 2] - 1;
+    const double w0 = ab.v0[k0], w1 = ab.v0[k0 + 1], w2 = ab.v0[k0 + 2];
+    {
+      const double x0 = ab.v1[k0], x1 = ab.v1[k0 + 1], x2 = ab.v1[k0 + 2];
+      const double y0 = ab.v2[k0], y1 = ab.v2[k0 + 1], y2 = ab.v2[k0 + 2];
+      const double N0 = F.N_a[v0], N1 = F.N_a[v1], N2 = F.N_a[v2];
+      double N_b = 0.0, dNx = 0.0, dNy = 0.0, beta_b = 0.0, beta_eff_b = 0.0;
+      N_b += w0 * N0; N_b += w1 * N1; N_b += w2 * N2;
+      dNx += x0 * N0; dNx += x1 * N1; dNx += x2 * N2;
+      dNy += y0 * N0; dNy += y1 * N1; dNy += y2 * N2;
+      beta_b += w0 * F.beta_a[v0]; beta_b += w1 * F.beta_a[v1]; beta_b += w2 * F.beta_a[v2];
+      beta_eff_b += w0 * F.beta_eff_a[v0]; beta_eff_b += w1 * F.beta_eff_a[v1]; beta_eff_b += w2 * F.beta_eff_a[v2];
+      if (P.do_GL_subgrid_friction) beta_eff_b = beta_eff_b * pow(fraction_gr_b[ti], P.subgrid_exponent);
+      F.N_b[ti] = N_b; F.dN_dx_b[ti] = dNx; F.dN_dy_b[ti] = dNy;
+      F.beta_b[ti] = beta_b; F.beta_eff_b[ti] = beta_eff_b;
+    }
+#pragma unroll 4
+    for (int l = 0; l < nz; l++) {
+      const size_t o = (size_t)l * nV;
+      const double e0 = F.eta_3D_a[o + v0], e1 = F.eta_3D_a[o + v1], e2 = F.eta_3D_a[o + v2];
+      const double a0 = F.F1_3D_a[o + v0], a1 = F.F1_3D_a[o + v1], a2 = F.F1_3D_a[o + v2];
+      const double b0 = F.F2_3D_a[o + v0], b1 = F.F2_3D_a[o + v1], b2 = F.F2_3D_a[o + v2];
+      double e = 0.0, a = 0.0, b = 0.0;
+      e += w0 * e0; e += w1 * e1; e += w2 * e2;
+      a += w0 * a0; a += w1 * a1; a += w2 * a2;
+      b += w0 * b0; b += w1 * b1; b += w2 * b2;
+      const size_t ob = (size_t)l * nTri + ti;
+      F.eta_3D_b[ob] = e; F.F1_3D_b[ob] = a; F.F2_3D_b[ob] = b;
+    }
+    return;
+  }
+  k_triangle_diva_general<NZA>(tl, ti, nV, nTri, nz, P, ab, fraction_gr_b, F);
 }
 
 // ---------------------------------------------------------------------------------
