@@ -551,3 +551,27 @@ def test_error_paths_on_device():
         m2.nz = 40
         m2.zeta = np.linspace(0.0, 1.0, 40)
         diva.initialise_DIVA_solver(m2, C)
+
+
+def test_remap_DIVA_solver_lifecycle(oracle):
+    """remap_DIVA_solver (DIVA_main.f90:264-373): b -> a (old mesh), a(old) -> a(new) by the caller's remapping, a -> b
+    (new mesh); checked against the same chain of oracle SpMVs, and the remapped solver then solves."""
+    from scipy.spatial import cKDTree
+    mesh_old, C, ice_old = experiments.MISMIPplus(16e3)
+    mesh_new, _, ice_new = experiments.MISMIPplus(10e3)
+    S = diva.initialise_DIVA_solver(mesh_old, C)
+    S.solve_DIVA(ice_old)
+    u_old, eta_old = S.u_vav_b.copy(), S.eta_3D_b.copy()
+    nearest = cKDTree(mesh_old.V).query(mesh_new.V)[1]           # stand-in for the conservative mesh-to-mesh remapping
+    S2 = diva.remap_DIVA_solver(S, mesh_new, lambda d: d[nearest])
+    mesh_old.ops = oracle.calc_all_matrix_operators_mesh(mesh_old)
+    mesh_new.ops = oracle.calc_all_matrix_operators_mesh(mesh_new)
+    want_u = oracle.spmv(mesh_new.ops["M_map_a_b"], oracle.spmv(mesh_old.ops["M_map_b_a"], u_old)[nearest])
+    want_eta = oracle.spmv_2D(mesh_new.ops["M_map_a_b"], np.asfortranarray(oracle.spmv_2D(mesh_old.ops["M_map_b_a"], eta_old)[nearest]))
+    assert S2.u_vav_b.shape == (mesh_new.nTri,) and rel(S2.u_vav_b, want_u)[1] < 1e-12
+    assert rel(S2.eta_3D_b, want_eta)[1] < 1e-12
+    assert not S2.u_base_b.any()                                  # everything else is reallocated
+    info = S2.solve_DIVA(ice_new)
+    assert info.n_visc_its > 0 and np.isfinite(S2.u_vav_b).all()
+    with pytest.raises(UfeError, match="remapped"):
+        diva.remap_DIVA_solver(S2, mesh_old, lambda d: d)

@@ -4,6 +4,7 @@ Same names, argument meaning and error behaviour as the Fortran procedures, on t
 the C ABI (include/ufe_diva.h):
 
   initialise_DIVA_solver / solve_DIVA / solve_SSA     DIVA_main.f90:37,88 ; SSA_main.f90:87
+  remap_DIVA_solver                                   DIVA_main.f90:264
   solve_SSA_DIVA_linearised                           solve_linearised_SSA_DIVA.f90:23
   solve_matrix_equation_CSR_PETSc                     src/UPSY/basic/petsc_basic.f90:32
   multiply_CSR_matrix_with_vector_1D/_2D              CSR_matrix_vector_multiplication.f90:198,336
@@ -495,6 +496,29 @@ class DIVASolver:
         ms, by = ct.c_double(), ct.c_double()
         check(capi.lib().ufe_bench_spmv(self._h, reps, int(flush_l2), ct.byref(ms), ct.byref(by)))
         return ms.value, by.value
+
+
+def remap_DIVA_solver(solver_old: DIVASolver, mesh_new: Mesh, map_from_mesh_to_mesh, comm=None) -> DIVASolver:
+    """remap_DIVA_solver(mesh_old, mesh_new, DIVA) (DIVA_main.f90:264-373): the seven fields that are re-used by the
+    next solve (u_vav_b, v_vav_b, tau_bx_b, tau_by_b, eta_3D_b, u_3D_b, v_3D_b) go b -> a on the old mesh (device),
+    a(old) -> a(new) through ``map_from_mesh_to_mesh(d_a_old) -> d_a_new`` (the reference's
+    map_from_mesh_to_mesh_with_reallocation_2D/3D, '2nd_order_conservative': the caller's remapping subsystem, out of
+    scope here), and a -> b on the new mesh (device); everything else is reallocated (zero).  Returns the solver for
+    ``mesh_new``; the old one is closed."""
+    names2, names3 = ("u_vav_b", "v_vav_b", "tau_bx_b", "tau_by_b"), ("eta_3D_b", "u_3D_b", "v_3D_b")
+    on_a = {n: solver_old.map_b_a_2D(getattr(solver_old, n)) for n in names2}
+    on_a.update({n: solver_old.map_b_a_3D(getattr(solver_old, n)) for n in names3})
+    C = solver_old.C
+    solver_old.close()
+    new = DIVASolver(mesh_new, C, comm)
+    for n, d in on_a.items():
+        d_new = np.asfortranarray(map_from_mesh_to_mesh(d), dtype=np.float64)
+        want = (mesh_new.nV,) if n in names2 else (mesh_new.nV, mesh_new.nz)
+        if d_new.shape != want:
+            raise UfeError(1, f"remap_DIVA_solver: remapped {n} has shape {d_new.shape}, expected {want}")
+        out = new.map_a_b_2D(d_new) if n in names2 else new.map_a_b_3D(d_new)
+        getattr(new, n)[...] = out
+    return new
 
 
 def initialise_DIVA_solver(mesh: Mesh, C: Config, comm=None, operators=None) -> DIVASolver:
