@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import numpy as np
 import torch, torch.distributed as dist
 import ufe_pkg; ufe_pkg.load()
-from ufemism2_0_b200 import experiments, diva, capi
+from ufemism2_0_b200 import experiments, diva, capi, mesh_types
 
 rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(local)
@@ -60,6 +60,27 @@ for name, (mesh, C, ice), pc_name, meth in cases:
         print(f'{name} [{meth}+{pc_name}]: ranks {world} comm {"peer" if info.reserved else "nccl"} Picard {info.n_visc_its} (oracle {nv}) '
               f'Krylov {info.n_Axb_its} flags {info.flags} u {ru[1]:.2e} v {rv[1]:.2e} u3D {r3:.2e} secondary {rs:.1e} wall {wall:.3f}s '
               f'{"OK" if good else "MISMATCH"}', flush=True)
+    thk = None
+    if name == 'MISMIP+ 8km':      # the thickness update that follows the solve: replicated on every rank
+        E = mesh_types.calc_mesh_edges(mesh)
+        S.set_mesh_edges(E)
+        n = mesh.nV
+        f = dict(Hi=ice.Hi, Hb=ice.Hb, SL=ice.SL, SMB=np.full(n, 0.3), BMB=np.zeros(n), LMB=np.zeros(n), fraction_margin=np.ones(n),
+                 mask_noice=np.zeros(n, dtype=np.int32), dHi_dt_target=np.zeros(n))
+        S.solve_DIVA_resident()    # leaves the velocities distributed: the thickness call has to gather them itself
+        thk = S.calc_dHi_dt(f, 1.0)
+        t_all = [torch.zeros(n, dtype=torch.float64, device='cuda') for _ in range(world)]
+        dist.all_gather(t_all, torch.from_numpy(thk['Hi_tplusdt']).cuda())
+        same = all(torch.equal(t_all[0], t) for t in t_all)
+        S.download()
+        if rank == 0:
+            Ed = {k: getattr(E, k) for k in ('nE', 'VE', 'ETri', 'A', 'Cw', 'D_x', 'D_y', 'D')}
+            want = O.calc_dHi_dt(mesh, Ed, C, dict(f, u_vav_b=S.u_vav_b, v_vav_b=S.v_vav_b), 1.0)
+            rt = np.abs(thk['Hi_tplusdt'] - want['Hi_tplusdt']).max() / np.abs(want['Hi_tplusdt']).max()
+            good_t = same and rt < 1e-6
+            ok &= good_t
+            print(f'{name} thickness update (calc_dHi_dt, replicated on {world} ranks): identical on all ranks {same}, Hi_tplusdt vs oracle {rt:.2e} '
+                  f'Krylov {thk["n_Axb_its"]} {"OK" if good_t else "MISMATCH"}', flush=True)
     S.close()
 dist.barrier()
 if rank == 0:

@@ -115,6 +115,8 @@ struct ufe_handle {
   double *sym = nullptr;                       // symmetric peer buffer (several ranks): owns S.x, kw.pg, kw.sg
   SecondaryFields sec;                         // calc_secondary_velocities outputs (allocated on first use)
   bool sec_alloc = false, sec_current = false;
+  bool outputs_gathered = false;               // several ranks: the solution fields are full-length on every rank
+  int last_is_diva = 1;
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
   int pc_used = -1;                            // resolved preconditioner for the cached pattern (-1 = undecided)
   int pc_age = -1, pc_last_its = 0;            // bjacobi_lu reuse: solves since the last factorisation (-1 = never), its of the last solve
@@ -747,6 +749,8 @@ static int picard_resident(ufe_handle *h, int is_diva, ufe_solve_info *info) {
   memset(info, 0, sizeof *info);
   const int64_t launches0 = g_launch_count;
   h->sec_current = false;
+  h->outputs_gathered = false;
+  h->last_is_diva = is_diva;
   cudaEventRecord(h->ev[0], h->st);
   if (!h->grounded_ice_exists) {           // DIVA_main.f90:123-134
     const size_t nT = nTri;
@@ -843,7 +847,7 @@ static int picard_resident(ufe_handle *h, int is_diva, ufe_solve_info *info) {
 // all ranks end up with full-length results (the reference keeps distributed slices; the
 // C ABI exchanges full arrays, so gather the owned slices of the outputs at the end)
 static int gather_outputs(ufe_handle *h, int is_diva) {
-  if (h->comm.nranks <= 1) return UFE_OK;
+  if (h->comm.nranks <= 1 || h->outputs_gathered) return UFE_OK;
   const int nTri = h->dm.nTri, nV = h->dm.nV, nz = h->dm.nz;
   HaloPlan pb = h->plan_b_for_b, pa = h->plan_a_for_b;
   for (int q = 0; q < pb.nranks; q++) { pb.need_lo[q] = 0; pb.need_hi[q] = nTri; pa.need_lo[q] = 0; pa.need_hi[q] = nV; }
@@ -858,8 +862,11 @@ static int gather_outputs(ufe_handle *h, int is_diva) {
     double *a3[] = {F.du_dz_3D_a, F.dv_dz_3D_a, F.eta_3D_a};
     for (double *p : a3) UFE_TRY(ufe_halo_exchange(h->st, h->comm, pa, p, nV, nz, 1));
   }
+  h->outputs_gathered = true;
   return UFE_OK;
 }
+// several ranks: make the resident solution fields full-length on this rank (collective)
+int ufe_handle_gather_outputs(ufe_handle *h) { return gather_outputs(h, h->last_is_diva); }
 
 extern "C" int ufe_diva_upload(ufe_handle *h, const ufe_ice_inputs *ice, const ufe_diva_state *state) {
   UFE_CUDA(cudaSetDevice(h->device));

@@ -56,6 +56,7 @@ struct ThkHandleView {
   ThicknessState **slot;
 };
 int ufe_handle_thickness_view(ufe_handle *h, ThkHandleView *v);
+int ufe_handle_gather_outputs(ufe_handle *h);
 int ufe_build_operators_a_a(cudaStream_t st, const DevMesh &dm, DevFamily &F);
 
 template <typename T>
@@ -333,11 +334,11 @@ static int thk_ctx(ufe_handle *h, ThkCtx &c, bool need_state) {
   const int nranks = c.hv.nranks, device = c.hv.device;
   ThicknessState **slot = c.hv.slot;
   c.dm = c.hv.dm; c.st = c.hv.st; c.u_res = c.hv.u_vav_b; c.v_res = c.hv.v_vav_b;
-  if (nranks != 1) {
-    ufe_set_error("the ice-thickness path runs on a single-rank handle (nranks = %d)", nranks);
-    return UFE_ERR_INVALID;
-  }
   UFE_CUDA(cudaSetDevice(device));
+  // Several ranks: this sub-path is replicated, not sharded -- every rank holds the full-length inputs (the C ABI
+  // exchanges global arrays) and computes the whole update, bit-identically; the only collective is the gather that
+  // makes the resident velocities of the last solve full-length on every rank.
+  if (nranks > 1) UFE_TRY(ufe_handle_gather_outputs(h));
   c.h = h;
   c.t = *slot;
   if (need_state && !c.t) { ufe_set_error("ufe_mesh_set_edges has not been called on this handle"); return UFE_ERR_INVALID; }
