@@ -16,6 +16,9 @@ the named mesh.  Legs of the b200 arm:
           buffers - H2D of all ice inputs + state and D2H of all results inside the timed region;
   roofline : the Krylov MatMult kernel (k_kspmv) on the resident stiffness matrix, CUDA events on
           the launching stream, L2 flushed between launches (ufe_bench_spmv);
+  thickness_update(_large_mesh) : SURVEY.md 8f rank 2, reported beside the metric, not part of it: one
+          ``calc_dHi_dt_semiimplicit`` call on the velocities the solve left on the device (host buffers in and
+          out), its device-time split and the achieved GB/s of k_thk_divq (N = 1 only);
   cpu_baseline : the oracle's restatement of the reference CPU path (GMRES(30) + block-Jacobi
           ILU(0), per-iteration re-assembly) on a bounded sample, rank 0, N = 1 only.
 

@@ -67,7 +67,9 @@ template <typename T>
 static int dalloc(T **p, size_t n) {
   *p = nullptr;
   UFE_CUDA(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
+  // the handle's stream is non-blocking: a null-stream memset is not ordered before work on it, so wait here
   UFE_CUDA(cudaMemset(*p, 0, sizeof(T) * (n ? n : 1)));
+  UFE_CUDA(cudaStreamSynchronize(0));
   return UFE_OK;
 }
 template <typename T>
@@ -422,6 +424,7 @@ static int peer_setup(ufe_handle *h) {
   const size_t total = (size_t)pc.off_flags + 64;
   UFE_CUDA(cudaMalloc(&h->sym, total * sizeof(double)));
   UFE_CUDA(cudaMemset(h->sym, 0, total * sizeof(double)));
+  UFE_CUDA(cudaStreamSynchronize(0));
   h->S.x = h->sym + pc.off_x;
   for (int q = 0; q <= P; q++) {
     int i1, i2;

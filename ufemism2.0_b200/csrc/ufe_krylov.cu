@@ -694,6 +694,9 @@ int ufe_krylov_alloc(KrylovWork &kw, int N, int n_loc, bool gmres, double *ext_p
   UFE_CUDA(cudaMemset(kw.sc, 0, sizeof(KrylovScalars)));
   UFE_CUDA(cudaMalloc(&kw.gm, sizeof(double) * GM_SIZE));
   UFE_CUDA(cudaMemset(kw.gm, 0, sizeof(double) * GM_SIZE));
+  // callers run on non-blocking streams: the null-stream memsets above are not ordered before their kernels
+  // (a stale reduction counter turns every dot product into garbage), so wait for them here
+  UFE_CUDA(cudaStreamSynchronize(0));
   UFE_CUDA(cudaMallocHost(&kw.sc_host, sizeof(KrylovScalars)));
   return UFE_OK;
 }

@@ -64,6 +64,7 @@ static int talloc(T **p, size_t n) {
   *p = nullptr;
   UFE_CUDA(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
   UFE_CUDA(cudaMemset(*p, 0, sizeof(T) * (n ? n : 1)));
+  UFE_CUDA(cudaStreamSynchronize(0));   // non-blocking handle stream: order the null-stream memset before any use
   return UFE_OK;
 }
 
