@@ -40,8 +40,11 @@ def nd_order(xy, adj, leaf=200):
     return np.array(order)
 
 
-for nV in [int(float(a)) for a in sys.argv[1:]] or [10_000, 40_000, 160_000]:
-    mesh, C, ice = experiments.antarctic(nV)
+for arg in sys.argv[1:] or ["10000", "40000", "mismipplus:2000"]:
+    if arg.startswith("mismipplus:"):
+        mesh, C, ice = experiments.MISMIPplus(float(arg.split(":")[1]))
+    else:
+        mesh, C, ice = experiments.antarctic(int(float(arg)))
     mesh.ops = O.calc_all_matrix_operators_mesh(mesh)
     nT = mesh.nTri
     z = np.zeros(nT)
@@ -56,7 +59,10 @@ for nV in [int(float(a)) for a in sys.argv[1:]] or [10_000, 40_000, 160_000]:
     t = time.time(); p = nd_order(mesh.TriGC, G); t_ord = time.time() - t
     perm = np.stack([2 * p, 2 * p + 1], axis=1).ravel()
     res = {}
-    for name, P in (("nested dissection", perm), ("x-sorted (banded)", np.arange(2 * nT))):
+    orderings = [("nested dissection", perm)]
+    if 2 * nT <= 70_000:
+        orderings.append(("x-sorted (banded)", np.arange(2 * nT)))
+    for name, P in orderings:
         Mp = M[P][:, P].tocsc()
         t = time.time()
         lu = spla.splu(Mp, permc_spec="NATURAL", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
