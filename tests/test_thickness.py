@@ -479,3 +479,46 @@ def test_gpu_calc_dHi_dt_matches_oracle(oracle, method):
     with pytest.raises(diva.UfeError, match="unknown choice_ice_integration_method"):
         S.calc_dHi_dt(f, 1.0)
     S.close()
+
+
+@pytest.mark.gpu
+def test_gpu_flux_limited_timestep(oracle):
+    """calc_flux_limited_timestep actually limiting dt: one thinning vertex with 1e-9 m of ice => dt_lim = Hi / 1e-9 = 1 yr
+    (the reference's formula as written), which the device finds with its block-min + atomicMin reduction."""
+    mesh = synthetic.lattice_mesh(-400e3, 400e3, -300e3, 300e3, 25, 21, jitter=0.2, delaunay=True, nz=8)
+    E = mesh_types.calc_mesh_edges(mesh)
+    f = _random_case(mesh, E, seed=21, with_prescribed=False)
+    k = int(np.nonzero((mesh.VBI == 0) & (f["mask_noice"] == 0))[0][7])
+    f["Hi"][k], f["SMB"][k], f["fraction_margin"][k] = 1e-9, -50.0, 1.0
+    C = config.Config(dt_ice_min=0.5, dt_ice_max=10.0, nz=8)
+    want = oracle.calc_dHi_dt_explicit(mesh, _edges_dict(E), C, f, 2.0)
+    assert want["dt"] == 1.0
+    S = _solver(mesh, C)
+    S.set_mesh_edges(E)
+    got = S.calc_dHi_dt_explicit(f, 2.0)
+    assert got["dt"] == 1.0 and _relmax(got["Hi_tplusdt"], want["Hi_tplusdt"]) < TOL_VAL
+    S.close()
+
+
+@pytest.mark.gpu
+def test_gpu_vertical_velocities_nz8(oracle):
+    mesh, C, ice = experiments.ISMIP_HOM("C", 80e3, 17)
+    mesh8 = synthetic.lattice_mesh(mesh.xmin, mesh.xmax, mesh.ymin, mesh.ymax, 17, 17, jitter=0.2, nz=8)
+    ice8 = synthetic.geometry_ISMIP_HOM_C(mesh8, 80e3)
+    C.nz = 8
+    C.visc_it_nit = 6
+    S = diva.initialise_DIVA_solver(mesh8, C)
+    S.solve_DIVA(ice8)
+    E = mesh_types.calc_mesh_edges(mesh8)
+    S.set_mesh_edges(E)
+    sec = S.calc_secondary_velocities()
+    nV, nz = mesh8.nV, 8
+    zx, zy, zz = _zeta_gradients(oracle, mesh8, ice8.Hi, ice8.Hs)
+    rng = np.random.default_rng(5)
+    vin = dict(Hi=ice8.Hi, Hib=ice8.Hib, dHb_dt=np.zeros(nV), dHi_dt=0.1 * rng.standard_normal(nV), BMB=-rng.random(nV),
+               mask_grounded_ice=ice8.mask_grounded_ice, mask_floating_ice=ice8.mask_floating_ice,
+               dzeta_dx_ak=zx, dzeta_dy_ak=zy, dzeta_dz_ak=zz)
+    w = S.calc_vertical_velocities(vin)
+    want = oracle.calc_vertical_velocities(mesh8, _edges_dict(E), vin, S.u_3D_b, S.v_3D_b, sec["u_3D"], sec["v_3D"], vin["BMB"])
+    assert w.shape == (nV, 8) and np.abs(want).max() > 0.0 and _relmax(w, want) < 1e-10
+    S.close()
