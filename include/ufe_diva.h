@@ -134,9 +134,13 @@ typedef struct ufe_config {
   int32_t krylov_guess_nonzero; /* 0 = KSP default (x0 = 0, petsc_basic.f90:99-128) */
   int32_t krylov_pc_lag;        /* UFE_PC_BJACOBI_LU: reuse a factorisation across Picard iterations until a solve
                                  * needs more than this many Krylov iterations; 0 = factorise every iteration */
-  int32_t krylov_pc_strip_only; /* UFE_PC_BJACOBI_LU with several ranks: 0 = replicate the exact factorisation on every
-                                 * rank when the whole system's dense blocks fit (small systems), else one strip block
-                                 * per rank; 1 = always one strip block per rank (PETSc bjacobi structure) */
+  int32_t krylov_pc_strip_only; /* several ranks.  0: systems of at most 131072 unknowns (env UFE_REDUNDANT_MAX_UNKNOWNS) are
+                                 * not partitioned at all -- every rank solves the whole system redundantly and
+                                 * bit-identically without communication (every kernel is launch-latency-bound at that
+                                 * size); larger ones are row-partitioned, and UFE_PC_BJACOBI_LU replicates the exact
+                                 * factorisation on every rank when the whole system's dense blocks fit, else one strip
+                                 * block per rank.  1: always partition the rows, one strip block per rank (PETSc's
+                                 * bjacobi structure).  Read by ufe_diva_create. */
 } ufe_config;
 
 /* ---- inputs read from type_ice_model / type_bed_roughness_model ------------------
@@ -193,7 +197,7 @@ typedef struct ufe_solve_info {
   double ms_total, ms_closures, ms_assembly, ms_krylov, ms_h2d, ms_d2h;
   int64_t gpu_launches;            /* kernels launched by this library during the call */
   int32_t krylov_pc_used;          /* UFE_PC_* actually applied (resolves UFE_PC_AUTO) */
-  int32_t reserved;
+  int32_t reserved;                /* several ranks: 0 NCCL, 1 peer memory inside the Krylov loop, 2 redundant (not partitioned) */
 } ufe_solve_info;
 
 /* multi-GPU communicator description: one process per GPU, NCCL underneath.

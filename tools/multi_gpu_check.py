@@ -25,6 +25,8 @@ def rel(a, b, ref):
     return np.linalg.norm(a - b) / np.linalg.norm(ref), np.abs(a - b).max() / np.abs(ref).max()
 
 ok = True
+# the cases below are small: keep their rows partitioned (the default would solve them redundantly on every rank)
+os.environ['UFE_REDUNDANT_MAX_UNKNOWNS'] = '0'
 cases = []
 for pc_name, meth in (('auto', 'bicgstab'), ('bjacobi2', 'bicgstab'), ('bjacobi2', 'gmres'), ('auto', 'gmres')):
     cases.append(('ISMIP-HOM A', experiments.ISMIP_HOM('A', 160e3, 41), pc_name, meth))
@@ -82,6 +84,25 @@ for name, (mesh, C, ice), pc_name, meth in cases:
             print(f'{name} thickness update (calc_dHi_dt, replicated on {world} ranks): identical on all ranks {same}, Hi_tplusdt vs oracle {rt:.2e} '
                   f'Krylov {thk["n_Axb_its"]} {"OK" if good_t else "MISMATCH"}', flush=True)
     S.close()
+# the default for small systems: not partitioned, every rank solves the whole system, bit-identical results
+del os.environ['UFE_REDUNDANT_MAX_UNKNOWNS']
+mesh, C, ice = experiments.MISMIPplus(8e3)
+C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
+C.visc_it_nit = 8
+S = diva.initialise_DIVA_solver(mesh, C, make_comm())
+info = S.solve_DIVA(ice)
+u_all = [torch.zeros(mesh.nTri, dtype=torch.float64, device='cuda') for _ in range(world)]
+dist.all_gather(u_all, torch.from_numpy(S.u_vav_b).cuda())
+same = all(torch.equal(u_all[0], t) for t in u_all)
+if rank == 0:
+    D, nv, _ = oracle_cache['MISMIP+ 8km']
+    ref = np.concatenate([D['u_vav_b'], D['v_vav_b']])
+    ru = rel(S.u_vav_b, D['u_vav_b'], ref)
+    good = same and info.reserved == 2 and max(ru) < 1e-6 and S.ownership() == (1, mesh.nV, 1, mesh.nTri)
+    ok &= good
+    print(f'MISMIP+ 8km redundant default: ranks {world} mode {info.reserved} identical on all ranks {same} Picard {info.n_visc_its} (oracle {nv}) '
+          f'u {ru[1]:.2e} {"OK" if good else "MISMATCH"}', flush=True)
+S.close()
 dist.barrier()
 if rank == 0:
     print('MULTI_GPU_CHECK', 'PASS' if ok else 'FAIL', flush=True)

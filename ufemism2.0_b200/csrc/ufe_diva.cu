@@ -117,6 +117,7 @@ struct ufe_handle {
   double *sym = nullptr;                       // symmetric peer buffer (several ranks): owns S.x, kw.pg, kw.sg
   SecondaryFields sec;                         // calc_secondary_velocities outputs (allocated on first use)
   bool sec_alloc = false, sec_current = false;
+  int redundant_ranks = 0;                     // > 0: this many ranks each solve the whole (small) system redundantly
   bool outputs_gathered = false;               // several ranks: the solution fields are full-length on every rank
   int last_is_diva = 1;
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
@@ -478,6 +479,18 @@ extern "C" int ufe_diva_create(const ufe_mesh *mesh, const ufe_config *cfg, cons
   h->cfg = *cfg;
   h->comm.rank = comm ? comm->rank : 0;
   h->comm.nranks = comm ? comm->nranks : 1;
+  // Small systems are not partitioned: below ~1.3e5 unknowns every kernel of the path is launch-latency-bound
+  // (profiles/r1_sweep_spmv_krylov_*.jsonl), so strips only add halo epochs and reductions.  Every rank then solves
+  // the whole system redundantly and bit-identically, with no communication at all (PETSc's PCREDUNDANT idea applied
+  // to the whole solve).  krylov_pc_strip_only = 1 or UFE_REDUNDANT_MAX_UNKNOWNS=0 keep the row partition.
+  {
+    long long max_unknowns = 131072;
+    if (const char *e = getenv("UFE_REDUNDANT_MAX_UNKNOWNS")) max_unknowns = atoll(e);
+    if (h->comm.nranks > 1 && !cfg->krylov_pc_strip_only && 2LL * mesh->nTri <= max_unknowns) {
+      h->redundant_ranks = h->comm.nranks;
+      h->comm.rank = 0; h->comm.nranks = 1;
+    }
+  }
   h->device = comm ? comm->device : 0;
   int rc = UFE_OK;
   auto fail = [&](int code) { ufe_diva_destroy(h); return code; };
@@ -843,7 +856,7 @@ static int picard_resident(ufe_handle *h, int is_diva, ufe_solve_info *info) {
   info->ms_total = tot; info->ms_closures = ms_clo; info->ms_assembly = ms_asm; info->ms_krylov = ms_kry;
   info->gpu_launches = g_launch_count - launches0;
   info->krylov_pc_used = h->pc_used;
-  info->reserved = h->comm.peer.on;        // 1: peer-memory halo reads + reductions inside the Krylov loop
+  info->reserved = h->redundant_ranks > 0 ? 2 : h->comm.peer.on;        // 1: peer-memory halo reads + reductions inside the Krylov loop
   return UFE_OK;
 }
 
