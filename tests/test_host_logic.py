@@ -206,3 +206,13 @@ def test_workload_configs_equal_the_reference_cfg_files(cfg_file, make):
             "refgeo_idealised_SSA_icestream_m", "refgeo_idealised_ISMIP_HOM_L", "choice_idealised_sliding_law"}
     diffs = {k: (getattr(got, k), getattr(want, k)) for k in PATH_KEYS if k not in skip and getattr(got, k) != getattr(want, k)}
     assert not diffs, diffs
+
+
+def test_nested_dissection_prototype_solves_the_stiffness_system():
+    """tools/nd_prototype.py (round-2 planning prototype of the multifrontal solver): exact solve on a small MISMIP+ mesh."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "nd_prototype.py"), "mismipplus:16000", "24"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"residual ([0-9.e+-]+) \| x vs SuperLU ([0-9.e+-]+)", out.stdout)
+    assert m and float(m.group(1)) < 1e-12 and float(m.group(2)) < 1e-7, out.stdout
+    assert " level  fronts" in out.stdout
