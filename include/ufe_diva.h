@@ -370,6 +370,23 @@ int ufe_mesh_apply_operator(ufe_handle *h, int32_t family, int32_t which, const 
 int ufe_get_stiffness_csr(ufe_handle *h, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind,
                           double *val, double *bb);
 
+/* ---- staged for the multifrontal exact solver on wide meshes ---------------------------
+ * Host-only symbolic analysis: nested dissection (recursive coordinate bisection on the triangle centroids) of the
+ * block graph of the stiffness matrix -- one node per triangle's 2x2 (u,v) block.  Needs no GPU.  bptr / bind: block
+ * pattern, 0-based CSR over triangles.  The tree is stored in post-order (children before parents, root last); node i
+ * eliminates the triangles sep[0..n_sep) and its dense front is [sep; bnd] x [sep; bnd]; up[k] is the position of
+ * bnd[k] in the parent's [sep; bnd] list (extend-add of the Schur complement); the entry map gives, per block entry
+ * of the analysed pattern, the front it is assembled into and its block row / column there. */
+typedef struct ufe_nd_tree ufe_nd_tree;
+int ufe_nd_analyse(int32_t nT, const double *centroid_x, const double *centroid_y, const int32_t *bptr,
+                   const int32_t *bind, int32_t leaf_triangles, ufe_nd_tree **out);
+int ufe_nd_tree_info(const ufe_nd_tree *T, int32_t *n_nodes, int32_t *n_levels, int32_t *max_front,
+                     double *padded_front_bytes);
+int ufe_nd_tree_node(const ufe_nd_tree *T, int32_t i, int32_t *level, int32_t *parent, int32_t *n_sep, int32_t *n_bnd,
+                     const int32_t **sep, const int32_t **bnd, const int32_t **up);
+int ufe_nd_tree_entry_map(const ufe_nd_tree *T, const int32_t **node, const int32_t **row, const int32_t **col);
+void ufe_nd_tree_free(ufe_nd_tree *T);
+
 /* benchmark / roofline helpers: time `reps` launches of the stiffness-matrix SpMV (the
  * Krylov MatMult kernel) on the handle's resident matrix with CUDA events on the
  * launching stream; returns average ms per launch and the algorithmic bytes per launch

@@ -216,3 +216,72 @@ def test_nested_dissection_prototype_solves_the_stiffness_system():
     m = re.search(r"residual ([0-9.e+-]+) \| x vs SuperLU ([0-9.e+-]+)", out.stdout)
     assert m and float(m.group(1)) < 1e-12 and float(m.group(2)) < 1e-7, out.stdout
     assert " level  fronts" in out.stdout
+
+
+def _block_pattern(A, nT):
+    """0-based block CSR over triangles of a scipy matrix with the 2x2 (u,v) unknown ordering."""
+    import scipy.sparse as sp
+    P = sp.csr_matrix((np.ones(A.nnz), A.indices // 2, A.indptr), shape=(2 * nT, nT))
+    R = sp.csr_matrix((np.ones(2 * nT), (np.arange(2 * nT) // 2, np.arange(2 * nT))), shape=(nT, 2 * nT))
+    B = (R @ P).tocsr()
+    B.sort_indices()
+    return B.indptr.astype(np.int32), B.indices.astype(np.int32)
+
+
+@pytest.mark.parametrize("workload, leaf", [("mismipplus", 24), ("ismip_hom", 16)])
+def test_nd_symbolic_analysis_drives_an_exact_multifrontal_solve(oracle, workload, leaf):
+    """The staged host-side nested-dissection analysis (ufe_nd_analyse): a numpy multifrontal factorisation that uses
+    ONLY its maps (assembly map of every block entry, extend-add positions, post-order) solves the oracle's stiffness
+    system exactly; the tree invariants hold."""
+    import scipy.sparse.linalg as spla
+    from ufemism2_0_b200 import nd
+    mesh, C, ice = experiments.MISMIPplus(16e3) if workload == "mismipplus" else experiments.ISMIP_HOM("C", 80e3, 21)
+    mesh.ops = oracle.calc_all_matrix_operators_mesh(mesh)
+    cap = {}
+    orig = oracle.direct_solve
+    def grab(A, b):
+        cap.setdefault("A", A.to_scipy().tocsr()); cap.setdefault("b", np.asarray(b).copy())
+        return orig(A, b)
+    oracle.direct_solve = grab
+    try:
+        C.visc_it_nit = 0
+        oracle.solve_DIVA(mesh, ice, C, oracle.new_DIVA_state(mesh))
+    finally:
+        oracle.direct_solve = orig
+    A, b, nT = cap["A"], cap["b"], mesh.nTri
+    A.sort_indices()
+    bptr, bind = _block_pattern(A, nT)
+    T = nd.analyse(np.asarray(mesh.TriGC), bptr, bind, leaf)
+    # invariants: every triangle eliminated exactly once; children precede parents; root has no boundary
+    allsep = np.concatenate([n.sep for n in T.nodes])
+    assert np.array_equal(np.sort(allsep), np.arange(nT))
+    assert all(n.parent > i for i, n in enumerate(T.nodes[:-1])) and T.nodes[-1].parent == -1 and T.nodes[-1].bnd.size == 0
+    assert T.max_front == max(2 * (n.sep.size + n.bnd.size) for n in T.nodes) and T.n_levels == 1 + max(n.level for n in T.nodes)
+    # numeric phase from the maps alone
+    F = [np.zeros((2 * (n.sep.size + n.bnd.size),) * 2) for n in T.nodes]
+    Ac = A.tocoo()
+    # block entry index of every scalar entry: position of (i//2, j//2) in the block CSR
+    rowb, colb = Ac.row // 2, Ac.col // 2
+    e = np.array([bptr[r] + np.searchsorted(bind[bptr[r]:bptr[r + 1]], c) for r, c in zip(rowb, colb)])
+    for v, r, c, k in zip(Ac.data, Ac.row, Ac.col, e):
+        F[T.entry_node[k]][2 * T.entry_row[k] + r % 2, 2 * T.entry_col[k] + c % 2] += v
+    dof = lambda t: np.stack([2 * t, 2 * t + 1], axis=1).ravel()
+    X, F12, F21 = {}, {}, {}
+    for i, n in enumerate(T.nodes):
+        ns = 2 * n.sep.size
+        X[i] = np.linalg.inv(F[i][:ns, :ns])
+        F12[i], F21[i] = F[i][:ns, ns:], F[i][ns:, :ns]
+        if n.parent >= 0:
+            S = F[i][ns:, ns:] - F21[i] @ (X[i] @ F12[i])
+            m = dof(n.up.astype(np.int64))
+            F[n.parent][np.ix_(m, m)] += S
+    x, z = b.copy(), {}
+    for i, n in enumerate(T.nodes):
+        z[i] = X[i] @ x[dof(n.sep)]
+        x[dof(n.bnd)] -= F21[i] @ z[i]
+    for i in range(len(T.nodes) - 1, -1, -1):
+        n = T.nodes[i]
+        x[dof(n.sep)] = z[i] - X[i] @ (F12[i] @ x[dof(n.bnd)])
+    xr = spla.splu(A.tocsc()).solve(b)
+    assert np.linalg.norm(A @ x - b) <= 1e-12 * np.linalg.norm(b)
+    assert np.abs(x - xr).max() <= 1e-7 * np.abs(xr).max()

@@ -138,6 +138,7 @@ EXPORTS = [
     "ufe_mesh_apply_operator", "ufe_get_stiffness_csr", "ufe_bench_spmv", "ufe_get_ownership",
     "ufe_mesh_set_edges", "ufe_calc_dHi_dt", "ufe_calc_dHi_dt_explicit", "ufe_calc_dHi_dt_semiimplicit", "ufe_get_thickness_csr",
     "ufe_get_thickness_timing", "ufe_calc_vertical_velocities", "ufe_mesh_get_operator_a_a",
+    "ufe_nd_analyse", "ufe_nd_tree_info", "ufe_nd_tree_node", "ufe_nd_tree_entry_map", "ufe_nd_tree_free",
 ]
 
 _lib = None
