@@ -387,6 +387,21 @@ int ufe_nd_tree_node(const ufe_nd_tree *T, int32_t i, int32_t *level, int32_t *p
 int ufe_nd_tree_entry_map(const ufe_nd_tree *T, const int32_t **node, const int32_t **row, const int32_t **col);
 void ufe_nd_tree_free(ufe_nd_tree *T);
 
+/* Numeric phase on the device (csrc/ufe_nd_numeric.cu): exact solve of A x = b, the system the reference hands to
+ * PETSc at solve_linearised_SSA_DIVA.f90:159 (petsc_basic.f90:32-64), by a multifrontal factorisation over the tree --
+ * one batch of padded dense fronts per tree level, blocked Gauss-Jordan sweep of the pivot rows, extend-add of the
+ * Schur complements in a fixed order.  ptr / ind / val: scalar CSR of A, 0-based, N = 2 nTri rows, whose block pattern
+ * is the analysed one; host arrays, borrowed for the call.  `factor` may be called again with new values (same
+ * pattern: one analysis per mesh, one factorisation per Picard iteration); `solve` returns x = A^-1 b after n_refine
+ * steps of iterative refinement with the unscaled matrix and the relative residual |b - A x| / |b|.  No CPU fallback:
+ * create fails with UFE_ERR_CUDA without a device. */
+typedef struct ufe_nd_solver ufe_nd_solver;
+int ufe_nd_solver_create(const ufe_nd_tree *T, int32_t N, const int32_t *ptr, const int32_t *ind, ufe_nd_solver **out);
+int ufe_nd_solver_factor(ufe_nd_solver *S, const double *val);
+int ufe_nd_solver_solve(ufe_nd_solver *S, const double *b, double *x, int32_t n_refine, double *relres);
+int ufe_nd_solver_info(const ufe_nd_solver *S, double *factor_ms, double *solve_ms, double *front_bytes, double *factor_flops);
+void ufe_nd_solver_free(ufe_nd_solver *S);
+
 /* benchmark / roofline helpers: time `reps` launches of the stiffness-matrix SpMV (the
  * Krylov MatMult kernel) on the handle's resident matrix with CUDA events on the
  * launching stream; returns average ms per launch and the algorithmic bytes per launch

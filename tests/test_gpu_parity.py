@@ -575,3 +575,55 @@ def test_remap_DIVA_solver_lifecycle(oracle):
     assert info.n_visc_its > 0 and np.isfinite(S2.u_vav_b).all()
     with pytest.raises(UfeError, match="remapped"):
         diva.remap_DIVA_solver(S2, mesh_old, lambda d: d)
+
+
+# ------------------------------------------------------------------------------------------
+# multifrontal nested-dissection exact solver (ufe_nd_solver_*): the stiffness system of a linearised
+# solve, taken from the device in the reference layout, against a CPU sparse LU of the same system
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("workload, leaf", [("mismipplus_8km", 48), ("ismip_hom_c", 24), ("mismip_16km", 96)])
+def test_nd_multifrontal_solver_matches_sparse_LU(workload, leaf):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from ufemism2_0_b200 import nd
+    if workload == "mismipplus_8km":
+        mesh, C, ice = experiments.MISMIPplus(8e3)
+    elif workload == "ismip_hom_c":
+        mesh, C, ice = experiments.ISMIP_HOM("C", 80e3, 31)
+    else:
+        mesh, C, ice = experiments.MISMIP_8km(16e3)
+    C.visc_it_nit = 2
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        S.solve_DIVA(ice)
+        A, bb = S.get_stiffness_matrix()
+    finally:
+        S.close()
+    N = 2 * mesh.nTri
+    ptr, ind = (A.ptr - 1).astype(np.int32), (A.ind - 1).astype(np.int32)
+    M = sp.csr_matrix((A.val, ind, ptr), shape=(N, N))
+    xr = spla.splu(M.tocsc()).solve(bb)
+    sol = nd.Solver(np.asarray(mesh.TriGC), ptr, ind, leaf)
+    try:
+        sol.factor(A.val)
+        x0, r0 = sol.solve(bb, n_refine=0)
+        x1, r1 = sol.solve(bb, n_refine=2)
+        assert r0 < 1e-8 and r1 < 1e-13, (r0, r1)
+        assert np.abs(x1 - xr).max() <= 1e-9 * np.abs(xr).max()
+        # linearity and a second factorisation with new values on the same analysis
+        rng = np.random.default_rng(3)
+        b2 = rng.standard_normal(N)
+        x2, _ = sol.solve(b2, n_refine=2)
+        x3, _ = sol.solve(2.0 * bb - 3.0 * b2, n_refine=2)
+        assert np.abs(x3 - (2.0 * x1 - 3.0 * x2)).max() <= 1e-9 * max(np.abs(x1).max(), np.abs(x2).max()) * 5
+        M2 = M + sp.diags(np.abs(M.diagonal()) * 0.5)
+        M2 = M2.tocsr(); M2.sort_indices()
+        Mo = M.copy(); Mo.sort_indices()
+        if np.array_equal(M2.indices, Mo.indices) and np.array_equal(ind, Mo.indices):
+            sol.factor(M2.data)
+            x4, r4 = sol.solve(bb, n_refine=2)
+            assert r4 < 1e-13 and np.abs(M2 @ x4 - bb).max() <= 1e-10 * np.abs(bb).max()
+        info = sol.info()
+        assert info["factor_ms"] > 0 and info["front_bytes"] > 0
+    finally:
+        sol.close()

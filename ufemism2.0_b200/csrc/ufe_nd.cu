@@ -16,19 +16,7 @@
 #include <algorithm>
 #include <numeric>
 
-struct NdNode {
-  int level = 0, parent = -1, child[2] = {-1, -1};
-  std::vector<int> sep, bnd;          // 0-based triangle ids, ascending
-  std::vector<int> up;                // position of bnd[k] in the parent's [sep; bnd] list
-};
-
-struct ufe_nd_tree {
-  int nT = 0, n_levels = 0;
-  std::vector<NdNode> nodes;          // post-order: children before their parent, root last
-  std::vector<int> node_of;           // (nT) node that eliminates each triangle
-  std::vector<int> pos_in_sep;        // (nT) position of the triangle in its node's sep list
-  std::vector<int> entry_node, entry_row, entry_col;   // per block entry of the input pattern: front and block position
-};
+#include "ufe_nd.cuh"
 
 namespace {
 
@@ -113,6 +101,7 @@ extern "C" int ufe_nd_analyse(int32_t nT, const double *centroid_x, const double
       if (bind[k] < 0 || bind[k] >= nT) { ufe_set_error("ufe_nd_analyse: column out of range in row %d", i); return UFE_ERR_INVALID; }
   ufe_nd_tree *T = new ufe_nd_tree();
   T->nT = nT;
+  T->bptr.assign(bptr, bptr + nT + 1); T->bind.assign(bind, bind + bptr[nT]);
   const Graph G = symmetrise(nT, bptr, bind);
   {
     std::vector<char> mark(nT, 0);

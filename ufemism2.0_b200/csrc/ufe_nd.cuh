@@ -1,0 +1,19 @@
+// Elimination tree of the nested-dissection analysis (ufe_nd.cu), shared with the numeric phase (ufe_nd_numeric.cu).
+#pragma once
+#include <vector>
+
+struct NdNode {
+  int level = 0, parent = -1, child[2] = {-1, -1};
+  std::vector<int> sep, bnd;          // 0-based triangle ids, ascending
+  std::vector<int> up;                // position of bnd[k] in the parent's [sep; bnd] list
+};
+
+struct ufe_nd_tree {
+  int nT = 0, n_levels = 0;
+  std::vector<NdNode> nodes;          // post-order: children before their parent, root last
+  std::vector<int> node_of;           // (nT) node that eliminates each triangle
+  std::vector<int> pos_in_sep;        // (nT) position of the triangle in its node's sep list
+  std::vector<int> entry_node, entry_row, entry_col;   // per block entry of the input pattern: front and block position
+  std::vector<int> bptr, bind;        // the analysed block pattern (the numeric phase looks scalar entries up in it)
+};
+

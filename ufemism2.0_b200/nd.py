@@ -2,8 +2,9 @@
 
 ``analyse`` returns the elimination tree of the stiffness matrix' block graph in post-order with, per node, ``sep``
 (triangles eliminated there), ``bnd`` (rest of the dense front) and ``up`` (extend-add positions in the parent's
-front), plus the assembly map of every block entry.  The numeric multifrontal phase on the device is the next step
-(DESIGN.md section 9); ``tests/test_host_logic.py`` drives a numpy numeric phase from these maps to check them."""
+front), plus the assembly map of every block entry; ``tests/test_host_logic.py`` drives a numpy numeric phase from
+these maps to check them.  ``Solver`` is the numeric multifrontal phase on the device (``ufe_nd_solver_*``,
+csrc/ufe_nd_numeric.cu): analyse once per mesh, ``factor`` per matrix, ``solve`` per right-hand side."""
 from __future__ import annotations
 
 import ctypes as ct
@@ -65,3 +66,72 @@ def analyse(centroids: np.ndarray, bptr: np.ndarray, bind: np.ndarray, leaf_tria
         lib.ufe_nd_tree_free.restype = None
         lib.ufe_nd_tree_free(T)
     return tree
+
+
+def block_pattern(ptr: np.ndarray, ind: np.ndarray, nT: int):
+    """0-based block CSR over triangles (sorted columns) of a 0-based scalar CSR pattern with the (u,v) interleaved
+    unknown numbering n = 2 ti + uv (mesh_translation_tables.f90:181-198, here 0-based)."""
+    rows = np.repeat(np.arange(2 * nT, dtype=np.int64), np.diff(ptr)) // 2
+    key = np.unique(rows * nT + np.asarray(ind, dtype=np.int64) // 2)
+    br, bc = key // nT, key % nT
+    bptr = np.zeros(nT + 1, dtype=np.int32)
+    np.cumsum(np.bincount(br, minlength=nT), out=bptr[1:])
+    return bptr, bc.astype(np.int32)
+
+
+class Solver:
+    """Exact multifrontal solve of a stiffness system on the device.  ptr / ind: 0-based scalar CSR pattern (N = 2 nT)."""
+
+    def __init__(self, centroids: np.ndarray, ptr: np.ndarray, ind: np.ndarray, leaf_triangles: int = 96):
+        self._lib = capi.lib()
+        self._T, self._S = ct.c_void_p(), ct.c_void_p()
+        nT = centroids.shape[0]
+        self.N = 2 * nT
+        ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+        ind = np.ascontiguousarray(ind, dtype=np.int32)
+        bptr, bind = block_pattern(ptr, ind, nT)
+        x = np.ascontiguousarray(centroids[:, 0], dtype=np.float64)
+        y = np.ascontiguousarray(centroids[:, 1], dtype=np.float64)
+        check(self._lib.ufe_nd_analyse(nT, vp(x), vp(y), vp(bptr), vp(bind), int(leaf_triangles), ct.byref(self._T)))
+        nn, nl, mf, pb = ct.c_int32(), ct.c_int32(), ct.c_int32(), ct.c_double()
+        check(self._lib.ufe_nd_tree_info(self._T, ct.byref(nn), ct.byref(nl), ct.byref(mf), ct.byref(pb)))
+        self.n_fronts, self.n_levels, self.max_front = nn.value, nl.value, mf.value
+        try:
+            check(self._lib.ufe_nd_solver_create(self._T, self.N, vp(ptr), vp(ind), ct.byref(self._S)))
+        except Exception:
+            self.close()
+            raise
+
+    def factor(self, val: np.ndarray):
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        check(self._lib.ufe_nd_solver_factor(self._S, vp(val)))
+
+    def solve(self, b: np.ndarray, n_refine: int = 1):
+        """returns (x, |b - A x| / |b|)"""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(self.N)
+        rr = ct.c_double()
+        check(self._lib.ufe_nd_solver_solve(self._S, vp(b), vp(x), int(n_refine), ct.byref(rr)))
+        return x, rr.value
+
+    def info(self):
+        f, s, by, fl = ct.c_double(), ct.c_double(), ct.c_double(), ct.c_double()
+        check(self._lib.ufe_nd_solver_info(self._S, ct.byref(f), ct.byref(s), ct.byref(by), ct.byref(fl)))
+        return {"factor_ms": f.value, "solve_ms": s.value, "front_bytes": by.value, "factor_flops": fl.value,
+                "n_fronts": self.n_fronts, "n_levels": self.n_levels, "max_front": self.max_front}
+
+    def close(self):
+        self._lib.ufe_nd_solver_free.restype = None
+        self._lib.ufe_nd_tree_free.restype = None
+        if self._S:
+            self._lib.ufe_nd_solver_free(self._S)
+            self._S = ct.c_void_p()
+        if self._T:
+            self._lib.ufe_nd_tree_free(self._T)
+            self._T = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
