@@ -479,7 +479,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": label, "nV": nV, "nTri": nT, "nz": nz, "unknowns": 2 * nT,
                    "krylov": f"{C.b200_krylov_method}+{C.b200_krylov_pc}",
-                   "krylov_pc_used": {0: "jacobi", 1: "bjacobi2", 2: "bjacobi_lu"}.get(last.krylov_pc_used, str(last.krylov_pc_used)),
+                   "krylov_pc_used": {0: "jacobi", 1: "bjacobi2", 2: "bjacobi_lu", 4: "nd_lu"}.get(last.krylov_pc_used, str(last.krylov_pc_used)),
                    "rtol": C.stress_balance_PETSc_rtol, "abstol": C.stress_balance_PETSc_abstol,
                    "picard_tol": C.visc_it_norm_dUV_tol, "visc_it_nit": C.visc_it_nit,
                    "l2": "step working set rewritten every Picard iteration; SpMV roofline leg flushes L2 (512 MiB) between launches"},

@@ -627,3 +627,31 @@ def test_nd_multifrontal_solver_matches_sparse_LU(workload, leaf):
         assert info["factor_ms"] > 0 and info["front_bytes"] > 0
     finally:
         sol.close()
+
+
+@pytest.mark.parametrize("workload, method, lag", [("mismipplus_8km", "bicgstab", 0), ("mismipplus_8km", "gmres", 20),
+                                                   ("ismip_hom_c", "bicgstab", 0)])
+def test_DIVA_with_nd_lu_preconditioner(oracle, workload, method, lag):
+    """krylov_pc = 'nd_lu': the multifrontal solver as the exact preconditioner of the Picard loop's linear solves;
+    same Picard count and velocities as the oracle's direct solve, one or two Krylov iterations per fresh factorisation."""
+    if workload == "mismipplus_8km":
+        mesh, C, ice = experiments.MISMIPplus(8e3)
+        C.visc_it_nit = 6
+    else:
+        mesh, C, ice = experiments.ISMIP_HOM("C", 80e3, 21)
+        C.visc_it_nit = 8
+    oracle.calc_all_matrix_operators_mesh(mesh)
+    C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
+    C.b200_krylov_pc, C.b200_krylov_pc_lag, C.b200_krylov_method = "nd_lu", lag, method
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        info = S.solve_DIVA(ice)
+        D = oracle.new_DIVA_state(mesh)
+        nv, _ = oracle.solve_DIVA(mesh, ice, C, D, "direct")
+        assert info.n_visc_its == nv and (info.flags & (diva.KRYLOV_MAXIT | diva.KRYLOV_DIVERGED)) == 0
+        assert info.krylov_pc_used == 4
+        if lag == 0:
+            assert info.n_Axb_its <= 3 * info.n_visc_its, (info.n_Axb_its, info.n_visc_its)
+        _check_uv(S, D)
+    finally:
+        S.close()

@@ -86,6 +86,7 @@ class Config:
     b200_krylov_method: str = "bicgstab"      # 'bicgstab' | 'gmres'
     # 'jacobi' | 'bjacobi2' (2x2 u-v blocks) | 'bjacobi_lu' (one block per GPU, solved exactly by block
     # cyclic reduction; needs a banded = x-sorted, narrow mesh) | 'auto' (bjacobi_lu when it fits, else bjacobi2)
+    # | 'nd_lu' (exact multifrontal nested-dissection factorisation of the whole matrix: wide meshes, one GPU)
     b200_krylov_pc: str = "auto"
     b200_krylov_pc_strip_only: bool = False   # several ranks: True = one strip block per rank even when the replicated exact solve fits
     b200_krylov_pc_lag: int = 0               # bjacobi_lu: >0 reuses a factorisation until a solve needs more Krylov its than this (0: factorise every Picard it)

@@ -199,7 +199,7 @@ static int validate_config(const ufe_config *c) {
   if (c->choice_ice_rheology_Glen < 0 || c->choice_ice_rheology_Glen > 1) { ufe_set_error("unknown choice_ice_rheology_Glen (code %d)!", c->choice_ice_rheology_Glen); return UFE_ERR_INVALID; }
   if (c->choice_enhancement_factor_transition < 0 || c->choice_enhancement_factor_transition > 1) { ufe_set_error("unknown choice_enhancement_factor_transition!"); return UFE_ERR_INVALID; }
   if (c->do_subgrid_friction_on_A_grid) { ufe_set_error("do_subgrid_friction_on_A_grid = .true. is not supported (needs Hs_slope and grounding-line masks)"); return UFE_ERR_INVALID; }
-  if (c->krylov_method < 0 || c->krylov_method > 1 || c->krylov_pc < 0 || c->krylov_pc > 3) { ufe_set_error("unknown krylov method / preconditioner"); return UFE_ERR_INVALID; }
+  if (c->krylov_method < 0 || c->krylov_method > 1 || c->krylov_pc < 0 || c->krylov_pc > UFE_PC_ND_LU) { ufe_set_error("unknown krylov method / preconditioner"); return UFE_ERR_INVALID; }
   if (c->choice_sliding_law == UFE_SLID_IDEALISED && c->choice_idealised_sliding_law == UFE_IDEAL_SSA_ICESTREAM &&
       c->Glens_flow_law_exponent != 3.0) { ufe_set_error("Schoof only derived a solution for the case of n=3!"); return UFE_ERR_INVALID; }
   return UFE_OK;
@@ -711,9 +711,13 @@ static int linearised_resident(ufe_handle *h, double rtol, double abstol, int *n
       if (rc == UFE_ERR_CUDA) return rc;
       if (rc != UFE_OK && h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) return rc;
       h->pc_used = rc == UFE_OK ? UFE_PC_BJACOBI_LU : UFE_PC_BJACOBI2;
+    } else if (h->cfg.krylov_pc == UFE_PC_ND_LU) {    // wide meshes: multifrontal nested dissection, one analysis per pattern
+      if (h->comm.nranks > 1) { h->pc_used = -1; ufe_set_error("krylov_pc nd_lu: one GPU only (the fronts are not distributed yet)"); return UFE_ERR_INVALID; }
+      const int rc = ufe_pclu_setup_nd(h->st, h->S, h->dm.nTri, h->hGC.data(), h->hGC.data() + h->dm.nTri, &h->pclu);
+      if (rc != UFE_OK) { h->pc_used = -1; return rc; }
     }
   }
-  if (h->pc_used == UFE_PC_BJACOBI_LU) {
+  if (h->pc_used == UFE_PC_BJACOBI_LU || h->pc_used == UFE_PC_ND_LU) {
     // PCSetUp.  The factorisation of an earlier Picard iteration's matrix is still a good
     // preconditioner while the viscosity changes slowly, so it is reused (krylov_pc_lag > 0) until
     // the Krylov count shows it has aged: refactorise when the previous solve needed more than

@@ -42,7 +42,7 @@ struct ufe_nd_solver {
   int *sepdof = nullptr, *upmap = nullptr;   // global unknown of every sep row; parent row of every bnd row
   long long *dst = nullptr;                  // per scalar CSR entry: destination in F
   int *ptr = nullptr, *ind = nullptr;        // 0-based scalar CSR of A
-  double *val = nullptr, *scale = nullptr;
+  double *val = nullptr, *scale = nullptr, *dself = nullptr, *dpair = nullptr;
   double *F = nullptr, *W = nullptr, *Z = nullptr, *ipp = nullptr, *colbuf = nullptr;
   double *b = nullptr, *x = nullptr, *r = nullptr, *dx = nullptr;
   size_t f_doubles = 0, w_doubles = 0;
@@ -56,12 +56,14 @@ struct ufe_nd_solver {
 // ------------------------------------------------------------------------------------------------------------------
 // assembly
 // ------------------------------------------------------------------------------------------------------------------
+// also keeps row i of the 2x2 (u,v) diagonal block of its triangle: dself = a_ii, dpair = a_i,i^1
 __global__ void k_nd_scale(int N, const int *__restrict__ ptr, const int *__restrict__ ind, const double *__restrict__ val,
-                           double *__restrict__ scale) {
+                           double *__restrict__ scale, double *__restrict__ dself, double *__restrict__ dpair) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  double d = 0.0;
-  for (int k = ptr[i]; k < ptr[i + 1]; k++) if (ind[k] == i) d += val[k];
+  double d = 0.0, o = 0.0;
+  for (int k = ptr[i]; k < ptr[i + 1]; k++) { if (ind[k] == i) d += val[k]; else if (ind[k] == (i ^ 1)) o += val[k]; }
+  dself[i] = d; dpair[i] = o;
   d = fabs(d);
   scale[i] = d > 0.0 ? 1.0 / sqrt(d) : 1.0;
 }
@@ -215,14 +217,18 @@ __global__ void k_nd_extend(int g, int p, int first, const double *__restrict__ 
 // ------------------------------------------------------------------------------------------------------------------
 // solve
 // ------------------------------------------------------------------------------------------------------------------
-// w_s = scaled right-hand side of the front's own unknowns, everything else zero
+// w_s = scaled right-hand side of the front's own unknowns, everything else zero.  dself != nullptr: the right-hand
+// side is first multiplied by the 2x2 diagonal blocks of A (the solver then applies (B A)^-1, B = block-Jacobi scaling)
 __global__ void k_nd_rhs(int g, int first, const int *__restrict__ ns, const int *__restrict__ sep_off,
                          const int *__restrict__ sepdof, const double *__restrict__ scale, const double *__restrict__ b,
-                         double *__restrict__ Wl) {
+                         const double *__restrict__ dself, const double *__restrict__ dpair, double *__restrict__ Wl) {
   const int z = blockIdx.y, f = first + z, r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= g) return;
   double v = 0.0;
-  if (r < ns[f]) { const int d = sepdof[sep_off[f] + r]; v = scale[d] * b[d]; }
+  if (r < ns[f]) {
+    const int d = sepdof[sep_off[f] + r];
+    v = scale[d] * (dself ? dself[d] * b[d] + dpair[d] * b[d ^ 1] : b[d]);
+  }
   Wl[(size_t)z * g + r] = v;
 }
 
@@ -299,7 +305,7 @@ template <class T> static int nd_upload(T **d, const std::vector<T> &h) {
 extern "C" void ufe_nd_solver_free(ufe_nd_solver *S) {
   if (!S) return;
   void *p[] = {S->ns, S->nb, S->parent, S->slot, S->sep_off, S->up_off, S->sepdof, S->upmap, S->dst, S->ptr, S->ind, S->val,
-               S->scale, S->F, S->W, S->Z, S->ipp, S->colbuf, S->b, S->x, S->r, S->dx};
+               S->scale, S->dself, S->dpair, S->F, S->W, S->Z, S->ipp, S->colbuf, S->b, S->x, S->r, S->dx};
   for (void *q : p) if (q) cudaFree(q);
   if (S->e0) cudaEventDestroy(S->e0);
   if (S->e1) cudaEventDestroy(S->e1);
@@ -401,7 +407,7 @@ extern "C" int ufe_nd_solver_create(const ufe_nd_tree *T, int32_t N, const int32
   }
   size_t ipp_n = 0, col_n = 0;
   for (const NdLevelDev &L : S->lev) { ipp_n = std::max(ipp_n, (size_t)L.n * NDB * NDB); col_n = std::max(col_n, (size_t)L.n * L.g * NDB); }
-  const struct { double **p; size_t n; } bufs[] = {{&S->val, (size_t)S->nnz}, {&S->scale, (size_t)N}, {&S->F, S->f_doubles},
+  const struct { double **p; size_t n; } bufs[] = {{&S->val, (size_t)S->nnz}, {&S->scale, (size_t)N}, {&S->dself, (size_t)N}, {&S->dpair, (size_t)N}, {&S->F, S->f_doubles},
       {&S->W, S->w_doubles}, {&S->Z, S->w_doubles}, {&S->ipp, ipp_n}, {&S->colbuf, col_n}, {&S->b, (size_t)N}, {&S->x, (size_t)N},
       {&S->r, (size_t)N}, {&S->dx, (size_t)N}};
   for (const auto &bf : bufs)
@@ -416,10 +422,9 @@ extern "C" int ufe_nd_solver_create(const ufe_nd_tree *T, int32_t N, const int32
 }
 
 // factorisation from values already on the device (same order as the pattern given to create)
-static int nd_factor_device(ufe_nd_solver *S, const double *dval) {
-  cudaStream_t st = S->st;
+static int nd_factor_device(ufe_nd_solver *S, cudaStream_t st, const double *dval) {
   const int N = S->N, tb = 256;
-  k_nd_scale<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale); UFE_LAUNCH_CHECK();
+  k_nd_scale<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dself, S->dpair); UFE_LAUNCH_CHECK();
   UFE_CUDA(cudaMemsetAsync(S->F, 0, S->f_doubles * sizeof(double), st));
   k_nd_assemble<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dst, S->F); UFE_LAUNCH_CHECK();
   for (int l = (int)S->lev.size() - 1; l >= 0; l--) {
@@ -445,12 +450,11 @@ static int nd_factor_device(ufe_nd_solver *S, const double *dval) {
 }
 
 // x (+)= A^-1 r with the factors; r, x device vectors of length N
-static int nd_apply_device(ufe_nd_solver *S, const double *r, double *x, int accumulate) {
-  cudaStream_t st = S->st;
+static int nd_apply_device(ufe_nd_solver *S, cudaStream_t st, const double *r, double *x, int accumulate, int premul) {
   const int nl = (int)S->lev.size();
   for (int l = 0; l < nl; l++) {
     const NdLevelDev &L = S->lev[l];
-    k_nd_rhs<<<dim3((L.g + 255) / 256, L.n), 256, 0, st>>>(L.g, L.first, S->ns, S->sep_off, S->sepdof, S->scale, r, S->W + L.w_off);
+    k_nd_rhs<<<dim3((L.g + 255) / 256, L.n), 256, 0, st>>>(L.g, L.first, S->ns, S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->dpair, S->W + L.w_off);
     UFE_LAUNCH_CHECK();
   }
   for (int l = nl - 1; l >= 0; l--) {
@@ -486,7 +490,7 @@ extern "C" int ufe_nd_solver_factor(ufe_nd_solver *S, const double *val) {
   if (!S || !val) { ufe_set_error("ufe_nd_solver_factor: bad argument"); return UFE_ERR_INVALID; }
   UFE_CUDA(cudaMemcpyAsync(S->val, val, (size_t)S->nnz * sizeof(double), cudaMemcpyHostToDevice, S->st));
   UFE_CUDA(cudaEventRecord(S->e0, S->st));
-  UFE_TRY(nd_factor_device(S, S->val));
+  UFE_TRY(nd_factor_device(S, S->st, S->val));
   UFE_CUDA(cudaEventRecord(S->e1, S->st));
   UFE_CUDA(cudaStreamSynchronize(S->st));
   UFE_CUDA(cudaEventElapsedTime(&S->factor_ms, S->e0, S->e1));
@@ -500,10 +504,10 @@ extern "C" int ufe_nd_solver_solve(ufe_nd_solver *S, const double *b, double *x,
   const int N = S->N, tb = 256;
   UFE_CUDA(cudaMemcpyAsync(S->b, b, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, S->st));
   UFE_CUDA(cudaEventRecord(S->e0, S->st));
-  UFE_TRY(nd_apply_device(S, S->b, S->x, 0));
+  UFE_TRY(nd_apply_device(S, S->st, S->b, S->x, 0, 0));
   for (int it = 0; it < n_refine; it++) {
     k_nd_residual<<<(N + tb - 1) / tb, tb, 0, S->st>>>(N, S->ptr, S->ind, S->val, S->b, S->x, S->r); UFE_LAUNCH_CHECK();
-    UFE_TRY(nd_apply_device(S, S->r, S->x, 1));
+    UFE_TRY(nd_apply_device(S, S->st, S->r, S->x, 1, 0));
   }
   UFE_CUDA(cudaEventRecord(S->e1, S->st));
   k_nd_residual<<<(N + tb - 1) / tb, tb, 0, S->st>>>(N, S->ptr, S->ind, S->val, S->b, S->x, S->r); UFE_LAUNCH_CHECK();
@@ -529,3 +533,40 @@ extern "C" int ufe_nd_solver_info(const ufe_nd_solver *S, double *factor_ms, dou
   if (factor_flops) *factor_flops = S->flops;
   return UFE_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// the same solver as the exact preconditioner of the Krylov loop (krylov_pc = UFE_PC_ND_LU; ufe_pclu.cu dispatches here).
+// The Krylov loop iterates on B A x = B b with B the 2x2 block-Jacobi scaling folded in at assembly time
+// (ufe_assembly.cu), so the preconditioner is  z = (B A)^-1 r = A^-1 (D r),  D = the 2x2 diagonal blocks of A.
+// ------------------------------------------------------------------------------------------------------------------
+int ufe_nd_pc_create(cudaStream_t st, const DevSystem &S, int nT, const double *gcx, const double *gcy, int leaf, ufe_nd_solver **out) {
+  *out = nullptr;
+  if (S.m_loc != S.N || S.r1 != 1 || S.N != 2 * nT) {
+    ufe_set_error("nd_lu preconditioner: the rows of the system must not be partitioned (one GPU)"); return UFE_ERR_INVALID;
+  }
+  std::vector<int> ptr(S.N + 1), ind(S.nnz);
+  UFE_CUDA(cudaStreamSynchronize(st));
+  UFE_CUDA(cudaMemcpy(ptr.data(), S.ptr, ptr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  UFE_CUDA(cudaMemcpy(ind.data(), S.ind, ind.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int &v : ptr) v -= 1;
+  for (int &v : ind) v -= 1;
+  // block pattern over triangles
+  std::vector<int> bptr(nT + 1, 0), bind, row;
+  for (int t = 0; t < nT; t++) {
+    row.clear();
+    for (int k = ptr[2 * t]; k < ptr[2 * t + 2]; k++) row.push_back(ind[k] >> 1);
+    std::sort(row.begin(), row.end());
+    row.erase(std::unique(row.begin(), row.end()), row.end());
+    bind.insert(bind.end(), row.begin(), row.end());
+    bptr[t + 1] = (int)bind.size();
+  }
+  ufe_nd_tree *T = nullptr;
+  UFE_TRY(ufe_nd_analyse(nT, gcx, gcy, bptr.data(), bind.data(), leaf, &T));
+  const int rc = ufe_nd_solver_create(T, S.N, ptr.data(), ind.data(), out);
+  ufe_nd_tree_free(T);
+  return rc;
+}
+
+int ufe_nd_pc_factor(cudaStream_t st, ufe_nd_solver *S, const double *dval) { return nd_factor_device(S, st, dval); }
+
+int ufe_nd_pc_apply(cudaStream_t st, ufe_nd_solver *S, const double *r, double *z) { return nd_apply_device(S, st, r, z, 0, 1); }

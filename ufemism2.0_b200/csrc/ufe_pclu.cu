@@ -50,6 +50,7 @@ struct PcLU {
   double *ipp = nullptr, *colbuf = nullptr;  // Gauss-Jordan scratch: [items][32*32], [items][g][32]
   double *c = nullptr;                       // 2*K*g work vectors (rhs -> solution, staging)
   size_t bytes = 0;
+  ufe_nd_solver *nd = nullptr;               // UFE_PC_ND_LU: the multifrontal solver replaces everything above
 };
 
 // operand addressing for the batched kernels: item z of a level works on node
@@ -481,6 +482,7 @@ __global__ void k_vec_out(int n, const double *__restrict__ c, double *__restric
 // ------------------------------------------------------------------------------------
 void ufe_pclu_free(PcLU *pc) {
   if (!pc) return;
+  ufe_nd_solver_free(pc->nd);
   cudaFree(pc->D); cudaFree(pc->LS); cudaFree(pc->US); cudaFree(pc->Pm); cudaFree(pc->Qm);
   cudaFree(pc->ipp); cudaFree(pc->colbuf); cudaFree(pc->c); cudaFree(pc->gvec);
   delete pc;
@@ -545,7 +547,21 @@ int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int replicate, size_t ma
   return UFE_OK;
 }
 
+// wide meshes: the banded blocks do not fit, the nested-dissection multifrontal solver does (ufe_nd_numeric.cu)
+int ufe_pclu_setup_nd(cudaStream_t st, const DevSystem &S, int nT, const double *gcx, const double *gcy, PcLU **out) {
+  *out = nullptr;
+  const char *e = getenv("UFE_ND_LEAF");
+  const int leaf = e && atoi(e) > 0 ? atoi(e) : 96;
+  PcLU *pc = new PcLU();
+  pc->n_loc = S.m_loc;
+  const int rc = ufe_nd_pc_create(st, S, nT, gcx, gcy, leaf, &pc->nd);
+  if (rc != UFE_OK) { delete pc; return rc; }
+  *out = pc;
+  return UFE_OK;
+}
+
 int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
+  if (pc->nd) return ufe_nd_pc_factor(st, pc->nd, S.val);
   const int g = pc->g, K = pc->K;
   const size_t blk = (size_t)g * g * K * sizeof(double);
   UFE_CUDA(cudaMemsetAsync(pc->D, 0, blk, st));
@@ -608,6 +624,7 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
 
 // z = M^-1 r  (r, z owned-length vectors; may alias)
 int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z) {
+  if (pc->nd) return ufe_nd_pc_apply(st, pc->nd, r, z);
   const int g = pc->g, K = pc->K, total = K * g;
   double *c = pc->c, *y = pc->c + total;
   if (pc->replicated) {      // all-gather the distributed residual, solve globally, keep the own slice

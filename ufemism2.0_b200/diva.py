@@ -29,7 +29,7 @@ from .mesh_types import Mesh
 
 PICARD_MAXIT, KRYLOV_MAXIT, KRYLOV_DIVERGED = 1, 2, 4
 KRYLOV_METHODS = {"bicgstab": 0, "gmres": 1}
-KRYLOV_PCS = {"jacobi": 0, "bjacobi2": 1, "bjacobi_lu": 2, "auto": 3}
+KRYLOV_PCS = {"jacobi": 0, "bjacobi2": 1, "bjacobi_lu": 2, "auto": 3, "nd_lu": 4}
 FAMILIES = {"a_b": (0, ("map", "ddx", "ddy")), "b_a": (1, ("map", "ddx", "ddy")),
             "b_b": (2, ("ddx", "ddy", "d2dx2", "d2dxdy", "d2dy2"))}
 
