@@ -16,6 +16,8 @@ the named mesh.  Legs of the b200 arm:
           buffers - H2D of all ice inputs + state and D2H of all results inside the timed region;
   roofline : the Krylov MatMult kernel (k_kspmv) on the resident stiffness matrix, CUDA events on
           the launching stream, L2 flushed between launches (ufe_bench_spmv);
+  wide_mesh_nd_lu : reported beside the metric: one converged cold-start solve_DIVA on a wide (square, Antarctic-shaped)
+                    mesh with the multifrontal nested-dissection preconditioner (krylov_pc = nd_lu), one GPU.
   thickness_update(_large_mesh) : SURVEY.md 8f rank 2, reported beside the metric, not part of it: one
           ``calc_dHi_dt_semiimplicit`` call on the velocities the solve left on the device (host buffers in and
           out), its device-time split and the achieved GB/s of k_thk_divq (N = 1 only);
@@ -59,6 +61,8 @@ def parse_args():
     ap.add_argument("--no-large-roofline", action="store_true",
                     help="skip the SpMV roofline leg on the ~1M-vertex mesh (the configuration the >= 70 %% target is quoted on)")
     ap.add_argument("--large-vertices", type=int, default=1_000_000)
+    ap.add_argument("--wide-vertices", type=int, default=100_000,
+                    help="size of the wide-mesh full-solve leg (krylov_pc = nd_lu); 0 skips it")
     return ap.parse_args()
 
 
@@ -466,6 +470,26 @@ def main():
             thickness_large = thickness_leg(SL, meshL, CL, iceL, reps=2)
         SL.close()
         del meshL, iceL
+    # reported beside the metric: a converged cold-start DIVA solve on a WIDE mesh (x-sorted bandwidth too large for the
+    # banded exact preconditioner) with the multifrontal nested-dissection preconditioner, one GPU.  Never fatal.
+    wide = None
+    if world == 1 and args.wide_vertices > 0:
+        try:
+            import copy
+            from ufemism2_0_b200 import experiments
+            meshW, CW, iceW = experiments.antarctic(args.wide_vertices)
+            CW = copy.copy(CW)
+            CW.b200_krylov_pc, CW.b200_krylov_pc_lag, CW.b200_krylov_maxits = "nd_lu", 0, 200
+            SW = diva.initialise_DIVA_solver(meshW, CW)
+            t0 = time.time(); iw = SW.solve_DIVA(iceW); tw = time.time() - t0
+            SW.close()
+            wide = {"workload": f"synthetic Antarctic-shaped mesh nV={meshW.nV} (N={2 * meshW.nTri} unknowns), cold start, krylov_pc=nd_lu",
+                    "solves_per_s": 1.0 / tw, "wall_s": tw, "n_visc_its": iw.n_visc_its, "n_Axb_its": iw.n_Axb_its, "flags": iw.flags,
+                    "picard_converged": bool(iw.n_visc_its < CW.visc_it_nit), "ms_krylov": iw.ms_krylov,
+                    "note": "host buffers, includes the once-per-mesh symbolic analysis inside the first linear solve"}
+            del meshW, iceW
+        except Exception as e:      # reported, the metric above does not depend on it
+            wide = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         S.close()
         if world > 1:
@@ -491,7 +515,7 @@ def main():
         "e2e": e2e, "warm": warm, "gpu_launches": int(sum(i.gpu_launches for i in infos)),
         "roofline": roofline, "roofline_bench_workload": roofline_small, "krylov_iteration": krylov_iteration,
         "other_kernels_large_mesh": other_kernels, "thickness_update": thickness,
-        "thickness_update_large_mesh": thickness_large, "clocks": clocks,
+        "thickness_update_large_mesh": thickness_large, "wide_mesh_nd_lu": wide, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_leg(mesh, C, ice, args.cpu_seconds, n_visc_full=last.n_visc_its)

@@ -285,3 +285,23 @@ def test_nd_symbolic_analysis_drives_an_exact_multifrontal_solve(oracle, workloa
     xr = spla.splu(A.tocsc()).solve(b)
     assert np.linalg.norm(A @ x - b) <= 1e-12 * np.linalg.norm(b)
     assert np.abs(x - xr).max() <= 1e-7 * np.abs(xr).max()
+
+
+def test_nd_solver_fails_loudly_without_a_device():
+    """The numeric multifrontal phase has no CPU fallback: on a machine without a GPU ufe_nd_solver_create returns
+    UFE_ERR_CUDA with a message; a pattern that was not analysed is rejected before anything is allocated."""
+    import torch
+    from ufemism2_0_b200 import nd
+    from ufemism2_0_b200.capi import UfeError
+    nT = 64
+    gc = np.stack([np.arange(nT, dtype=float), np.zeros(nT)], axis=1)
+    rows = np.repeat(np.arange(2 * nT), 2)
+    cols = np.stack([np.arange(2 * nT), np.arange(2 * nT) ^ 1], axis=1).ravel()      # 2x2 diagonal blocks only
+    ptr = np.arange(0, 4 * nT + 1, 2, dtype=np.int32)
+    if not torch.cuda.is_available():
+        with pytest.raises(UfeError) as e:
+            nd.Solver(gc, ptr, cols.astype(np.int32), 8)
+        assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+    bptr, bind = nd.block_pattern(ptr, cols, nT)
+    assert np.array_equal(bptr, np.arange(nT + 1)) and np.array_equal(bind, np.arange(nT))
+    assert rows.size == cols.size
