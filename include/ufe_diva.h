@@ -98,7 +98,7 @@ enum { UFE_KRYLOV_BICGSTAB = 0, UFE_KRYLOV_GMRES = 1 };
 /* UFE_PC_BJACOBI_LU: block Jacobi over contiguous row ranges (like PETSc's per-rank blocks) with an
  * exact block-tridiagonal LU solve inside each block (the reference uses ILU(0) there). */
 enum { UFE_PC_JACOBI = 0, UFE_PC_BJACOBI2 = 1, UFE_PC_BJACOBI_LU = 2,
-       UFE_PC_AUTO = 3 /* BJACOBI_LU when its dense blocks fit the memory budget, else BJACOBI2 */,
+       UFE_PC_AUTO = 3 /* BJACOBI_LU when its dense blocks fit the memory budget, else (one GPU) ND_LU when its fronts fit, else BJACOBI2 */,
        UFE_PC_ND_LU = 4 /* exact: multifrontal nested-dissection factorisation of the whole matrix (csrc/ufe_nd_numeric.cu);
                            for wide meshes whose banded blocks do not fit BJACOBI_LU; one GPU; krylov_pc_lag applies */ };
 

@@ -85,7 +85,7 @@ class Config:
     # knob and is unused there.
     b200_krylov_method: str = "bicgstab"      # 'bicgstab' | 'gmres'
     # 'jacobi' | 'bjacobi2' (2x2 u-v blocks) | 'bjacobi_lu' (one block per GPU, solved exactly by block
-    # cyclic reduction; needs a banded = x-sorted, narrow mesh) | 'auto' (bjacobi_lu when it fits, else bjacobi2)
+    # cyclic reduction; needs a banded = x-sorted, narrow mesh) | 'auto' (bjacobi_lu when it fits, else nd_lu on one GPU when it fits, else bjacobi2)
     # | 'nd_lu' (exact multifrontal nested-dissection factorisation of the whole matrix: wide meshes, one GPU)
     b200_krylov_pc: str = "auto"
     b200_krylov_pc_strip_only: bool = False   # several ranks: True = one strip block per rank even when the replicated exact solve fits

@@ -711,6 +711,14 @@ static int linearised_resident(ufe_handle *h, double rtol, double abstol, int *n
       if (rc == UFE_ERR_CUDA) return rc;
       if (rc != UFE_OK && h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) return rc;
       h->pc_used = rc == UFE_OK ? UFE_PC_BJACOBI_LU : UFE_PC_BJACOBI2;
+      // auto on a wide mesh (the banded blocks do not fit): the multifrontal solver when its fronts fit this GPU,
+      // else 2x2 block Jacobi as before.  UFE_AUTO_ND=0 keeps the old behaviour.
+      const char *e = getenv("UFE_AUTO_ND");
+      if (rc != UFE_OK && h->comm.nranks == 1 && !(e && atoi(e) == 0)) {
+        const int rc2 = ufe_pclu_setup_nd(h->st, h->S, h->dm.nTri, h->hGC.data(), h->hGC.data() + h->dm.nTri, &h->pclu);
+        if (rc2 == UFE_OK) h->pc_used = UFE_PC_ND_LU;
+        else { cudaGetLastError(); h->pclu = nullptr; }
+      }
     } else if (h->cfg.krylov_pc == UFE_PC_ND_LU) {    // wide meshes: multifrontal nested dissection, one analysis per pattern
       if (h->comm.nranks > 1) { h->pc_used = -1; ufe_set_error("krylov_pc nd_lu: one GPU only (the fronts are not distributed yet)"); return UFE_ERR_INVALID; }
       const int rc = ufe_pclu_setup_nd(h->st, h->S, h->dm.nTri, h->hGC.data(), h->hGC.data() + h->dm.nTri, &h->pclu);
