@@ -305,3 +305,92 @@ def test_nd_solver_fails_loudly_without_a_device():
     bptr, bind = nd.block_pattern(ptr, cols, nT)
     assert np.array_equal(bptr, np.arange(nT + 1)) and np.array_equal(bind, np.arange(nT))
     assert rows.size == cols.size
+
+
+def _multifrontal_solve_from_maps(T, A, b, bptr, bind):
+    """numpy numeric phase driven only by the maps of the symbolic analysis (same organisation as the device code:
+    assembly map, partial elimination of sep, extend-add through ``up``, forward / backward sweeps over the post-order)."""
+    A = A.tocsr(); A.sort_indices()
+    Ac = A.tocoo()
+    F = [np.zeros((2 * (n.sep.size + n.bnd.size),) * 2) for n in T.nodes]
+    e = np.array([bptr[r] + np.searchsorted(bind[bptr[r]:bptr[r + 1]], c) for r, c in zip(Ac.row // 2, Ac.col // 2)], dtype=np.int64)
+    for v, r, c, k in zip(Ac.data, Ac.row, Ac.col, e):
+        F[T.entry_node[k]][2 * T.entry_row[k] + r % 2, 2 * T.entry_col[k] + c % 2] += v
+    dof = lambda t: np.stack([2 * t, 2 * t + 1], axis=1).ravel().astype(np.int64)
+    X, F12, F21 = {}, {}, {}
+    for i, n in enumerate(T.nodes):
+        ns = 2 * n.sep.size
+        X[i] = np.linalg.inv(F[i][:ns, :ns])
+        F12[i], F21[i] = F[i][:ns, ns:], F[i][ns:, :ns]
+        if n.parent >= 0:
+            m = dof(n.up.astype(np.int64))
+            F[n.parent][np.ix_(m, m)] += F[i][ns:, ns:] - F21[i] @ (X[i] @ F12[i])
+    x, z = b.astype(float).copy(), {}
+    for i, n in enumerate(T.nodes):
+        z[i] = X[i] @ x[dof(n.sep)]
+        x[dof(n.bnd)] -= F21[i] @ z[i]
+    for i in range(len(T.nodes) - 1, -1, -1):
+        n = T.nodes[i]
+        x[dof(n.sep)] = z[i] - X[i] @ (F12[i] @ x[dof(n.bnd)])
+    return x
+
+
+@pytest.mark.parametrize("case", ["single_triangle", "one_leaf", "two_components", "long_range_couplings", "unsymmetric_pattern",
+                                  "coincident_centroids"])
+def test_nd_symbolic_analysis_edge_cases(case):
+    """Patterns that are not meshes: a 1-triangle system, a tree that is a single leaf, a disconnected graph, random
+    far couplings (what periodic BC rows produce), a structurally unsymmetric pattern (BC rows reference neighbours that
+    do not reference them back) and coincident centroids (degenerate bisection) -- every one must give maps that solve
+    the system exactly."""
+    import scipy.sparse as sp
+    from ufemism2_0_b200 import nd
+    rng = np.random.default_rng(11)
+    nT, leaf = {"single_triangle": (1, 4), "one_leaf": (7, 8), "two_components": (60, 6), "long_range_couplings": (150, 8),
+                "unsymmetric_pattern": (120, 8), "coincident_centroids": (40, 4)}[case]
+    gc = rng.uniform(0, 1, (nT, 2))
+    if case == "coincident_centroids":
+        gc[:] = 0.5
+    # block pattern: k nearest neighbours in the plane (+ extras), always with the diagonal
+    d = ((gc[:, None, :] - gc[None, :, :]) ** 2).sum(-1)
+    k = min(nT, 6)
+    nb = np.argsort(d, axis=1, kind="stable")[:, :k]
+    rows, cols = np.repeat(np.arange(nT), k), nb.ravel()
+    if case == "two_components":
+        half = nT // 2
+        keep = (rows < half) == (cols < half)
+        rows, cols = rows[keep], cols[keep]
+    if case == "long_range_couplings":
+        extra = rng.integers(0, nT, (30, 2))
+        rows, cols = np.concatenate([rows, extra[:, 0]]), np.concatenate([cols, extra[:, 1]])
+    if case != "unsymmetric_pattern":
+        rows, cols = np.concatenate([rows, cols]), np.concatenate([cols, rows])
+    rows, cols = np.concatenate([rows, np.arange(nT)]), np.concatenate([cols, np.arange(nT)])
+    B = sp.csr_matrix((np.ones(rows.size), (rows, cols)), shape=(nT, nT)); B.sum_duplicates(); B.sort_indices()
+    bptr, bind = B.indptr.astype(np.int32), B.indices.astype(np.int32)
+    # scalar matrix: random 2x2 blocks on the pattern, diagonally dominant
+    Bc = B.tocoo()
+    r2 = (2 * Bc.row[:, None] + np.array([0, 0, 1, 1])[None, :]).ravel()
+    c2 = (2 * Bc.col[:, None] + np.array([0, 1, 0, 1])[None, :]).ravel()
+    A = sp.csr_matrix((rng.standard_normal(r2.size), (r2, c2)), shape=(2 * nT, 2 * nT))
+    A = (A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)).tocsr()
+    b = rng.standard_normal(2 * nT)
+    T = nd.analyse(gc, bptr, bind, leaf)
+    assert np.array_equal(np.sort(np.concatenate([n.sep for n in T.nodes])), np.arange(nT))
+    assert T.nodes[-1].parent == -1 and T.nodes[-1].bnd.size == 0
+    if case in ("single_triangle", "one_leaf", "coincident_centroids"):
+        assert len(T.nodes) == 1 and T.n_levels == 1
+    # the scalar pattern of A has exactly the analysed block pattern
+    b2ptr, b2ind = nd.block_pattern(A.indptr, A.indices, nT)
+    assert np.array_equal(b2ptr, bptr) and np.array_equal(b2ind, bind)
+    x = _multifrontal_solve_from_maps(T, A, b, bptr, bind)
+    assert np.linalg.norm(A @ x - b) <= 1e-12 * np.linalg.norm(b)
+
+
+def test_nd_analyse_rejects_bad_arguments():
+    from ufemism2_0_b200 import nd
+    from ufemism2_0_b200.capi import UfeError
+    gc = np.zeros((3, 2))
+    with pytest.raises(UfeError):
+        nd.analyse(gc, np.array([0, 1, 2, 3], dtype=np.int32), np.array([0, 1, 7], dtype=np.int32), 4)     # column out of range
+    with pytest.raises(UfeError):
+        nd.analyse(gc, np.array([0, 1, 2, 3], dtype=np.int32), np.array([0, 1, 2], dtype=np.int32), 0)     # leaf size < 1
