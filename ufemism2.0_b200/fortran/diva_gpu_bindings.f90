@@ -139,6 +139,49 @@ module diva_gpu_bindings
       integer(c_int32_t), intent(out)   :: n_its, flags
     end function ufe_krylov_solve
 
+    ! exact multifrontal nested-dissection solver for the b-grid (u,v) systems (csrc/ufe_nd.cu, ufe_nd_numeric.cu):
+    ! analyse + create once per mesh, factor + solve per Picard iteration; also reachable as cfg%krylov_pc = 4 (nd_lu)
+    integer(c_int) function ufe_nd_analyse( nT, gcx, gcy, bptr, bind_, leaf_triangles, tree) bind(C, name='ufe_nd_analyse')
+      import :: c_int, c_int32_t, c_double, c_ptr
+      integer(c_int32_t), value       :: nT, leaf_triangles
+      real(c_double),     intent(in)  :: gcx(*), gcy(*)          ! mesh%TriGC(:,1), mesh%TriGC(:,2)
+      integer(c_int32_t), intent(in)  :: bptr(*), bind_(*)       ! 0-based block pattern over triangles
+      type(c_ptr),        intent(out) :: tree
+    end function ufe_nd_analyse
+
+    subroutine ufe_nd_tree_free( tree) bind(C, name='ufe_nd_tree_free')
+      import :: c_ptr
+      type(c_ptr), value :: tree
+    end subroutine ufe_nd_tree_free
+
+    integer(c_int) function ufe_nd_solver_create( tree, N, ptr, ind, solver) bind(C, name='ufe_nd_solver_create')
+      import :: c_int, c_int32_t, c_ptr
+      type(c_ptr),        value       :: tree
+      integer(c_int32_t), value       :: N
+      integer(c_int32_t), intent(in)  :: ptr(*), ind(*)          ! A_CSR%ptr - 1, A_CSR%ind - 1
+      type(c_ptr),        intent(out) :: solver
+    end function ufe_nd_solver_create
+
+    integer(c_int) function ufe_nd_solver_factor( solver, val) bind(C, name='ufe_nd_solver_factor')
+      import :: c_int, c_double, c_ptr
+      type(c_ptr),    value      :: solver
+      real(c_double), intent(in) :: val(*)                       ! A_CSR%val
+    end function ufe_nd_solver_factor
+
+    integer(c_int) function ufe_nd_solver_solve( solver, b, x, n_refine, relres) bind(C, name='ufe_nd_solver_solve')
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr),        value       :: solver
+      real(c_double),     intent(in)  :: b(*)
+      real(c_double),     intent(out) :: x(*)
+      integer(c_int32_t), value       :: n_refine
+      real(c_double),     intent(out) :: relres
+    end function ufe_nd_solver_solve
+
+    subroutine ufe_nd_solver_free( solver) bind(C, name='ufe_nd_solver_free')
+      import :: c_ptr
+      type(c_ptr), value :: solver
+    end subroutine ufe_nd_solver_free
+
     ! multiply_CSR_matrix_with_vector_1D / _2D (CSR_matrix_vector_multiplication.f90:198,336)
     integer(c_int) function ufe_spmv( A, x, y, nlayers) bind(C, name='ufe_spmv')
       import :: c_int, c_int32_t, c_double, ufe_csr
