@@ -491,14 +491,14 @@ def test_calc_secondary_velocities(homA, oracle):
 
 def test_two_rank_nccl_solve_if_two_gpus():
     """Strip partition over two GPUs (halo exchange + all-reduces over NCCL, replicated exact
-    preconditioner); runs tools/multi_gpu_check.py under torchrun.  Skipped on one-GPU boxes."""
+    preconditioner); runs tests/tools/multi_gpu_check.py under torchrun.  Skipped on one-GPU boxes."""
     import os, subprocess, sys
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "multi_gpu_check.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "tools", "multi_gpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 

@@ -209,8 +209,8 @@ def test_workload_configs_equal_the_reference_cfg_files(cfg_file, make):
 
 
 def test_nested_dissection_prototype_solves_the_stiffness_system():
-    """tools/nd_prototype.py (round-2 planning prototype of the multifrontal solver): exact solve on a small MISMIP+ mesh."""
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "nd_prototype.py"), "mismipplus:16000", "24"],
+    """tests/tools/nd_prototype.py (round-2 planning prototype of the multifrontal solver): exact solve on a small MISMIP+ mesh."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "nd_prototype.py"), "mismipplus:16000", "24"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     m = re.search(r"residual ([0-9.e+-]+) \| x vs SuperLU ([0-9.e+-]+)", out.stdout)

@@ -1,6 +1,6 @@
 """bjacobi_lu preconditioner on a GPU box: convergence and parity (prints)."""
 import sys, os, copy, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import numpy as np
 import ufe_pkg; ufe_pkg.load()

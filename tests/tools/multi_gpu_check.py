@@ -1,7 +1,7 @@
-"""torchrun --nproc-per-node N tools/multi_gpu_check.py : N-rank solves (strip partition by
+"""torchrun --nproc-per-node N tests/tools/multi_gpu_check.py : N-rank solves (strip partition by
 partition_list, halo exchange + allreduce over NCCL) compared on rank 0 with the oracle."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import numpy as np
 import torch, torch.distributed as dist

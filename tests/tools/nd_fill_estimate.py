@@ -4,7 +4,7 @@ triangles whose 2-ring stencil crosses the cut), for the synthetic Antarctic-sha
 Prints nnz(L+U), the implied bytes, and the flop count from the column counts, next to the banded (x-sorted)
 ordering that bjacobi_lu uses today."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
 import ufe_pkg; ufe_pkg.load()

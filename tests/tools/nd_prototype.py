@@ -4,10 +4,10 @@ tree level processed as one batch (padded to the level's largest front), extend-
 mesh.  Verifies the solve against scipy on real stiffness matrices (values from the oracle's first Picard iteration)
 and prints, per tree level, the number of fronts, their sizes, the padded bytes and the dense flops.
 
-    python tools/nd_prototype.py mismipplus:4000 | antarctic:<nV> [leaf_triangles]
+    python tests/tools/nd_prototype.py mismipplus:4000 | antarctic:<nV> [leaf_triangles]
 """
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
 import ufe_pkg; ufe_pkg.load()
