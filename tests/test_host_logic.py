@@ -115,6 +115,11 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in txt and "ufe_oracle" not in txt and "oracle/" not in txt, f
+    # tools/ is oracle-free as well (the checker scripts that use the oracle live in tests/tools/)
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            txt = open(os.path.join(ROOT, "tools", f), errors="replace").read()
+            assert "import oracle" not in txt and "ufe_oracle" not in txt and "'oracle'" not in txt and '"oracle"' not in txt, f
 
 
 GLOO_WORKER = r'''
