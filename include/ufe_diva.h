@@ -391,12 +391,13 @@ void ufe_nd_tree_free(ufe_nd_tree *T);
 
 /* Numeric phase on the device (csrc/ufe_nd_numeric.cu): exact solve of A x = b, the system the reference hands to
  * PETSc at solve_linearised_SSA_DIVA.f90:159 (petsc_basic.f90:32-64), by a multifrontal factorisation over the tree --
- * one batch of padded dense fronts per tree level, blocked Gauss-Jordan sweep of the pivot rows, extend-add of the
- * Schur complements in a fixed order.  ptr / ind / val: scalar CSR of A, 0-based, N = 2 nTri rows, whose block pattern
- * is the analysed one; host arrays, borrowed for the call.  `factor` may be called again with new values (same
- * pattern: one analysis per mesh, one factorisation per Picard iteration); `solve` returns x = A^-1 b after n_refine
- * steps of iterative refinement with the unscaled matrix and the relative residual |b - A x| / |b|.  No CPU fallback:
- * create fails with UFE_ERR_CUDA without a device. */
+ * one dense front per tree node with its own shape, right-looking block LU (32-wide pivot blocks, 64-wide trailing
+ * updates), Schur complements pulled into the parents in a fixed order.  ptr / ind / val: scalar CSR of A in the
+ * reference's own convention (type_sparse_matrix_CSR_dp, CSR_sparse_matrix_type.f90:15-38: ptr(1) = 1, 1-based column
+ * indices), N = 2 nTri rows, whose block pattern is the analysed one; host arrays, borrowed for the call.  `factor` may
+ * be called again with new values (same pattern: one analysis per mesh, one factorisation per Picard iteration);
+ * `solve` returns x = A^-1 b after n_refine steps of iterative refinement with the unscaled matrix and the relative
+ * residual |b - A x| / |b|.  No CPU fallback: create fails with UFE_ERR_CUDA without a device. */
 typedef struct ufe_nd_solver ufe_nd_solver;
 int ufe_nd_solver_create(const ufe_nd_tree *T, int32_t N, const int32_t *ptr, const int32_t *ind, ufe_nd_solver **out);
 int ufe_nd_solver_factor(ufe_nd_solver *S, const double *val);

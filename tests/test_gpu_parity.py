@@ -603,7 +603,7 @@ def test_nd_multifrontal_solver_matches_sparse_LU(workload, leaf):
     ptr, ind = (A.ptr - 1).astype(np.int32), (A.ind - 1).astype(np.int32)
     M = sp.csr_matrix((A.val, ind, ptr), shape=(N, N))
     xr = spla.splu(M.tocsc()).solve(bb)
-    sol = nd.Solver(np.asarray(mesh.TriGC), ptr, ind, leaf)
+    sol = nd.Solver(np.asarray(mesh.TriGC), A.ptr, A.ind, leaf)     # the reference's 1-based arrays, as the C ABI takes them
     try:
         sol.factor(A.val)
         x0, r0 = sol.solve(bb, n_refine=0)

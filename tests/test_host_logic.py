@@ -305,7 +305,7 @@ def test_nd_solver_fails_loudly_without_a_device():
     ptr = np.arange(0, 4 * nT + 1, 2, dtype=np.int32)
     if not torch.cuda.is_available():
         with pytest.raises(UfeError) as e:
-            nd.Solver(gc, ptr, cols.astype(np.int32), 8)
+            nd.Solver(gc, ptr + 1, cols.astype(np.int32) + 1, 8)      # 1-based, like type_sparse_matrix_CSR_dp
         assert e.value.code == 2 and "no CPU fallback" in str(e.value)
     bptr, bind = nd.block_pattern(ptr, cols, nT)
     assert np.array_equal(bptr, np.arange(nT + 1)) and np.array_equal(bind, np.arange(nT))

@@ -20,8 +20,7 @@ for nV in sizes:
     A, bb = S.get_stiffness_matrix()
     S.close()
     N = 2 * mesh.nTri
-    ptr, ind = (A.ptr - 1).astype(np.int32), (A.ind - 1).astype(np.int32)
-    t = time.time(); sol = nd.Solver(np.asarray(mesh.TriGC), ptr, ind, leaf); t_sym = time.time() - t
+    t = time.time(); sol = nd.Solver(np.asarray(mesh.TriGC), A.ptr, A.ind, leaf); t_sym = time.time() - t
     sol.factor(A.val); sol.factor(A.val)
     f_ms = sol.info()["factor_ms"]
     out = {"nV": mesh.nV, "unknowns": N, "leaf_triangles": leaf, "symbolic_host_s": t_sym}

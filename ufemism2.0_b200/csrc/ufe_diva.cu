@@ -698,30 +698,43 @@ static int linearised_resident(ufe_handle *h, double rtol, double abstol, int *n
   PcLU *pc = nullptr;
   if (h->pc_used < 0) {                               // once per cached pattern
     h->pc_used = h->cfg.krylov_pc;
-    if (h->cfg.krylov_pc == UFE_PC_BJACOBI_LU || h->cfg.krylov_pc == UFE_PC_AUTO) {
-      const size_t budget = h->cfg.krylov_pc == UFE_PC_AUTO ? (size_t)24 << 30 : (size_t)100 << 30;
+    const double *gcx = h->hGC.data(), *gcy = h->hGC.data() + h->dm.nTri;
+    const bool pow2 = (h->comm.nranks & (h->comm.nranks - 1)) == 0;
+    if (h->cfg.krylov_pc == UFE_PC_AUTO) {
+      // auto: the multifrontal nested-dissection factorisation (exact, any mesh shape, 1 / 2 / 4 / 8 ranks) when its
+      // fronts fit; else the banded exact block solve; else 2x2 block Jacobi.  UFE_AUTO_ND=0 skips the first choice.
+      // The choice made is reported in ufe_solve_info.krylov_pc_used.
+      const char *e = getenv("UFE_AUTO_ND");
       int rc = UFE_ERR_INVALID;
-      if (h->comm.nranks > 1 && !h->cfg.krylov_pc_strip_only) {      // replicated exact solve when the whole system fits
+      if (!(e && atoi(e) == 0) && pow2 && !h->cfg.krylov_pc_strip_only) {
+        rc = ufe_pclu_setup_nd(h->st, h->S, &h->comm, h->dm.nTri, gcx, gcy, &h->pclu);
+        if (rc == UFE_ERR_CUDA) return rc;
+        if (rc == UFE_OK) h->pc_used = UFE_PC_ND_LU; else h->pclu = nullptr;
+      }
+      if (rc != UFE_OK) {
+        if (h->comm.nranks > 1 && !h->cfg.krylov_pc_strip_only) {      // replicated exact solve when the whole system fits
+          HaloPlan all = h->plan_b_for_b;
+          for (int q = 0; q < all.nranks; q++) { all.need_lo[q] = 0; all.need_hi[q] = h->dm.nTri; }
+          rc = ufe_pclu_setup(h->st, h->S, 1, (size_t)24 << 30, &h->pclu, &h->comm, &all);
+          if (rc == UFE_ERR_CUDA) return rc;
+        }
+        if (rc != UFE_OK) rc = ufe_pclu_setup(h->st, h->S, 0, (size_t)24 << 30, &h->pclu);
+        if (rc == UFE_ERR_CUDA) return rc;
+        h->pc_used = rc == UFE_OK ? UFE_PC_BJACOBI_LU : UFE_PC_BJACOBI2;
+      }
+    } else if (h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) {
+      int rc = UFE_ERR_INVALID;
+      if (h->comm.nranks > 1 && !h->cfg.krylov_pc_strip_only) {
         HaloPlan all = h->plan_b_for_b;
         for (int q = 0; q < all.nranks; q++) { all.need_lo[q] = 0; all.need_hi[q] = h->dm.nTri; }
         rc = ufe_pclu_setup(h->st, h->S, 1, (size_t)24 << 30, &h->pclu, &h->comm, &all);
         if (rc == UFE_ERR_CUDA) return rc;
       }
-      if (rc != UFE_OK) rc = ufe_pclu_setup(h->st, h->S, 0, budget, &h->pclu);
-      if (rc == UFE_ERR_CUDA) return rc;
-      if (rc != UFE_OK && h->cfg.krylov_pc == UFE_PC_BJACOBI_LU) return rc;
-      h->pc_used = rc == UFE_OK ? UFE_PC_BJACOBI_LU : UFE_PC_BJACOBI2;
-      // auto on a wide mesh (the banded blocks do not fit): the multifrontal solver when its fronts fit this GPU,
-      // else 2x2 block Jacobi as before.  UFE_AUTO_ND=0 keeps the old behaviour.
-      const char *e = getenv("UFE_AUTO_ND");
-      if (rc != UFE_OK && h->comm.nranks == 1 && !(e && atoi(e) == 0)) {
-        const int rc2 = ufe_pclu_setup_nd(h->st, h->S, h->dm.nTri, h->hGC.data(), h->hGC.data() + h->dm.nTri, &h->pclu);
-        if (rc2 == UFE_OK) h->pc_used = UFE_PC_ND_LU;
-        else { cudaGetLastError(); h->pclu = nullptr; }
-      }
-    } else if (h->cfg.krylov_pc == UFE_PC_ND_LU) {    // wide meshes: multifrontal nested dissection, one analysis per pattern
-      if (h->comm.nranks > 1) { h->pc_used = -1; ufe_set_error("krylov_pc nd_lu: one GPU only (the fronts are not distributed yet)"); return UFE_ERR_INVALID; }
-      const int rc = ufe_pclu_setup_nd(h->st, h->S, h->dm.nTri, h->hGC.data(), h->hGC.data() + h->dm.nTri, &h->pclu);
+      if (rc != UFE_OK) rc = ufe_pclu_setup(h->st, h->S, 0, (size_t)100 << 30, &h->pclu);
+      if (rc != UFE_OK) { h->pc_used = -1; return rc; }
+    } else if (h->cfg.krylov_pc == UFE_PC_ND_LU) {    // multifrontal nested dissection, one analysis per pattern
+      if (!pow2) { h->pc_used = -1; ufe_set_error("krylov_pc nd_lu: the number of ranks must be 1, 2, 4 or 8"); return UFE_ERR_INVALID; }
+      const int rc = ufe_pclu_setup_nd(h->st, h->S, &h->comm, h->dm.nTri, gcx, gcy, &h->pclu);
       if (rc != UFE_OK) { h->pc_used = -1; return rc; }
     }
   }

@@ -166,8 +166,9 @@ int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc);
 int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z);
 void ufe_pclu_free(PcLU *pc);
 // multifrontal nested-dissection solver as the exact preconditioner (ufe_nd_numeric.cu; krylov_pc = UFE_PC_ND_LU)
-int ufe_pclu_setup_nd(cudaStream_t st, const DevSystem &S, int nT, const double *gcx, const double *gcy, PcLU **out);
-int ufe_nd_pc_create(cudaStream_t st, const DevSystem &S, int nT, const double *gcx, const double *gcy, int leaf, ufe_nd_solver **out);
+int ufe_pclu_setup_nd(cudaStream_t st, const DevSystem &S, const Comm *comm, int nT, const double *gcx, const double *gcy, PcLU **out);
+int ufe_nd_pc_create(cudaStream_t st, const DevSystem &S, const Comm *comm, int nT, const double *gcx, const double *gcy, int leaf, ufe_nd_solver **out);
+void ufe_nd_pc_info(const ufe_nd_solver *S, double *front_bytes, double *flops, int *n_fronts);
 int ufe_nd_pc_factor(cudaStream_t st, ufe_nd_solver *S, const double *dval);
 int ufe_nd_pc_apply(cudaStream_t st, ufe_nd_solver *S, const double *r, double *z);
 int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm,

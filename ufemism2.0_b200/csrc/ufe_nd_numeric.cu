@@ -1,100 +1,176 @@
 // Numeric phase of the multifrontal nested-dissection solver (device code).
 //
 // Exact solve of the DIVA / SSA stiffness system  A x = b  (solve_linearised_SSA_DIVA.f90:159 hands exactly this
-// system to PETSc) for meshes whose x-sorted bandwidth is too wide for the banded block cyclic reduction of
-// ufe_pclu.cu.  The symbolic analysis (ufe_nd.cu) gives a binary elimination tree; every tree node owns one dense
-// front  [sep; bnd] x [sep; bnd]  (scalar unknowns: triangle t -> 2t, 2t+1, mesh_translation_tables.f90:181-198).
+// system to PETSc, petsc_basic.f90:32-141).  The symbolic analysis (ufe_nd.cu) gives a binary elimination tree; every
+// tree node owns one dense front  [sep; bnd] x [sep; bnd]  (scalar unknowns: triangle t -> 2t, 2t+1,
+// mesh_translation_tables.f90:181-198).
 //
-// Layout in HBM.  All fronts of one tree level are stored as ONE batch of row-major g_l x g_l matrices, g_l and the
-// pivot extent p_l being the level maxima rounded to 64 / 32:
-//      rows [0, p_l)   : the front's own unknowns (sep), padded with identity rows,
-//      rows [p_l, g_l) : the boundary unknowns (bnd), padded with zero rows,
-// so a level is a handful of batched launches (blockIdx.z = front) with no per-front shapes in the kernels.
+// Layout in HBM.  Every front has its OWN shape: p = its pivot count rounded up to 32 (identity-padded), nb boundary
+// unknowns, G = p + nb rows, leading dimension ld = G rounded up to 8; fronts of one tree level are stored back to
+// back, sorted by p (descending) so that the fronts still active at pivot step b form a prefix of the level.
 //
-// Factorisation, deepest level first.  A blocked in-place Gauss-Jordan sweep over the pivot blocks of [0, p_l) only
-// (32-wide panels, partial pivoting inside the 32 x 32 pivot block) leaves, with X = F11^-1,
-//      F11 <- X,    F12 <- X F12,    F21 <- -F21 X,    F22 <- F22 - F21 X F12   (the Schur complement),
-// and F22 is then added into the parent's front through the child -> parent index map (child slot 0, then slot 1:
-// the sums have a fixed order, so the factors are bit-reproducible).
-// Solve.  Every front has a work vector w (length g_l):  up the tree  y = F[:, 0:p] w_s;  z = y_s is kept,
-// w_b += y_b goes to the parent's w; down the tree  x_b comes from the parent,  x_s = z - F12' x_b.
+// Factorisation, deepest level first: right-looking block LU of the first p rows / columns, 32-wide pivot blocks,
+//      D_b^-1 (32 x 32 inverse, partial pivoting inside the block; kept in a side buffer),
+//      L_ib = A_ib D_b^-1  (i > b: later pivot rows AND the boundary rows),        [k_mf_panel]
+//      A_ij -= L_ib A_bj   (i, j > b; 128 x 128 tiles, 8 x 8 per thread, K = 32)   [k_mf_update]
+// which leaves L, U in place and the Schur complement in the boundary block; the parent PULLS the Schur complements of
+// its two children through inverse index maps (child 0 then child 1: fixed summation order, bit-reproducible). [k_mf_extend]
+// Solve: one CTA per front and one launch per level and direction: forward  y = L^-1 w  (boundary rows collect the
+// update for the parent, which pulls them), backward  x_s = U11^-1 (y - U12 x_b)  with x_b read from the parent.
+//
+// Several GPUs (one rank per GPU): rank r owns the sub-tree below the r-th node of level log2(P) and the nodes above it
+// on its left spine (root: rank 0; level 1: ranks 0, P/2; ...).  A child owned by another rank sends its packed Schur
+// complement (factorisation) and its boundary vector (forward sweep) to the parent's owner and receives the parent's
+// solution vector (backward sweep): ncclSend / ncclRecv, log2(P) exchanges per sweep.  The matrix values are
+// all-gathered per factorisation, the right-hand side per application; the solution is combined by one all-reduce
+// (every unknown has exactly one non-zero contribution).
 // The matrix is Jacobi-scaled symmetrically while it is assembled into the fronts (unit-magnitude diagonal, so the
 // pivot thresholds are scale-free); ufe_nd_solver_solve applies steps of iterative refinement with the unscaled CSR.
 #include "ufe_internal.cuh"
 #include "ufe_nd.cuh"
 
 #include <algorithm>
+#include <numeric>
 
-#define NDB 32    // pivot panel width
-#define NDT 64    // trailing-update tile
+#define MFB 32    // pivot block width
 
-struct NdLevelDev {
-  int n = 0, g = 0, p = 0, first = 0;   // fronts, padded front size, padded pivot extent, index of the level's first front
-  int max_nb = 0;                       // largest boundary (scalars) in the level
-  size_t f_off = 0, w_off = 0;          // offsets (doubles) of the level's batch in F and in W / Z
+struct MfStep { int n_active, max_trail; };
+struct MfLevel {
+  int n = 0, first = 0, steps = 0, maxG = 0, n_internal = 0, max_nb = 0;
+  std::vector<MfStep> step;
+};
+// one NCCL exchange between a child-1 front (owned by `peer_child`) and its parent (owned by `peer_parent`)
+struct MfLink {
+  int level;                 // level of the parent
+  int child_rank, parent_rank;
+  int child_front, parent_front;    // local front ids (valid on the owning rank only, else -1)
+  int nb, Gp;                       // child's boundary size, parent's front size
+  long long f_buf;                  // child side: packed send buffer in F; parent side: receive buffer in F (ld = nb)
+  int w_buf;                        // parent side: receive buffer in W (nb doubles); child side: buffer for the parent's w (Gp doubles)
+  long long child_schur = -1;       // child side: offset of the Schur block in F, its row stride, offset of the boundary vector in W
+  int child_ld = 0, child_wb = -1;
+  int parent_w = -1;                // parent side: offset of the parent's vector in W
 };
 
+struct MfGraph { const void *a = nullptr, *b = nullptr; int k0 = 0, k1 = 0; cudaGraphExec_t exec = nullptr; int nodes = 0; };
+
 struct ufe_nd_solver {
-  int nT = 0, N = 0, nnz = 0, n_fronts = 0;
-  std::vector<NdLevelDev> lev;
-  int *ns = nullptr, *nb = nullptr, *parent = nullptr, *slot = nullptr;   // per front (level-major order)
-  int *sep_off = nullptr, *up_off = nullptr;                              // per front: offsets into sepdof / upmap
+  int nT = 0, N = 0, nnz = 0, n_fronts = 0;       // n_fronts: fronts owned by this rank
+  int rank = 0, nranks = 1;
+  ncclComm_t nccl = nullptr;
+  std::vector<MfLevel> lev;
+  std::vector<MfLink> links;
+  // per local front (level-major order, p descending inside a level)
+  int *ns = nullptr, *p = nullptr, *nb = nullptr, *G = nullptr, *ld = nullptr, *woff = nullptr, *dioff = nullptr,
+      *sep_off = nullptr, *up_off = nullptr, *pwoff = nullptr;
+  long long *foff = nullptr;
+  // children as the extend-add / forward sweep see them: offset of the child's Schur block in F and its row stride,
+  // offset of the child's boundary vector in W; -1 = no child
+  long long *c_f[2] = {nullptr, nullptr};
+  int *c_ld[2] = {nullptr, nullptr}, *c_w[2] = {nullptr, nullptr};
+  int *pinv[2] = {nullptr, nullptr};         // per front row (indexed like W): row of child 0 / 1's boundary, or -1
   int *sepdof = nullptr, *upmap = nullptr;   // global unknown of every sep row; parent row of every bnd row
-  long long *dst = nullptr;                  // per scalar CSR entry: destination in F
-  int *ptr = nullptr, *ind = nullptr;        // 0-based scalar CSR of A
-  double *val = nullptr, *scale = nullptr, *dself = nullptr, *dpair = nullptr;
-  double *F = nullptr, *W = nullptr, *Z = nullptr, *ipp = nullptr, *colbuf = nullptr;
-  double *b = nullptr, *x = nullptr, *r = nullptr, *dx = nullptr;
-  size_t f_doubles = 0, w_doubles = 0;
+  long long *dst = nullptr;                  // per scalar CSR entry: destination in F, -1 = another rank's front
+  int *ptr = nullptr, *ind = nullptr;        // 1-based scalar CSR of the WHOLE matrix (ptr offsets 1-based)
+  bool own_pattern = false;                  // ptr / ind allocated here (else they alias the caller's device arrays)
+  double *val = nullptr;                     // whole-matrix values (standalone solver / several ranks), else nullptr
+  double *scale = nullptr, *dself = nullptr, *dpair = nullptr;
+  double *F = nullptr, *W = nullptr, *Dinv = nullptr;
+  double *b = nullptr, *x = nullptr, *r = nullptr;     // full-length work vectors
+  size_t f_doubles = 0, w_doubles = 0, di_blocks = 0;
+  std::vector<size_t> val_counts, row_counts;          // several ranks: per-rank nnz and row counts (strips)
   cudaStream_t st = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   float factor_ms = 0.f, solve_ms = 0.f;
   double flops = 0.0;
   bool factored = false;
+  int use_graphs = 1, k64 = 1;
+  MfGraph g_factor, g_apply[6];
 };
 
 // ------------------------------------------------------------------------------------------------------------------
 // assembly
 // ------------------------------------------------------------------------------------------------------------------
 // also keeps row i of the 2x2 (u,v) diagonal block of its triangle: dself = a_ii, dpair = a_i,i^1
-__global__ void k_nd_scale(int N, const int *__restrict__ ptr, const int *__restrict__ ind, const double *__restrict__ val,
+__global__ void k_mf_scale(int N, const int *__restrict__ ptr, const int *__restrict__ ind, const double *__restrict__ val,
                            double *__restrict__ scale, double *__restrict__ dself, double *__restrict__ dpair) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double d = 0.0, o = 0.0;
-  for (int k = ptr[i]; k < ptr[i + 1]; k++) { if (ind[k] == i) d += val[k]; else if (ind[k] == (i ^ 1)) o += val[k]; }
+  for (int k = ptr[i] - 1; k < ptr[i + 1] - 1; k++) { const int j = ind[k] - 1; if (j == i) d += val[k]; else if (j == (i ^ 1)) o += val[k]; }
   dself[i] = d; dpair[i] = o;
   d = fabs(d);
   scale[i] = d > 0.0 ? 1.0 / sqrt(d) : 1.0;
 }
 
 // one thread per matrix row: every (row, column) has its own destination, so plain adds are race-free
-__global__ void k_nd_assemble(int N, const int *__restrict__ ptr, const int *__restrict__ ind, const double *__restrict__ val,
+__global__ void k_mf_assemble(int N, const int *__restrict__ ptr, const int *__restrict__ ind, const double *__restrict__ val,
                               const double *__restrict__ scale, const long long *__restrict__ dst, double *__restrict__ F) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const double si = scale[i];
-  for (int k = ptr[i]; k < ptr[i + 1]; k++) F[dst[k]] += si * val[k] * scale[ind[k]];
+  for (int k = ptr[i] - 1; k < ptr[i + 1] - 1; k++) {
+    const long long d = dst[k];
+    if (d >= 0) F[d] += si * val[k] * scale[ind[k] - 1];
+  }
 }
 
-// identity on the padded pivot rows [ns, p) of every front of a level
-__global__ void k_nd_pad_identity(int g, int p, int first, const int *__restrict__ ns, double *__restrict__ Fl) {
-  const int z = blockIdx.y, r = ns[first + z] + blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < p) Fl[(size_t)z * g * g + (size_t)r * g + r] = 1.0;
+// identity on the padded pivot rows [ns, p) of every front
+__global__ void k_mf_pad(int nf, const int *__restrict__ ns, const int *__restrict__ p, const int *__restrict__ ld,
+                         const long long *__restrict__ foff, double *__restrict__ F) {
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (f >= nf) return;
+  const int r = ns[f] + lane;
+  if (r < p[f]) F[foff[f] + (size_t)r * ld[f] + r] = 1.0;
+}
+
+// parent front += Schur complements of its children (pull through the inverse maps; child 0 first, then child 1)
+__global__ void __launch_bounds__(256)
+k_mf_extend(int first, const int *__restrict__ G_, const int *__restrict__ ld_, const long long *__restrict__ foff,
+            const int *__restrict__ woff, const long long *__restrict__ cf0, const long long *__restrict__ cf1,
+            const int *__restrict__ cld0, const int *__restrict__ cld1, const int *__restrict__ pinv0,
+            const int *__restrict__ pinv1, double *__restrict__ F) {
+  const int f = first + blockIdx.z;
+  const long long o0 = cf0[f], o1 = cf1[f];
+  if (o0 < 0 && o1 < 0) return;
+  const int G = G_[f], ld = ld_[f];
+  const int i0 = blockIdx.y * 32, j = blockIdx.x * 32 + threadIdx.x;
+  if (i0 >= G || j >= G) return;
+  const int *q0 = pinv0 + woff[f], *q1 = pinv1 + woff[f];
+  const int b0 = o0 >= 0 ? q0[j] : -1, b1 = o1 >= 0 ? q1[j] : -1;
+  if (b0 < 0 && b1 < 0) return;
+  const int l0 = cld0[f], l1 = cld1[f];
+  double *A = F + foff[f];
+  for (int ii = threadIdx.y; ii < 32; ii += 8) {
+    const int i = i0 + ii;
+    if (i >= G) break;
+    double v = 0.0;
+    bool any = false;
+    if (b0 >= 0) { const int a0 = q0[i]; if (a0 >= 0) { v += F[o0 + (size_t)a0 * l0 + b0]; any = true; } }
+    if (b1 >= 0) { const int a1 = q1[i]; if (a1 >= 0) { v += F[o1 + (size_t)a1 * l1 + b1]; any = true; } }
+    if (any) A[(size_t)i * ld + j] += v;
+  }
+}
+
+// Schur block of a front -> contiguous nb x nb buffer (row stride nb) for the transfer to the parent's rank
+__global__ void k_mf_pack(int nb, int ld, const double *__restrict__ src, double *__restrict__ dst) {
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  if (j >= nb) return;
+  for (int i = blockIdx.y * 32 + threadIdx.y; i < min(nb, (int)blockIdx.y * 32 + 32); i += 8) dst[(size_t)i * nb + j] = src[(size_t)i * ld + j];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// partial Gauss-Jordan sweep of a level's fronts
+// factorisation kernels
 // ------------------------------------------------------------------------------------------------------------------
 // 32 x 32 inverse in shared memory by 1024 threads (i, j): Gauss-Jordan on [S | I2], partial pivoting as a row
 // permutation, searched only when the natural pivot is small (the fronts are Jacobi-scaled); vanishing pivots are
 // perturbed statically -- the refinement / Krylov iteration around the solver absorbs that.
-__device__ __forceinline__ void nd_invert32(double (*S)[NDB + 1], double (*I2)[NDB + 1], double (*Ip)[NDB + 1], int *perm,
+__device__ __forceinline__ void mf_invert32(double (*S)[MFB + 1], double (*I2)[MFB + 1], double (*Ip)[MFB + 1], int *perm,
                                             int i, int j) {
   I2[i][j] = (i == j) ? 1.0 : 0.0;
   if (i == 0) perm[j] = j;
   __syncthreads();
-  for (int p = 0; p < NDB; p++) {
+  for (int p = 0; p < MFB; p++) {
     if (fabs(S[perm[p]][p]) < 0.05) {
       __syncthreads();
       if (i == 0) {
@@ -124,373 +200,668 @@ __device__ __forceinline__ void nd_invert32(double (*S)[NDB + 1], double (*I2)[N
   __syncthreads();
 }
 
-// panel step for pivot block b; every CTA inverts A_PP itself (A_PP is not written here).
-//   y = 0, tile (P, J = x):  A_PJ <- Ipp A_PJ        (x == b: publish Ipp for the update kernel)
-//   y = 1, tile (I = x, P):  colbuf <- A_IP (old),  A_IP <- -A_IP Ipp
+// pivot step b of the fronts [first, first + gridDim.y): D_b^-1 (every CTA of a front inverts the 32 x 32 block itself;
+// it is not written here, the inverse goes to the side buffer) and the L panel rows of this CTA:  A_ib <- A_ib D_b^-1.
 __global__ void __launch_bounds__(1024)
-k_nd_panel(int g, int b, double *__restrict__ Fl, double *__restrict__ ipp, double *__restrict__ colbuf) {
-  const int z = blockIdx.z;
-  __shared__ double X[NDB][NDB + 1], Ip[NDB][NDB + 1], W1[NDB][NDB + 1], W2[NDB][NDB + 1];
-  __shared__ int perm[NDB];
-  const int j = threadIdx.x & 31, i = threadIdx.x >> 5, q = blockIdx.x;
-  if (blockIdx.y == 1 && q == b) return;
-  double *A = Fl + (size_t)z * g * g;
-  W1[i][j] = A[(size_t)(b * NDB + i) * g + b * NDB + j];
+k_mf_panel(int first, int b, int rows_per_cta, const int *__restrict__ G_, const int *__restrict__ ld_,
+           const long long *__restrict__ foff, const int *__restrict__ dioff, double *__restrict__ F, double *__restrict__ Dinv) {
+  const int f = first + blockIdx.y;
+  const int G = G_[f], ld = ld_[f];
+  const int r0 = (b + 1) * MFB;
+  const int rbeg = r0 + blockIdx.x * rows_per_cta;
+  if (blockIdx.x > 0 && rbeg >= G) return;
+  __shared__ double W1[MFB][MFB + 1], W2[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1];
+  __shared__ int perm[MFB];
+  const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
+  double *A = F + foff[f];
+  W1[i][j] = A[(size_t)(b * MFB + i) * ld + b * MFB + j];
   __syncthreads();
-  nd_invert32(W1, W2, Ip, perm, i, j);
-  if (blockIdx.y == 0) {
-    if (q == b) { ipp[(size_t)z * NDB * NDB + i * NDB + j] = Ip[i][j]; return; }
-    double *T = A + (size_t)(b * NDB) * g + q * NDB;
-    X[i][j] = T[(size_t)i * g + j];
+  mf_invert32(W1, W2, Ip, perm, i, j);
+  if (blockIdx.x == 0) Dinv[((size_t)dioff[f] + b) * (MFB * MFB) + i * MFB + j] = Ip[i][j];
+  const int rend = min(G, rbeg + rows_per_cta);
+  for (int r = rbeg; r < rend; r += MFB) {
+    const int row = r + i;
+    double *T = A + (size_t)row * ld + b * MFB;
+    X[i][j] = row < rend ? T[j] : 0.0;
     __syncthreads();
     double sum = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < NDB; k++) sum += Ip[i][k] * X[k][j];
-    T[(size_t)i * g + j] = sum;
-  } else {
-    double *T = A + (size_t)(q * NDB) * g + b * NDB;
-    X[i][j] = T[(size_t)i * g + j];
-    colbuf[((size_t)z * g + q * NDB + i) * NDB + j] = X[i][j];
+    for (int k = 0; k < MFB; k++) sum += X[i][k] * Ip[k][j];
+    if (row < rend) T[j] = sum;
     __syncthreads();
-    double sum = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < NDB; k++) sum += X[i][k] * Ip[k][j];
-    T[(size_t)i * g + j] = -sum;
   }
 }
 
-// trailing update  A_IJ <- A_IJ - A_IP(old) A_PJ(new)  for I, J != P; 64 x 64 tile per CTA, 4 x 4 micro-tile
-__global__ void __launch_bounds__(256)
-k_nd_update(int g, int b, double *__restrict__ Fl, const double *__restrict__ colbuf, const double *__restrict__ ipp) {
-  const int z = blockIdx.z;
-  __shared__ double Cb[NDT][NDB + 1], R[NDB][NDT + 1];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = blockIdx.y * NDT, j0 = blockIdx.x * NDT;
-  double *A = Fl + (size_t)z * g * g;
-  for (int q = threadIdx.x; q < NDT * NDB; q += 256) {
-    const int ii = q / NDB, kk = q % NDB;
-    Cb[ii][kk] = ((i0 + ii) / NDB == b) ? 0.0 : colbuf[((size_t)z * g + i0 + ii) * NDB + kk];
-    const int k2 = q / NDT, jj = q % NDT;
-    R[k2][jj] = A[(size_t)(b * NDB + k2) * g + j0 + jj];
-  }
-  __syncthreads();
-  if ((int)blockIdx.y == (b * NDB) / NDT && (int)blockIdx.x == (b * NDB) / NDT)
-    for (int q = threadIdx.x; q < NDB * NDB; q += 256)
-      A[(size_t)(b * NDB + q / NDB) * g + b * NDB + q % NDB] = ipp[(size_t)z * NDB * NDB + q];
-  double acc[4][4] = {};
-#pragma unroll
-  for (int kk = 0; kk < NDB; kk++) {
-    double a[4], r[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) { a[q] = Cb[ty + 16 * q][kk]; r[q] = R[kk][tx + 16 * q]; }
-#pragma unroll
-    for (int p = 0; p < 4; p++)
-#pragma unroll
-      for (int q = 0; q < 4; q++) acc[p][q] += a[p] * r[q];
-  }
-#pragma unroll
-  for (int p = 0; p < 4; p++) {
-    const int i = i0 + ty + 16 * p;
-    if (i / NDB == b) continue;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int j = j0 + tx + 16 * q;
-      if (j / NDB == b) continue;
-      A[(size_t)i * g + j] -= acc[p][q];
+// second pivot block b1 = b0 + 1 of a 64-wide outer step (the trailing matrix has NOT been updated with block b0 yet):
+//   column part (blockIdx.x < nx_col):  D1 = A_11 - L_10 U_01,  D1^-1 -> side buffer,
+//                                       L_i1 = (A_i1 - L_i0 U_01) D1^-1   for the rows i > b1 of this CTA,
+//   row part (blockIdx.x >= nx_col):    U_1j = A_1j - L_10 U_0j            for the columns j > b1 of this CTA.
+// The two parts read and write disjoint blocks, so they share one launch.
+__global__ void __launch_bounds__(1024)
+k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_, const int *__restrict__ ld_,
+            const long long *__restrict__ foff, const int *__restrict__ dioff, double *__restrict__ F, double *__restrict__ Dinv) {
+  const int f = first + blockIdx.y;
+  const int G = G_[f], ld = ld_[f];
+  const int b0 = b1 - 1, r1 = (b1 + 1) * MFB;
+  const bool colpart = (int)blockIdx.x < nx_col;
+  const int cbeg = r1 + (colpart ? (int)blockIdx.x : (int)blockIdx.x - nx_col) * chunk;
+  if (cbeg >= G && !(colpart && blockIdx.x == 0)) return;
+  __shared__ double W1[MFB][MFB + 1], W2[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1];
+  __shared__ int perm[MFB];
+  const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
+  double *A = F + foff[f];
+  const int cend = min(G, cbeg + chunk);
+  if (colpart) {
+    X[i][j] = A[(size_t)(b1 * MFB + i) * ld + b0 * MFB + j];          // L_10
+    Y[i][j] = A[(size_t)(b0 * MFB + i) * ld + b1 * MFB + j];          // U_01
+    __syncthreads();
+    double d = A[(size_t)(b1 * MFB + i) * ld + b1 * MFB + j];
+#pragma unroll 8
+    for (int k = 0; k < MFB; k++) d -= X[i][k] * Y[k][j];
+    W1[i][j] = d;
+    __syncthreads();
+    mf_invert32(W1, W2, Ip, perm, i, j);
+    if (blockIdx.x == 0) Dinv[((size_t)dioff[f] + b1) * (MFB * MFB) + i * MFB + j] = Ip[i][j];
+    for (int r = cbeg; r < cend; r += MFB) {
+      const int row = r + i;
+      double *T = A + (size_t)row * ld;
+      __syncthreads();
+      X[i][j] = row < cend ? T[b0 * MFB + j] : 0.0;                   // L_i0
+      __syncthreads();
+      double v = row < cend ? T[b1 * MFB + j] : 0.0;
+#pragma unroll 8
+      for (int k = 0; k < MFB; k++) v -= X[i][k] * Y[k][j];
+      W1[i][j] = v;
+      __syncthreads();
+      double sum = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < MFB; k++) sum += W1[i][k] * Ip[k][j];
+      if (row < cend) T[b1 * MFB + j] = sum;
+    }
+  } else {
+    X[i][j] = A[(size_t)(b1 * MFB + i) * ld + b0 * MFB + j];          // L_10
+    for (int c = cbeg; c < cend; c += MFB) {
+      const int col = c + j;
+      __syncthreads();
+      Y[i][j] = col < cend ? A[(size_t)(b0 * MFB + i) * ld + col] : 0.0;   // U_0j
+      __syncthreads();
+      double sum = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < MFB; k++) sum += X[i][k] * Y[k][j];
+      if (col < cend) A[(size_t)(b1 * MFB + i) * ld + col] -= sum;
     }
   }
 }
 
-// extend-add of the Schur complements of the fronts in child slot `want` into their parents' fronts
-__global__ void k_nd_extend(int g, int p, int first, const double *__restrict__ Fl, int gp, double *__restrict__ Fp,
-                            const int *__restrict__ nb, const int *__restrict__ parent, const int *__restrict__ slot,
-                            const int *__restrict__ up_off, const int *__restrict__ upmap, int want) {
-  const int z = blockIdx.z, f = first + z;
-  if (slot[f] != want || parent[f] < 0) return;
-  const int n = nb[f];
-  const int r = blockIdx.y * 16 + threadIdx.y, c = blockIdx.x * 16 + threadIdx.x;
-  if (r >= n || c >= n) return;
-  const int *up = upmap + up_off[f];
-  Fp[(size_t)parent[f] * gp * gp + (size_t)up[r] * gp + up[c]] += Fl[(size_t)z * g * g + (size_t)(p + r) * g + p + c];
+// trailing update after the pivot blocks b .. b + nkb - 1 (nkb = 1 or 2):  A_ij -= sum_k L_ik A_kj  for i, j >= 32 (b + nkb).
+// Tile (8 TG) x (8 TG), TG x TG threads, 8 x 8 register micro-tile made of 2 x 2 sub-blocks (rows 2 ty + 2 TG p + {0,1},
+// columns 2 tx + 2 TG q + {0,1}): the L values are broadcast loads, the U values and all accesses to A are 16-byte
+// accesses of adjacent columns.  With nkb = 2 the tile of A is read and written once per 64 pivots.
+template <int TG>
+__global__ void __launch_bounds__(TG * TG, TG == 16 ? 1 : 4)
+k_mf_update(int first, int b, int nkb, const int *__restrict__ G_, const int *__restrict__ ld_, const long long *__restrict__ foff,
+            double *__restrict__ F) {
+  constexpr int T = 8 * TG, NT = TG * TG;
+  const int f = first + blockIdx.z;
+  const int G = G_[f], ld = ld_[f];
+  const int r0 = (b + nkb) * MFB;
+  const int i0 = r0 + blockIdx.y * T, j0 = r0 + blockIdx.x * T;
+  if (i0 >= G || j0 >= G) return;
+  double *A = F + foff[f];
+  extern __shared__ __align__(16) double mf_sm[];
+  double(*sL)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(mf_sm);          // [T][33]
+  double(*sU)[T] = reinterpret_cast<double(*)[T]>(mf_sm + T * (MFB + 1));      // [32][T]
+  const int t = threadIdx.x;
+  const int tx = t % TG, ty = t / TG;
+  double acc[8][8];
+#pragma unroll
+  for (int p = 0; p < 8; p++)
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[p][q] = 0.0;
+  for (int kb = b; kb < b + nkb; kb++) {
+    if (kb > b) __syncthreads();
+    for (int q = t; q < T * MFB; q += NT) {
+      const int row = q >> 5, k = q & 31;
+      sL[row][k] = (i0 + row < G) ? A[(size_t)(i0 + row) * ld + kb * MFB + k] : 0.0;
+    }
+    for (int q = t; q < MFB * (T / 2); q += NT) {
+      const int k = q / (T / 2), c = 2 * (q % (T / 2));
+      double2 v = make_double2(0.0, 0.0);
+      if (j0 + c < G) v = *reinterpret_cast<const double2 *>(A + (size_t)(kb * MFB + k) * ld + j0 + c);
+      *reinterpret_cast<double2 *>(&sU[k][c]) = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int k = 0; k < MFB; k++) {
+      double a[8], u[8];
+#pragma unroll
+      for (int p = 0; p < 4; p++) { a[2 * p] = sL[2 * ty + 2 * TG * p][k]; a[2 * p + 1] = sL[2 * ty + 2 * TG * p + 1][k]; }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double2 v = *reinterpret_cast<const double2 *>(&sU[k][2 * tx + 2 * TG * q]);
+        u[2 * q] = v.x; u[2 * q + 1] = v.y;
+      }
+#pragma unroll
+      for (int p = 0; p < 8; p++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[p][q] += a[p] * u[q];
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const int i = i0 + 2 * ty + 2 * TG * (p >> 1) + (p & 1);
+    if (i >= G) continue;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int j = j0 + 2 * tx + 2 * TG * q;
+      if (j >= G) continue;
+      double2 *c = reinterpret_cast<double2 *>(A + (size_t)i * ld + j);
+      double2 v = *c;
+      v.x -= acc[p][2 * q]; v.y -= acc[p][2 * q + 1];
+      *c = v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// solve
+// solve kernels: one CTA (1024 threads) per front, one launch per level and direction
 // ------------------------------------------------------------------------------------------------------------------
-// w_s = scaled right-hand side of the front's own unknowns, everything else zero.  dself != nullptr: the right-hand
-// side is first multiplied by the 2x2 diagonal blocks of A (the solver then applies (B A)^-1, B = block-Jacobi scaling)
-__global__ void k_nd_rhs(int g, int first, const int *__restrict__ ns, const int *__restrict__ sep_off,
-                         const int *__restrict__ sepdof, const double *__restrict__ scale, const double *__restrict__ b,
-                         const double *__restrict__ dself, const double *__restrict__ dpair, double *__restrict__ Wl) {
-  const int z = blockIdx.y, f = first + z, r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= g) return;
-  double v = 0.0;
-  if (r < ns[f]) {
-    const int d = sepdof[sep_off[f] + r];
-    v = scale[d] * (dself ? dself[d] * b[d] + dpair[d] * b[d ^ 1] : b[d]);
+// forward:  w = [scaled rhs of the own unknowns ; 0] + the boundary vectors of the children, then  y = L^-1 w  block by
+// block; the boundary rows end up holding this front's contribution to its parent.  dself != nullptr: the right-hand
+// side is first multiplied by the 2x2 diagonal blocks of A (the solver then applies (B A)^-1, B = block-Jacobi scaling).
+__global__ void __launch_bounds__(1024)
+k_mf_fwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, const int *__restrict__ G_,
+         const int *__restrict__ ld_, const long long *__restrict__ foff, const int *__restrict__ woff_,
+         const int *__restrict__ cw0, const int *__restrict__ cw1, const int *__restrict__ pinv0, const int *__restrict__ pinv1,
+         const int *__restrict__ sep_off, const int *__restrict__ sepdof, const double *__restrict__ scale,
+         const double *__restrict__ rhs, const double *__restrict__ dself, const double *__restrict__ dpair,
+         const double *__restrict__ F, double *__restrict__ W) {
+  const int f = first + blockIdx.x;
+  const int ns = ns_[f], p = p_[f], G = G_[f], ld = ld_[f], wo = woff_[f];
+  const double *A = F + foff[f];
+  double *w = W + wo;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+  const int w0 = cw0[f], w1 = cw1[f];
+  __shared__ double ys[MFB];
+  for (int i = t; i < G; i += blockDim.x) {
+    double v = 0.0;
+    if (i < ns) {
+      const int d = sepdof[sep_off[f] + i];
+      v = scale[d] * (dself ? dself[d] * rhs[d] + dpair[d] * rhs[d ^ 1] : rhs[d]);
+    }
+    if (w0 >= 0) { const int a = pinv0[wo + i]; if (a >= 0) v += W[w0 + a]; }
+    if (w1 >= 0) { const int a = pinv1[wo + i]; if (a >= 0) v += W[w1 + a]; }
+    w[i] = v;
   }
-  Wl[(size_t)z * g + r] = v;
-}
-
-// y = F[:, 0:ns] w_s (one warp per row):  own rows -> z,  boundary rows -> w_b += y
-__global__ void __launch_bounds__(256)
-k_nd_fwd(int g, int p, int first, const int *__restrict__ ns, const int *__restrict__ nb, const double *__restrict__ Fl,
-         double *__restrict__ Wl, double *__restrict__ Zl) {
-  const int z = blockIdx.z, f = first + z;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int n = ns[f];
-  if (row >= p + nb[f] || (row >= n && row < p)) return;
-  const double *Fr = Fl + (size_t)z * g * g + (size_t)row * g, *w = Wl + (size_t)z * g;
-  double sum = 0.0;
-  for (int j = lane; j < n; j += 32) sum += Fr[j] * w[j];
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-  if (lane == 0) {
-    if (row < p) Zl[(size_t)z * g + row] = sum;
-    else Wl[(size_t)z * g + row] += sum;
-  }
-}
-
-// child -> parent: parent.w[up[r]] += child.w_b[r] (slot `want`), or parent -> child: child.w_b[r] = parent.w[up[r]]
-__global__ void k_nd_vec_updown(int g, int p, int first, int gp, double *__restrict__ Wl, double *__restrict__ Wp,
-                                const int *__restrict__ nb, const int *__restrict__ parent, const int *__restrict__ slot,
-                                const int *__restrict__ up_off, const int *__restrict__ upmap, int want, int down) {
-  const int z = blockIdx.y, f = first + z, r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (parent[f] < 0 || r >= nb[f]) return;
-  if (!down && slot[f] != want) return;
-  const size_t ip = (size_t)parent[f] * gp + upmap[up_off[f] + r], ic = (size_t)z * g + p + r;
-  if (down) Wl[ic] = Wp[ip];
-  else Wp[ip] += Wl[ic];
-}
-
-// x_s = z - F12' x_b (one warp per own row); written to w_s (for the children) and, unscaled, to the global solution
-__global__ void __launch_bounds__(256)
-k_nd_bwd(int g, int p, int first, const int *__restrict__ ns, const int *__restrict__ nb, const int *__restrict__ sep_off,
-         const int *__restrict__ sepdof, const double *__restrict__ scale, const double *__restrict__ Fl,
-         double *__restrict__ Wl, const double *__restrict__ Zl, double *__restrict__ x, int accumulate) {
-  const int z = blockIdx.z, f = first + z;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= ns[f]) return;
-  const int n = nb[f];
-  const double *Fr = Fl + (size_t)z * g * g + (size_t)row * g + p, *w = Wl + (size_t)z * g + p;
-  double sum = 0.0;
-  for (int j = lane; j < n; j += 32) sum += Fr[j] * w[j];
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-  if (lane == 0) {
-    const double xs = Zl[(size_t)z * g + row] - sum;
-    const int d = sepdof[sep_off[f] + row];
-    Wl[(size_t)z * g + row] = xs;
-    if (accumulate) x[d] += scale[d] * xs; else x[d] = scale[d] * xs;
+  __syncthreads();
+  const int nblk = p / MFB;
+  for (int b = 0; b < nblk; b++) {
+    if (t < MFB) ys[t] = w[b * MFB + t];
+    __syncthreads();
+    const double yl = ys[lane];
+    for (int r = (b + 1) * MFB + warp; r < G; r += nwarps) {
+      double v = A[(size_t)r * ld + b * MFB + lane] * yl;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) w[r] -= v;
+    }
+    __syncthreads();
   }
 }
 
-// r = b - A x, unscaled CSR, one thread per row
-__global__ void k_nd_residual(int N, const int *__restrict__ ptr, const int *__restrict__ ind, const double *__restrict__ val,
+// backward:  x_b from the parent's vector,  x_s = U11^-1 (y - U12 x_b)  block by block (D_b^-1 from the side buffer);
+// x_s stays in w (for the children) and goes, unscaled, to the global solution vector
+__global__ void __launch_bounds__(1024)
+k_mf_bwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, const int *__restrict__ nb_,
+         const int *__restrict__ ld_, const long long *__restrict__ foff, const int *__restrict__ woff_,
+         const int *__restrict__ pwoff, const int *__restrict__ up_off, const int *__restrict__ upmap,
+         const int *__restrict__ dioff, const int *__restrict__ sep_off, const int *__restrict__ sepdof,
+         const double *__restrict__ scale, const double *__restrict__ F, const double *__restrict__ Dinv,
+         double *__restrict__ W, double *__restrict__ x, int accumulate) {
+  const int f = first + blockIdx.x;
+  const int ns = ns_[f], p = p_[f], nb = nb_[f], ld = ld_[f], G = p + nb;
+  const double *A = F + foff[f];
+  double *w = W + woff_[f];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;      // 32 warps
+  __shared__ double ts[MFB];
+  if (nb > 0) {
+    const double *pw = W + pwoff[f];
+    const int *up = upmap + up_off[f];
+    for (int r = t; r < nb; r += blockDim.x) w[p + r] = pw[up[r]];
+  }
+  __syncthreads();
+  for (int b = p / MFB - 1; b >= 0; b--) {
+    const int row = b * MFB + warp;
+    const double *Ar = A + (size_t)row * ld;
+    double v = 0.0;
+    for (int j = (b + 1) * MFB + lane; j < G; j += 32) v += Ar[j] * w[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) ts[warp] = w[row] - v;
+    __syncthreads();
+    double xv = Dinv[((size_t)dioff[f] + b) * (MFB * MFB) + warp * MFB + lane] * ts[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xv += __shfl_xor_sync(0xffffffffu, xv, o);
+    __syncthreads();
+    if (lane == 0) w[row] = xv;
+    __syncthreads();
+  }
+  for (int i = t; i < ns; i += blockDim.x) {
+    const int d = sepdof[sep_off[f] + i];
+    const double xs = scale[d] * w[i];
+    if (accumulate) x[d] += xs; else x[d] = xs;
+  }
+}
+
+// r = b - A x, unscaled CSR (1-based), one thread per row
+__global__ void k_mf_residual(int N, const int *__restrict__ ptr, const int *__restrict__ ind, const double *__restrict__ val,
                               const double *__restrict__ b, const double *__restrict__ x, double *__restrict__ r) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double s = b[i];
-  for (int k = ptr[i]; k < ptr[i + 1]; k++) s -= val[k] * x[ind[k]];
+  for (int k = ptr[i] - 1; k < ptr[i + 1] - 1; k++) s -= val[k] * x[ind[k] - 1];
   r[i] = s;
+}
+
+__global__ void k_mf_copy_slice(int n, const double *__restrict__ src, double *__restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-template <class T> static int nd_upload(T **d, const std::vector<T> &h) {
+template <class T> static int mf_upload(T **d, const std::vector<T> &h) {
   UFE_CUDA(cudaMalloc((void **)d, std::max<size_t>(1, h.size()) * sizeof(T)));
   if (!h.empty()) UFE_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   return UFE_OK;
 }
 
+static void mf_graph_drop(MfGraph &g) { if (g.exec) cudaGraphExecDestroy(g.exec); g = MfGraph(); }
+
 extern "C" void ufe_nd_solver_free(ufe_nd_solver *S) {
   if (!S) return;
-  void *p[] = {S->ns, S->nb, S->parent, S->slot, S->sep_off, S->up_off, S->sepdof, S->upmap, S->dst, S->ptr, S->ind, S->val,
-               S->scale, S->dself, S->dpair, S->F, S->W, S->Z, S->ipp, S->colbuf, S->b, S->x, S->r, S->dx};
-  for (void *q : p) if (q) cudaFree(q);
+  mf_graph_drop(S->g_factor);
+  for (MfGraph &g : S->g_apply) mf_graph_drop(g);
+  void *q[] = {S->ns, S->p, S->nb, S->G, S->ld, S->woff, S->dioff, S->sep_off, S->up_off, S->pwoff, S->foff, S->c_f[0], S->c_f[1],
+               S->c_ld[0], S->c_ld[1], S->c_w[0], S->c_w[1], S->pinv[0], S->pinv[1], S->sepdof, S->upmap, S->dst, S->val, S->scale,
+               S->dself, S->dpair, S->F, S->W, S->Dinv, S->b, S->x, S->r};
+  for (void *v : q) if (v) cudaFree(v);
+  if (S->own_pattern) { cudaFree(S->ptr); cudaFree(S->ind); }
   if (S->e0) cudaEventDestroy(S->e0);
   if (S->e1) cudaEventDestroy(S->e1);
   if (S->st) cudaStreamDestroy(S->st);
   delete S;
 }
 
-// ptr / ind: scalar CSR pattern of A, 0-based, N = 2 nT rows; its block pattern must be the one that was analysed.
-extern "C" int ufe_nd_solver_create(const ufe_nd_tree *T, int32_t N, const int32_t *ptr, const int32_t *ind, ufe_nd_solver **out) {
-  if (!T || !ptr || !ind || !out || N != 2 * T->nT) { ufe_set_error("ufe_nd_solver_create: bad argument"); return UFE_ERR_INVALID; }
+// Builds the device layout.  ptr / ind: scalar CSR pattern of the WHOLE matrix A, 1-based (the reference's
+// type_sparse_matrix_CSR_dp convention), N = 2 nT rows, on the host; its block pattern must be the one that was analysed.
+// d_ptr / d_ind: the same pattern already on the device (aliased, not copied), or nullptr.
+static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind, const int *d_ptr, const int *d_ind,
+                     int rank, int nranks, ncclComm_t nccl, ufe_nd_solver **out) {
+  *out = nullptr;
+  if (!T || !ptr || !ind || N != 2 * T->nT) { ufe_set_error("ufe_nd_solver_create: bad argument"); return UFE_ERR_INVALID; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     ufe_set_error("ufe_nd_solver_create: no CUDA device (there is no CPU fallback)"); return UFE_ERR_CUDA;
   }
   const int nn = (int)T->nodes.size(), nl = T->n_levels;
+  int Ld = 0;
+  while ((1 << Ld) < nranks) Ld++;
+  if ((1 << Ld) != nranks) { ufe_set_error("nd_lu: the number of ranks must be a power of two (got %d)", nranks); return UFE_ERR_INVALID; }
+  // owner of every node: the sub-tree below the r-th node of level Ld belongs to rank r, nodes above to the left spine
+  std::vector<int> owner(nn, 0), span(nn, 1);
+  for (int q = nn - 1; q >= 0; q--) {            // post-order: parents have larger indices than their children
+    const NdNode &nd = T->nodes[q];
+    if (nd.parent < 0) { owner[q] = 0; span[q] = nranks; }
+    if (nd.child[0] < 0) { if (span[q] > 1) { ufe_set_error("nd_lu: the elimination tree is too shallow for %d ranks", nranks); return UFE_ERR_INVALID; } continue; }
+    const int half = span[q] / 2;
+    owner[nd.child[0]] = owner[q]; span[nd.child[0]] = std::max(1, half);
+    owner[nd.child[1]] = owner[q] + half; span[nd.child[1]] = std::max(1, half);
+  }
   ufe_nd_solver *S = new ufe_nd_solver();
-  S->nT = T->nT; S->N = N; S->nnz = ptr[N]; S->n_fronts = nn;
+  S->nT = T->nT; S->N = N; S->nnz = ptr[N] - 1; S->rank = rank; S->nranks = nranks; S->nccl = nccl;
+  if (const char *e = getenv("UFE_ND_GRAPHS")) S->use_graphs = atoi(e);
+  if (const char *e = getenv("UFE_ND_K64")) S->k64 = atoi(e);
+  if (nranks > 1) S->use_graphs = 0;
   S->lev.resize(nl);
-  // level-major front numbering
-  std::vector<int> zof(nn), fof(nn);
+  // local fronts, level-major, p descending inside a level
+  std::vector<int> lid(nn, -1);
+  std::vector<std::vector<int>> by_level(nl);
+  for (int q = 0; q < nn; q++) if (owner[q] == rank) by_level[T->nodes[q].level].push_back(q);
+  auto pad32 = [](int v) { return std::max(MFB, (v + MFB - 1) / MFB * MFB); };
+  std::vector<int> node_of_front;
+  for (int l = 0; l < nl; l++) {
+    std::stable_sort(by_level[l].begin(), by_level[l].end(), [&](int a, int b) { return T->nodes[a].sep.size() > T->nodes[b].sep.size(); });
+    S->lev[l].first = (int)node_of_front.size(); S->lev[l].n = (int)by_level[l].size();
+    for (int q : by_level[l]) { lid[q] = (int)node_of_front.size(); node_of_front.push_back(q); }
+  }
+  const int nf = (int)node_of_front.size();
+  S->n_fronts = nf;
+  std::vector<int> ns(nf), p(nf), nb(nf), G(nf), ld(nf), woff(nf), dioff(nf), sep_off(nf), up_off(nf), pwoff(nf, 0);
+  std::vector<long long> foff(nf), cf[2];
+  std::vector<int> cld[2], cw[2];
+  for (int s = 0; s < 2; s++) { cf[s].assign(nf, -1); cld[s].assign(nf, 0); cw[s].assign(nf, -1); }
+  size_t fo = 0, wo = 0, dio = 0, so = 0, uo = 0;
+  for (int f = 0; f < nf; f++) {
+    const NdNode &nd = T->nodes[node_of_front[f]];
+    ns[f] = 2 * (int)nd.sep.size(); p[f] = pad32(ns[f]); nb[f] = nd.parent >= 0 ? 2 * (int)nd.bnd.size() : 0;
+    G[f] = p[f] + nb[f]; ld[f] = (G[f] + 7) / 8 * 8;
+    foff[f] = (long long)fo; fo += (size_t)ld[f] * ld[f];
+    woff[f] = (int)wo; wo += ld[f];
+    dioff[f] = (int)dio; dio += p[f] / MFB;
+    sep_off[f] = (int)so; so += ns[f];
+    up_off[f] = (int)uo; uo += nb[f];
+    const double pp = p[f], bb = nb[f];
+    S->flops += 2.0 / 3.0 * pp * pp * pp + 2.0 * pp * pp * bb + 2.0 * pp * bb * bb;
+  }
+  // exchange buffers at the cut levels (child 1 of a node whose ranks span > 1 lives on another rank)
   for (int q = 0; q < nn; q++) {
     const NdNode &nd = T->nodes[q];
-    NdLevelDev &L = S->lev[nd.level];
-    zof[q] = L.n++;
-    L.p = std::max(L.p, 2 * (int)nd.sep.size());
-    L.max_nb = std::max(L.max_nb, 2 * (int)nd.bnd.size());
+    if (span[q] <= 1 || nd.child[1] < 0) continue;
+    const int c = nd.child[1];
+    if (owner[q] != rank && owner[c] != rank) continue;
+    MfLink L;
+    L.level = nd.level; L.child_rank = owner[c]; L.parent_rank = owner[q];
+    L.child_front = owner[c] == rank ? lid[c] : -1; L.parent_front = owner[q] == rank ? lid[q] : -1;
+    L.nb = 2 * (int)T->nodes[c].bnd.size();
+    L.Gp = pad32(2 * (int)nd.sep.size()) + (nd.parent >= 0 ? 2 * (int)nd.bnd.size() : 0);
+    L.f_buf = (long long)fo; fo += ((size_t)L.nb * L.nb + 7) / 8 * 8;
+    L.w_buf = (int)wo; wo += (size_t)((owner[q] == rank ? L.nb : L.Gp) + 7) / 8 * 8;
+    S->links.push_back(L);
   }
-  int first = 0;
-  for (NdLevelDev &L : S->lev) {
-    L.p = std::max(NDB, (L.p + NDB - 1) / NDB * NDB);
-    L.g = (L.p + L.max_nb + NDT - 1) / NDT * NDT;
-    L.first = first; first += L.n;
-    L.f_off = S->f_doubles; S->f_doubles += (size_t)L.n * L.g * L.g;
-    L.w_off = S->w_doubles; S->w_doubles += (size_t)L.n * L.g;
-    S->flops += 2.0 * (double)L.n * (double)L.g * (double)L.g * (double)L.p;
-  }
-  for (const NdLevelDev &L : S->lev)
-    if (L.n > 65535) { ufe_set_error("ufe_nd_solver_create: %d fronts in one level (limit 65535): use larger leaves", L.n); delete S; return UFE_ERR_INVALID; }
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  if ((double)S->f_doubles * 8.0 > 0.9 * (double)free_b) {
-    ufe_set_error("ufe_nd_solver_create: the padded fronts need %.1f GB, %.1f GB are free", S->f_doubles * 8e-9, free_b * 1e-9);
-    delete S; return UFE_ERR_INVALID;
-  }
-  for (int q = 0; q < nn; q++) fof[q] = S->lev[T->nodes[q].level].first + zof[q];
-  std::vector<int> ns(nn), nb(nn), parent(nn), slot(nn), sep_off(nn), up_off(nn), sepdof, upmap;
-  {
-    std::vector<int> so(nn + 1, 0), uo(nn + 1, 0);
-    for (int q = 0; q < nn; q++) {
-      const NdNode &nd = T->nodes[q];
-      const int f = fof[q];
-      ns[f] = 2 * (int)nd.sep.size(); nb[f] = nd.parent >= 0 ? 2 * (int)nd.bnd.size() : 0;
-      parent[f] = nd.parent >= 0 ? zof[nd.parent] : -1;
-      slot[f] = nd.parent >= 0 && T->nodes[nd.parent].child[1] == q ? 1 : 0;
-    }
-    for (int f = 0; f < nn; f++) { so[f + 1] = so[f] + ns[f]; uo[f + 1] = uo[f] + nb[f]; }
-    sepdof.resize(so[nn]); upmap.resize(uo[nn]);
-    for (int q = 0; q < nn; q++) {
-      const NdNode &nd = T->nodes[q];
-      const int f = fof[q];
-      sep_off[f] = so[f]; up_off[f] = uo[f];
-      for (size_t k = 0; k < nd.sep.size(); k++) { sepdof[so[f] + 2 * k] = 2 * nd.sep[k]; sepdof[so[f] + 2 * k + 1] = 2 * nd.sep[k] + 1; }
-      if (nd.parent < 0) continue;
+  S->f_doubles = fo; S->w_doubles = wo; S->di_blocks = dio;
+  if (wo > 0x7fffffffULL) { ufe_set_error("nd_lu: work vectors exceed 2^31 entries"); delete S; return UFE_ERR_INVALID; }
+  // children / parent views, inverse maps, sep dofs, up maps
+  std::vector<int> sepdof(so), upmap(uo), pinv0(wo, -1), pinv1(wo, -1);
+  for (int f = 0; f < nf; f++) {
+    const int q = node_of_front[f];
+    const NdNode &nd = T->nodes[q];
+    for (size_t k = 0; k < nd.sep.size(); k++) { sepdof[sep_off[f] + 2 * k] = 2 * nd.sep[k]; sepdof[sep_off[f] + 2 * k + 1] = 2 * nd.sep[k] + 1; }
+    if (nd.parent >= 0) {
       const NdNode &pa = T->nodes[nd.parent];
-      const int pns = (int)pa.sep.size(), pp = S->lev[pa.level].p;
+      const int pns = (int)pa.sep.size(), pp = pad32(2 * pns);
       for (size_t k = 0; k < nd.bnd.size(); k++) {
         const int u = nd.up[k], row = u < pns ? 2 * u : pp + 2 * (u - pns);
-        upmap[uo[f] + 2 * k] = row; upmap[uo[f] + 2 * k + 1] = row + 1;
+        upmap[up_off[f] + 2 * k] = row; upmap[up_off[f] + 2 * k + 1] = row + 1;
+      }
+      if (owner[nd.parent] == rank) pwoff[f] = woff[lid[nd.parent]];
+    }
+    for (int s = 0; s < 2; s++) {
+      const int c = nd.child[s];
+      if (c < 0) continue;
+      const NdNode &ch = T->nodes[c];
+      const int pns = (int)nd.sep.size();
+      std::vector<int> &pv = s == 0 ? pinv0 : pinv1;
+      for (size_t k = 0; k < ch.bnd.size(); k++) {
+        const int u = ch.up[k], row = u < pns ? 2 * u : p[f] + 2 * (u - pns);
+        pv[woff[f] + row] = 2 * (int)k; pv[woff[f] + row + 1] = 2 * (int)k + 1;
+      }
+      if (owner[c] == rank) {
+        const int cfr = lid[c];
+        cf[s][f] = foff[cfr] + (long long)p[cfr] * ld[cfr] + p[cfr]; cld[s][f] = ld[cfr]; cw[s][f] = woff[cfr] + p[cfr];
       }
     }
   }
-  // destination of every scalar entry: its block entry's front and block position
+  for (MfLink &L : S->links) {
+    if (L.parent_front >= 0) {
+      cf[1][L.parent_front] = L.f_buf; cld[1][L.parent_front] = L.nb; cw[1][L.parent_front] = L.w_buf;
+      L.parent_w = woff[L.parent_front];
+    }
+    if (L.child_front >= 0) {
+      const int c = L.child_front;
+      pwoff[c] = L.w_buf;
+      L.child_schur = foff[c] + (long long)p[c] * ld[c] + p[c]; L.child_ld = ld[c]; L.child_wb = woff[c] + p[c];
+    }
+  }
+  // per-level / per-step launch shapes
+  for (int l = 0; l < nl; l++) {
+    MfLevel &Lv = S->lev[l];
+    for (int z = 0; z < Lv.n; z++) {
+      const int f = Lv.first + z;
+      Lv.steps = std::max(Lv.steps, p[f] / MFB); Lv.maxG = std::max(Lv.maxG, G[f]); Lv.max_nb = std::max(Lv.max_nb, nb[f]);
+      if (cf[0][f] >= 0 || cf[1][f] >= 0) Lv.n_internal++;
+    }
+    Lv.step.resize(Lv.steps);
+    for (int b = 0; b < Lv.steps; b++) {
+      MfStep st{0, 0};
+      for (int z = 0; z < Lv.n; z++) {
+        const int f = Lv.first + z;
+        if (p[f] > b * MFB) { st.n_active = z + 1; st.max_trail = std::max(st.max_trail, G[f] - (b + 1) * MFB); }
+      }
+      Lv.step[b] = st;
+    }
+    if (Lv.n > 65535) { ufe_set_error("ufe_nd_solver_create: %d fronts in one level (limit 65535): use larger leaves", Lv.n); delete S; return UFE_ERR_INVALID; }
+  }
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  if ((double)S->f_doubles * 8.0 > 0.92 * (double)free_b) {
+    ufe_set_error("ufe_nd_solver_create: the fronts need %.1f GB, %.1f GB are free", S->f_doubles * 8e-9, free_b * 1e-9);
+    delete S; return UFE_ERR_INVALID;
+  }
+  // destination of every scalar entry: its block entry's front and position there (-1: a front of another rank)
   std::vector<long long> dst(S->nnz);
   for (int i = 0; i < N; i++) {
     const int bi = i >> 1;
-    for (int k = ptr[i]; k < ptr[i + 1]; k++) {
-      const int j = ind[k], bj = j >> 1;
+    for (int k = ptr[i] - 1; k < ptr[i + 1] - 1; k++) {
+      const int j = ind[k] - 1, bj = j >> 1;
       int e = -1;
-      if (j >= 0 && j < N) for (int t = T->bptr[bi]; t < T->bptr[bi + 1]; t++) if (T->bind[t] == bj) { e = t; break; }
-      if (e < 0) { ufe_set_error("ufe_nd_solver_create: entry (%d,%d) is not in the analysed block pattern", i, j); delete S; return UFE_ERR_INVALID; }
+      if (j >= 0 && j < N) {
+        const int *lo = T->bind.data() + T->bptr[bi], *hi = T->bind.data() + T->bptr[bi + 1];
+        const int *it = std::lower_bound(lo, hi, bj);
+        if (it != hi && *it == bj) e = (int)(it - T->bind.data());
+        else for (int t = T->bptr[bi]; t < T->bptr[bi + 1]; t++) if (T->bind[t] == bj) { e = t; break; }   // unsorted block rows
+      }
+      if (e < 0) { ufe_set_error("ufe_nd_solver_create: entry (%d,%d) is not in the analysed block pattern", i + 1, j + 1); delete S; return UFE_ERR_INVALID; }
       const int q = T->entry_node[e];
-      const NdNode &nd = T->nodes[q];
-      const NdLevelDev &L = S->lev[nd.level];
-      const int nsb = (int)nd.sep.size();
+      if (owner[q] != rank) { dst[k] = -1; continue; }
+      const int f = lid[q];
+      const int nsb = ns[f] / 2;
       const int br = T->entry_row[e], bc = T->entry_col[e];
-      const int row = (br < nsb ? 2 * br : L.p + 2 * (br - nsb)) + (i & 1), col = (bc < nsb ? 2 * bc : L.p + 2 * (bc - nsb)) + (j & 1);
-      dst[k] = (long long)(L.f_off + (size_t)zof[q] * L.g * L.g + (size_t)row * L.g + col);
+      const int row = (br < nsb ? 2 * br : p[f] + 2 * (br - nsb)) + (i & 1), col = (bc < nsb ? 2 * bc : p[f] + 2 * (bc - nsb)) + (j & 1);
+      dst[k] = foff[f] + (long long)row * ld[f] + col;
     }
   }
   int rc = UFE_OK;
   auto fail = [&](int c) { ufe_nd_solver_free(S); return c; };
-  if ((rc = nd_upload(&S->ns, ns)) || (rc = nd_upload(&S->nb, nb)) || (rc = nd_upload(&S->parent, parent)) ||
-      (rc = nd_upload(&S->slot, slot)) || (rc = nd_upload(&S->sep_off, sep_off)) || (rc = nd_upload(&S->up_off, up_off)) ||
-      (rc = nd_upload(&S->sepdof, sepdof)) || (rc = nd_upload(&S->upmap, upmap)) || (rc = nd_upload(&S->dst, dst)))
+  if ((rc = mf_upload(&S->ns, ns)) || (rc = mf_upload(&S->p, p)) || (rc = mf_upload(&S->nb, nb)) || (rc = mf_upload(&S->G, G)) ||
+      (rc = mf_upload(&S->ld, ld)) || (rc = mf_upload(&S->woff, woff)) || (rc = mf_upload(&S->dioff, dioff)) ||
+      (rc = mf_upload(&S->sep_off, sep_off)) || (rc = mf_upload(&S->up_off, up_off)) || (rc = mf_upload(&S->pwoff, pwoff)) ||
+      (rc = mf_upload(&S->foff, foff)) || (rc = mf_upload(&S->c_f[0], cf[0])) || (rc = mf_upload(&S->c_f[1], cf[1])) ||
+      (rc = mf_upload(&S->c_ld[0], cld[0])) || (rc = mf_upload(&S->c_ld[1], cld[1])) || (rc = mf_upload(&S->c_w[0], cw[0])) ||
+      (rc = mf_upload(&S->c_w[1], cw[1])) || (rc = mf_upload(&S->pinv[0], pinv0)) || (rc = mf_upload(&S->pinv[1], pinv1)) ||
+      (rc = mf_upload(&S->sepdof, sepdof)) || (rc = mf_upload(&S->upmap, upmap)) || (rc = mf_upload(&S->dst, dst)))
     return fail(rc);
-  {
+  if (d_ptr && d_ind) { S->ptr = const_cast<int *>(d_ptr); S->ind = const_cast<int *>(d_ind); }
+  else {
     std::vector<int> hp(ptr, ptr + N + 1), hi(ind, ind + S->nnz);
-    if ((rc = nd_upload(&S->ptr, hp)) || (rc = nd_upload(&S->ind, hi))) return fail(rc);
+    S->own_pattern = true;
+    if ((rc = mf_upload(&S->ptr, hp)) || (rc = mf_upload(&S->ind, hi))) return fail(rc);
   }
-  size_t ipp_n = 0, col_n = 0;
-  for (const NdLevelDev &L : S->lev) { ipp_n = std::max(ipp_n, (size_t)L.n * NDB * NDB); col_n = std::max(col_n, (size_t)L.n * L.g * NDB); }
-  const struct { double **p; size_t n; } bufs[] = {{&S->val, (size_t)S->nnz}, {&S->scale, (size_t)N}, {&S->dself, (size_t)N}, {&S->dpair, (size_t)N}, {&S->F, S->f_doubles},
-      {&S->W, S->w_doubles}, {&S->Z, S->w_doubles}, {&S->ipp, ipp_n}, {&S->colbuf, col_n}, {&S->b, (size_t)N}, {&S->x, (size_t)N},
-      {&S->r, (size_t)N}, {&S->dx, (size_t)N}};
+  const struct { double **q; size_t n; } bufs[] = {{&S->scale, (size_t)N}, {&S->dself, (size_t)N}, {&S->dpair, (size_t)N}, {&S->F, S->f_doubles},
+      {&S->W, S->w_doubles}, {&S->Dinv, S->di_blocks * MFB * MFB}, {&S->b, (size_t)N}, {&S->x, (size_t)N}, {&S->r, (size_t)N}};
   for (const auto &bf : bufs)
-    if (cudaMalloc((void **)bf.p, std::max<size_t>(1, bf.n) * sizeof(double)) != cudaSuccess) {
+    if (cudaMalloc((void **)bf.q, std::max<size_t>(1, bf.n) * sizeof(double)) != cudaSuccess) {
       ufe_set_error("ufe_nd_solver_create: out of device memory (%zu doubles)", bf.n); cudaGetLastError(); return fail(UFE_ERR_CUDA);
     }
+  UFE_CUDA(cudaMemset(S->W, 0, S->w_doubles * sizeof(double)));
   if (cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&S->e0) != cudaSuccess ||
       cudaEventCreate(&S->e1) != cudaSuccess) { ufe_set_error("ufe_nd_solver_create: stream / event creation failed"); return fail(UFE_ERR_CUDA); }
+  static bool attr_set = false;
+  if (!attr_set) {
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 * (MFB + 1) + MFB * 128) * sizeof(double))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((64 * (MFB + 1) + MFB * 64) * sizeof(double))));
+    attr_set = true;
+  }
   UFE_CUDA(cudaDeviceSynchronize());
   *out = S;
   return UFE_OK;
 }
 
-// factorisation from values already on the device (same order as the pattern given to create)
-static int nd_factor_device(ufe_nd_solver *S, cudaStream_t st, const double *dval) {
-  const int N = S->N, tb = 256;
-  k_nd_scale<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dself, S->dpair); UFE_LAUNCH_CHECK();
-  UFE_CUDA(cudaMemsetAsync(S->F, 0, S->f_doubles * sizeof(double), st));
-  k_nd_assemble<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dst, S->F); UFE_LAUNCH_CHECK();
-  for (int l = (int)S->lev.size() - 1; l >= 0; l--) {
-    const NdLevelDev &L = S->lev[l];
-    double *Fl = S->F + L.f_off;
-    k_nd_pad_identity<<<dim3((L.p + 127) / 128, L.n), 128, 0, st>>>(L.g, L.p, L.first, S->ns, Fl); UFE_LAUNCH_CHECK();
-    for (int b = 0; b < L.p / NDB; b++) {
-      k_nd_panel<<<dim3(L.g / NDB, 2, L.n), 1024, 0, st>>>(L.g, b, Fl, S->ipp, S->colbuf); UFE_LAUNCH_CHECK();
-      k_nd_update<<<dim3(L.g / NDT, L.g / NDT, L.n), 256, 0, st>>>(L.g, b, Fl, S->colbuf, S->ipp); UFE_LAUNCH_CHECK();
-    }
-    if (l > 0 && L.max_nb > 0) {
-      const NdLevelDev &P = S->lev[l - 1];
-      const int t = (L.max_nb + 15) / 16;
-      for (int want = 0; want < 2; want++) {
-        k_nd_extend<<<dim3(t, t, L.n), dim3(16, 16), 0, st>>>(L.g, L.p, L.first, Fl, P.g, S->F + P.f_off, S->nb, S->parent, S->slot,
-                                                              S->up_off, S->upmap, want);
-        UFE_LAUNCH_CHECK();
-      }
-    }
+extern "C" int ufe_nd_solver_create(const ufe_nd_tree *T, int32_t N, const int32_t *ptr, const int32_t *ind, ufe_nd_solver **out) {
+  if (!out) { ufe_set_error("ufe_nd_solver_create: bad argument"); return UFE_ERR_INVALID; }
+  ufe_nd_solver *S = nullptr;
+  UFE_TRY(mf_create(T, N, ptr, ind, nullptr, nullptr, 0, 1, nullptr, &S));
+  if (cudaMalloc((void **)&S->val, std::max<size_t>(1, (size_t)S->nnz) * sizeof(double)) != cudaSuccess) {
+    ufe_set_error("ufe_nd_solver_create: out of device memory"); ufe_nd_solver_free(S); return UFE_ERR_CUDA;
   }
-  S->factored = true;
+  *out = S;
   return UFE_OK;
 }
 
-// x (+)= A^-1 r with the factors; r, x device vectors of length N
-static int nd_apply_device(ufe_nd_solver *S, cudaStream_t st, const double *r, double *x, int accumulate, int premul) {
-  const int nl = (int)S->lev.size();
-  for (int l = 0; l < nl; l++) {
-    const NdLevelDev &L = S->lev[l];
-    k_nd_rhs<<<dim3((L.g + 255) / 256, L.n), 256, 0, st>>>(L.g, L.first, S->ns, S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->dpair, S->W + L.w_off);
-    UFE_LAUNCH_CHECK();
-  }
-  for (int l = nl - 1; l >= 0; l--) {
-    const NdLevelDev &L = S->lev[l];
-    k_nd_fwd<<<dim3(L.g / 8, 1, L.n), 256, 0, st>>>(L.g, L.p, L.first, S->ns, S->nb, S->F + L.f_off, S->W + L.w_off, S->Z + L.w_off);
-    UFE_LAUNCH_CHECK();
-    if (l > 0 && L.max_nb > 0) {
-      const NdLevelDev &P = S->lev[l - 1];
-      for (int want = 0; want < 2; want++) {
-        k_nd_vec_updown<<<dim3((L.max_nb + 127) / 128, L.n), 128, 0, st>>>(L.g, L.p, L.first, P.g, S->W + L.w_off, S->W + P.w_off, S->nb,
-                                                                           S->parent, S->slot, S->up_off, S->upmap, want, 0);
+// ------------------------------------------------------------------------------------------------------------------
+// launch sequences
+// ------------------------------------------------------------------------------------------------------------------
+static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *dval) {
+  const int N = S->N, tb = 256, nf = S->n_fronts;
+  k_mf_scale<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dself, S->dpair); UFE_LAUNCH_CHECK();
+  UFE_CUDA(cudaMemsetAsync(S->F, 0, S->f_doubles * sizeof(double), st));
+  k_mf_assemble<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dst, S->F); UFE_LAUNCH_CHECK();
+  if (nf > 0) { k_mf_pad<<<(nf + 7) / 8, 256, 0, st>>>(nf, S->ns, S->p, S->ld, S->foff, S->F); UFE_LAUNCH_CHECK(); }
+  for (int l = (int)S->lev.size() - 1; l >= 0; l--) {
+    const MfLevel &L = S->lev[l];
+    // Schur complements of children on other ranks arrive first (the level below is complete on every rank)
+    for (const MfLink &K : S->links) {
+      if (K.level != l || K.nb == 0) continue;
+      const size_t cnt = (size_t)K.nb * K.nb;
+      if (K.child_front >= 0) {
+        k_mf_pack<<<dim3((K.nb + 31) / 32, (K.nb + 31) / 32), dim3(32, 8), 0, st>>>(K.nb, K.child_ld, S->F + K.child_schur, S->F + K.f_buf);
         UFE_LAUNCH_CHECK();
+        UFE_NCCL(ncclSend(S->F + K.f_buf, cnt, ncclDouble, K.parent_rank, S->nccl, st));
+      } else {
+        UFE_NCCL(ncclRecv(S->F + K.f_buf, cnt, ncclDouble, K.child_rank, S->nccl, st));
       }
+      g_launch_count++;
     }
-  }
-  for (int l = 0; l < nl; l++) {
-    const NdLevelDev &L = S->lev[l];
-    if (l > 0 && L.max_nb > 0) {
-      const NdLevelDev &P = S->lev[l - 1];
-      k_nd_vec_updown<<<dim3((L.max_nb + 127) / 128, L.n), 128, 0, st>>>(L.g, L.p, L.first, P.g, S->W + L.w_off, S->W + P.w_off, S->nb,
-                                                                         S->parent, S->slot, S->up_off, S->upmap, 0, 1);
+    if (L.n == 0) continue;
+    if (L.n_internal > 0) {
+      const int t = (L.maxG + 31) / 32;
+      k_mf_extend<<<dim3(t, t, L.n), dim3(32, 8), 0, st>>>(L.first, S->G, S->ld, S->foff, S->woff, S->c_f[0], S->c_f[1], S->c_ld[0],
+                                                            S->c_ld[1], S->pinv[0], S->pinv[1], S->F);
       UFE_LAUNCH_CHECK();
     }
-    k_nd_bwd<<<dim3(L.p / 8, 1, L.n), 256, 0, st>>>(L.g, L.p, L.first, S->ns, S->nb, S->sep_off, S->sepdof, S->scale, S->F + L.f_off,
-                                                    S->W + L.w_off, S->Z + L.w_off, x, accumulate);
-    UFE_LAUNCH_CHECK();
+    for (int b = 0; b < L.steps;) {
+      const MfStep &sp = L.step[b];
+      // few fronts: split the L panel of a front over several CTAs (each inverts the pivot block itself)
+      auto split = [&](int n_active, int extent, int *chunk) {
+        int nx = 1; *chunk = 1 << 28;
+        if (n_active < 96 && extent > 64) {
+          nx = std::min((extent + MFB - 1) / MFB, std::max(1, 296 / n_active));
+          *chunk = ((extent + nx - 1) / nx + MFB - 1) / MFB * MFB;
+          nx = (extent + *chunk - 1) / *chunk;
+        }
+        return std::max(nx, 1);
+      };
+      int chunk = 0;
+      const int nx = split(sp.n_active, sp.max_trail, &chunk);
+      k_mf_panel<<<dim3(nx, sp.n_active), 1024, 0, st>>>(L.first, b, chunk, S->G, S->ld, S->foff, S->dioff, S->F, S->Dinv);
+      UFE_LAUNCH_CHECK();
+      // second block of a 64-wide outer step: only when the same fronts are active in it (they are a prefix, too)
+      int nkb = 1, n_upd = sp.n_active, trail = sp.max_trail;
+      if (S->k64 && b + 1 < L.steps && L.step[b + 1].n_active == sp.n_active) {
+        const MfStep &s2 = L.step[b + 1];
+        int ch2 = 0;
+        const int nx2 = split(s2.n_active, s2.max_trail, &ch2);
+        k_mf_panel2<<<dim3(2 * nx2, s2.n_active), 1024, 0, st>>>(L.first, b + 1, nx2, ch2, S->G, S->ld, S->foff, S->dioff, S->F, S->Dinv);
+        UFE_LAUNCH_CHECK();
+        nkb = 2; n_upd = s2.n_active; trail = s2.max_trail;
+      }
+      b += nkb;
+      if (trail <= 0) continue;
+      const long long big_ctas = (long long)((trail + 127) / 128) * ((trail + 127) / 128) * n_upd;
+      if (trail >= 192 && big_ctas >= 120) {
+        const int t = (trail + 127) / 128;
+        k_mf_update<16><<<dim3(t, t, n_upd), 256, (128 * (MFB + 1) + MFB * 128) * sizeof(double), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
+      } else {
+        const int t = (trail + 63) / 64;
+        k_mf_update<8><<<dim3(t, t, n_upd), 64, (64 * (MFB + 1) + MFB * 64) * sizeof(double), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
+      }
+      UFE_LAUNCH_CHECK();
+    }
   }
   return UFE_OK;
+}
+
+// x (+)= A^-1 r with the factors; r: full-length right-hand side, x: full-length solution (this rank writes the unknowns
+// of its own fronts only).  premul: r is first multiplied by the 2x2 diagonal blocks.
+static int mf_apply_launches(ufe_nd_solver *S, cudaStream_t st, const double *r, double *x, int accumulate, int premul) {
+  const int nl = (int)S->lev.size();
+  for (int l = nl - 1; l >= 0; l--) {            // forward sweep, deepest level first
+    const MfLevel &L = S->lev[l];
+    for (const MfLink &K : S->links) {           // boundary vectors of children on other ranks
+      if (K.level != l || K.nb == 0) continue;
+      if (K.child_front >= 0) UFE_NCCL(ncclSend(S->W + K.child_wb, (size_t)K.nb, ncclDouble, K.parent_rank, S->nccl, st));
+      else UFE_NCCL(ncclRecv(S->W + K.w_buf, (size_t)K.nb, ncclDouble, K.child_rank, S->nccl, st));
+      g_launch_count++;
+    }
+    if (L.n == 0) continue;
+    k_mf_fwd<<<L.n, 1024, 0, st>>>(L.first, S->ns, S->p, S->G, S->ld, S->foff, S->woff, S->c_w[0], S->c_w[1], S->pinv[0], S->pinv[1],
+                                   S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->dpair, S->F, S->W);
+    UFE_LAUNCH_CHECK();
+  }
+  for (int l = 0; l < nl; l++) {                 // backward sweep, root first
+    const MfLevel &L = S->lev[l];
+    if (L.n > 0) {
+      k_mf_bwd<<<L.n, 1024, 0, st>>>(L.first, S->ns, S->p, S->nb, S->ld, S->foff, S->woff, S->pwoff, S->up_off, S->upmap, S->dioff,
+                                     S->sep_off, S->sepdof, S->scale, S->F, S->Dinv, S->W, x, accumulate);
+      UFE_LAUNCH_CHECK();
+    }
+    for (const MfLink &K : S->links) {           // the parent's solution vector goes to the child on the other rank
+      if (K.level != l || K.nb == 0) continue;
+      if (K.parent_front >= 0) UFE_NCCL(ncclSend(S->W + K.parent_w, (size_t)K.Gp, ncclDouble, K.child_rank, S->nccl, st));
+      else UFE_NCCL(ncclRecv(S->W + K.w_buf, (size_t)K.Gp, ncclDouble, K.parent_rank, S->nccl, st));
+      g_launch_count++;
+    }
+  }
+  return UFE_OK;
+}
+
+// Runs a launch sequence through a cached CUDA graph (single rank): the sequences are static per pattern, so they are
+// captured once per distinct argument set and replayed (the small-mesh solves are bound by launch latency otherwise).
+// Inside somebody else's capture the kernels are issued directly and become part of that graph.
+template <class Fn>
+static int mf_run(ufe_nd_solver *S, cudaStream_t st, MfGraph *slots, int nslots, const void *a, const void *b, int k0, int k1, Fn fn) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  UFE_CUDA(cudaStreamIsCapturing(st, &cs));
+  if (!S->use_graphs || cs != cudaStreamCaptureStatusNone) return fn();
+  MfGraph *g = nullptr;
+  for (int i = 0; i < nslots; i++) if (slots[i].exec && slots[i].a == a && slots[i].b == b && slots[i].k0 == k0 && slots[i].k1 == k1) { g = &slots[i]; break; }
+  if (!g) {
+    for (int i = 0; i < nslots; i++) if (!slots[i].exec) { g = &slots[i]; break; }
+    if (!g) { g = &slots[0]; mf_graph_drop(*g); }
+    const int64_t l0 = g_launch_count;
+    cudaGraph_t graph = nullptr;
+    UFE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = fn();
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != UFE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { ufe_set_error("nd_lu: graph capture failed: %s", cudaGetErrorString(ce)); return UFE_ERR_CUDA; }
+    const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { g->exec = nullptr; ufe_set_error("nd_lu: graph instantiation failed: %s", cudaGetErrorString(ie)); return UFE_ERR_CUDA; }
+    g->a = a; g->b = b; g->k0 = k0; g->k1 = k1; g->nodes = (int)(g_launch_count - l0);
+    g_launch_count = l0;
+  }
+  UFE_CUDA(cudaGraphLaunch(g->exec, st));
+  g_launch_count += g->nodes;
+  return UFE_OK;
+}
+
+static int mf_factor_device(ufe_nd_solver *S, cudaStream_t st, const double *dval) {
+  UFE_TRY(mf_run(S, st, &S->g_factor, 1, dval, nullptr, 0, 0, [&]() { return mf_factor_launches(S, st, dval); }));
+  S->factored = true;
+  return UFE_OK;
+}
+static int mf_apply_device(ufe_nd_solver *S, cudaStream_t st, const double *r, double *x, int accumulate, int premul) {
+  return mf_run(S, st, S->g_apply, 6, r, x, accumulate, premul, [&]() { return mf_apply_launches(S, st, r, x, accumulate, premul); });
 }
 
 // val: host values of A in the order of the pattern given to ufe_nd_solver_create
 extern "C" int ufe_nd_solver_factor(ufe_nd_solver *S, const double *val) {
-  if (!S || !val) { ufe_set_error("ufe_nd_solver_factor: bad argument"); return UFE_ERR_INVALID; }
+  if (!S || !val || !S->val) { ufe_set_error("ufe_nd_solver_factor: bad argument"); return UFE_ERR_INVALID; }
   UFE_CUDA(cudaMemcpyAsync(S->val, val, (size_t)S->nnz * sizeof(double), cudaMemcpyHostToDevice, S->st));
   UFE_CUDA(cudaEventRecord(S->e0, S->st));
-  UFE_TRY(nd_factor_device(S, S->st, S->val));
+  UFE_TRY(mf_factor_device(S, S->st, S->val));
   UFE_CUDA(cudaEventRecord(S->e1, S->st));
   UFE_CUDA(cudaStreamSynchronize(S->st));
   UFE_CUDA(cudaEventElapsedTime(&S->factor_ms, S->e0, S->e1));
@@ -504,13 +875,13 @@ extern "C" int ufe_nd_solver_solve(ufe_nd_solver *S, const double *b, double *x,
   const int N = S->N, tb = 256;
   UFE_CUDA(cudaMemcpyAsync(S->b, b, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, S->st));
   UFE_CUDA(cudaEventRecord(S->e0, S->st));
-  UFE_TRY(nd_apply_device(S, S->st, S->b, S->x, 0, 0));
+  UFE_TRY(mf_apply_device(S, S->st, S->b, S->x, 0, 0));
   for (int it = 0; it < n_refine; it++) {
-    k_nd_residual<<<(N + tb - 1) / tb, tb, 0, S->st>>>(N, S->ptr, S->ind, S->val, S->b, S->x, S->r); UFE_LAUNCH_CHECK();
-    UFE_TRY(nd_apply_device(S, S->st, S->r, S->x, 1, 0));
+    k_mf_residual<<<(N + tb - 1) / tb, tb, 0, S->st>>>(N, S->ptr, S->ind, S->val, S->b, S->x, S->r); UFE_LAUNCH_CHECK();
+    UFE_TRY(mf_apply_device(S, S->st, S->r, S->x, 1, 0));
   }
   UFE_CUDA(cudaEventRecord(S->e1, S->st));
-  k_nd_residual<<<(N + tb - 1) / tb, tb, 0, S->st>>>(N, S->ptr, S->ind, S->val, S->b, S->x, S->r); UFE_LAUNCH_CHECK();
+  k_mf_residual<<<(N + tb - 1) / tb, tb, 0, S->st>>>(N, S->ptr, S->ind, S->val, S->b, S->x, S->r); UFE_LAUNCH_CHECK();
   UFE_CUDA(cudaMemcpyAsync(x, S->x, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, S->st));
   std::vector<double> hr(N);
   UFE_CUDA(cudaMemcpyAsync(hr.data(), S->r, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, S->st));
@@ -524,7 +895,8 @@ extern "C" int ufe_nd_solver_solve(ufe_nd_solver *S, const double *b, double *x,
   return UFE_OK;
 }
 
-// timings of the last factor / solve call (CUDA events on the solver's stream), storage and flop count of the sweep
+// timings of the last factor / solve call (CUDA events on the solver's stream), storage and flop count of the
+// factorisation (2/3 p^3 + 2 p^2 nb + 2 p nb^2 per front, on the 32-padded pivot counts)
 extern "C" int ufe_nd_solver_info(const ufe_nd_solver *S, double *factor_ms, double *solve_ms, double *front_bytes, double *factor_flops) {
   if (!S) { ufe_set_error("null solver"); return UFE_ERR_INVALID; }
   if (factor_ms) *factor_ms = S->factor_ms;
@@ -538,35 +910,125 @@ extern "C" int ufe_nd_solver_info(const ufe_nd_solver *S, double *factor_ms, dou
 // the same solver as the exact preconditioner of the Krylov loop (krylov_pc = UFE_PC_ND_LU; ufe_pclu.cu dispatches here).
 // The Krylov loop iterates on B A x = B b with B the 2x2 block-Jacobi scaling folded in at assembly time
 // (ufe_assembly.cu), so the preconditioner is  z = (B A)^-1 r = A^-1 (D r),  D = the 2x2 diagonal blocks of A.
+// Several ranks: the rows of A are partitioned into contiguous strips (partition_list); pattern (once) and values
+// (per factorisation) are gathered so that every rank can assemble the fronts it owns.
 // ------------------------------------------------------------------------------------------------------------------
-int ufe_nd_pc_create(cudaStream_t st, const DevSystem &S, int nT, const double *gcx, const double *gcy, int leaf, ufe_nd_solver **out) {
-  *out = nullptr;
-  if (S.m_loc != S.N || S.r1 != 1 || S.N != 2 * nT) {
-    ufe_set_error("nd_lu preconditioner: the rows of the system must not be partitioned (one GPU)"); return UFE_ERR_INVALID;
+// all-gather of contiguous per-rank pieces of different sizes (rank order = strip order): out = [piece_0 | piece_1 | ...]
+static int mf_gatherv(ncclComm_t nccl, cudaStream_t st, int rank, const void *mine, const std::vector<size_t> &bytes, char *out) {
+  size_t off = 0;
+  UFE_NCCL(ncclGroupStart());
+  for (size_t q = 0; q < bytes.size(); q++) {
+    UFE_NCCL(ncclBroadcast((int)q == rank ? mine : (const void *)(out + off), out + off, bytes[q], ncclChar, (int)q, nccl, st));
+    off += bytes[q];
   }
-  std::vector<int> ptr(S.N + 1), ind(S.nnz);
+  UFE_NCCL(ncclGroupEnd());
+  g_launch_count++;
+  return UFE_OK;
+}
+
+int ufe_nd_pc_create(cudaStream_t st, const DevSystem &S, const Comm *comm, int nT, const double *gcx, const double *gcy, int leaf,
+                     ufe_nd_solver **out) {
+  *out = nullptr;
+  const int P = comm ? comm->nranks : 1, me = comm ? comm->rank : 0;
+  if (S.N != 2 * nT) { ufe_set_error("nd_lu preconditioner: the system must be the stiffness system of the mesh (N = 2 nTri)"); return UFE_ERR_INVALID; }
+  if (P == 1 && (S.m_loc != S.N || S.r1 != 1)) { ufe_set_error("nd_lu preconditioner: one rank must hold all rows"); return UFE_ERR_INVALID; }
   UFE_CUDA(cudaStreamSynchronize(st));
-  UFE_CUDA(cudaMemcpy(ptr.data(), S.ptr, ptr.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  UFE_CUDA(cudaMemcpy(ind.data(), S.ind, ind.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  for (int &v : ptr) v -= 1;
-  for (int &v : ind) v -= 1;
-  // block pattern over triangles
+  std::vector<int> ptr(S.N + 1), ind;
+  std::vector<size_t> vcnt(P, 0), rcnt(P, 0);
+  int *g_ptr = nullptr, *g_ind = nullptr;
+  if (P == 1) {
+    ind.resize(S.nnz);
+    UFE_CUDA(cudaMemcpy(ptr.data(), S.ptr, ptr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    UFE_CUDA(cudaMemcpy(ind.data(), S.ind, ind.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  } else {
+    // sizes first, then row lengths and column indices
+    long long mine[2] = {S.m_loc, S.nnz}, *d_sz = nullptr;
+    std::vector<long long> all(2 * P);
+    UFE_CUDA(cudaMalloc(&d_sz, sizeof(long long) * 2 * (P + 1)));
+    UFE_CUDA(cudaMemcpy(d_sz + 2 * P, mine, sizeof mine, cudaMemcpyHostToDevice));
+    UFE_NCCL(ncclAllGather(d_sz + 2 * P, d_sz, 2, ncclInt64, comm->nccl, st));
+    UFE_CUDA(cudaStreamSynchronize(st));
+    UFE_CUDA(cudaMemcpy(all.data(), d_sz, sizeof(long long) * 2 * P, cudaMemcpyDeviceToHost));
+    cudaFree(d_sz);
+    size_t rows = 0, nnz = 0;
+    std::vector<size_t> pb(P), ib(P);
+    for (int q = 0; q < P; q++) { rcnt[q] = (size_t)all[2 * q]; vcnt[q] = (size_t)all[2 * q + 1]; pb[q] = (rcnt[q] + 1) * sizeof(int); ib[q] = vcnt[q] * sizeof(int); rows += rcnt[q]; nnz += vcnt[q]; }
+    if ((int)rows != S.N) { ufe_set_error("nd_lu preconditioner: the strips of the ranks do not add up to the whole system"); return UFE_ERR_INVALID; }
+    int *d_lp = nullptr;
+    UFE_CUDA(cudaMalloc(&d_lp, sizeof(int) * (rows + P)));
+    UFE_CUDA(cudaMalloc(&g_ind, sizeof(int) * std::max<size_t>(1, nnz)));
+    UFE_TRY(mf_gatherv(comm->nccl, st, me, S.ptr, pb, reinterpret_cast<char *>(d_lp)));
+    UFE_TRY(mf_gatherv(comm->nccl, st, me, S.ind, ib, reinterpret_cast<char *>(g_ind)));
+    UFE_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> lp(rows + P);
+    UFE_CUDA(cudaMemcpy(lp.data(), d_lp, lp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_lp);
+    ind.resize(nnz);
+    UFE_CUDA(cudaMemcpy(ind.data(), g_ind, nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    size_t r = 0, o = 0, base = 0;
+    for (int q = 0; q < P; q++) {                       // local 1-based offsets -> global 1-based offsets
+      for (size_t i = 0; i < rcnt[q]; i++) ptr[r + i] = (int)(base + lp[o + i]);
+      r += rcnt[q]; o += rcnt[q] + 1; base += vcnt[q];
+    }
+    ptr[S.N] = (int)(base + 1);
+    UFE_CUDA(cudaMalloc(&g_ptr, sizeof(int) * (S.N + 1)));
+    UFE_CUDA(cudaMemcpy(g_ptr, ptr.data(), sizeof(int) * (S.N + 1), cudaMemcpyHostToDevice));
+  }
+  // block pattern over triangles (0-based, sorted)
   std::vector<int> bptr(nT + 1, 0), bind, row;
+  bind.reserve(ind.size() / 3);
   for (int t = 0; t < nT; t++) {
     row.clear();
-    for (int k = ptr[2 * t]; k < ptr[2 * t + 2]; k++) row.push_back(ind[k] >> 1);
+    for (int k = ptr[2 * t] - 1; k < ptr[2 * t + 2] - 1; k++) row.push_back((ind[k] - 1) >> 1);
     std::sort(row.begin(), row.end());
     row.erase(std::unique(row.begin(), row.end()), row.end());
     bind.insert(bind.end(), row.begin(), row.end());
     bptr[t + 1] = (int)bind.size();
   }
   ufe_nd_tree *T = nullptr;
-  UFE_TRY(ufe_nd_analyse(nT, gcx, gcy, bptr.data(), bind.data(), leaf, &T));
-  const int rc = ufe_nd_solver_create(T, S.N, ptr.data(), ind.data(), out);
+  int rc = ufe_nd_analyse(nT, gcx, gcy, bptr.data(), bind.data(), leaf, &T);
+  if (rc == UFE_OK) rc = mf_create(T, S.N, ptr.data(), ind.data(), P == 1 ? S.ptr : g_ptr, P == 1 ? S.ind : g_ind, me, P, comm ? comm->nccl : nullptr, out);
   ufe_nd_tree_free(T);
-  return rc;
+  if (rc != UFE_OK) { cudaFree(g_ptr); cudaFree(g_ind); return rc; }
+  ufe_nd_solver *M = *out;
+  if (P > 1) {
+    M->own_pattern = true;                 // g_ptr / g_ind belong to the solver now
+    M->val_counts = vcnt; M->row_counts = rcnt;
+    if (cudaMalloc((void **)&M->val, std::max<size_t>(1, (size_t)M->nnz) * sizeof(double)) != cudaSuccess) {
+      ufe_set_error("nd_lu preconditioner: out of device memory"); ufe_nd_solver_free(M); *out = nullptr; return UFE_ERR_CUDA;
+    }
+  }
+  return UFE_OK;
 }
 
-int ufe_nd_pc_factor(cudaStream_t st, ufe_nd_solver *S, const double *dval) { return nd_factor_device(S, st, dval); }
+// dval: the rows of this rank (S.val)
+int ufe_nd_pc_factor(cudaStream_t st, ufe_nd_solver *S, const double *dval) {
+  if (S->nranks == 1) return mf_factor_device(S, st, dval);
+  std::vector<size_t> bytes(S->nranks);
+  for (int q = 0; q < S->nranks; q++) bytes[q] = S->val_counts[q] * sizeof(double);
+  UFE_TRY(mf_gatherv(S->nccl, st, S->rank, dval, bytes, reinterpret_cast<char *>(S->val)));
+  return mf_factor_device(S, st, S->val);
+}
 
-int ufe_nd_pc_apply(cudaStream_t st, ufe_nd_solver *S, const double *r, double *z) { return nd_apply_device(S, st, r, z, 0, 1); }
+// r, z: the rows of this rank
+int ufe_nd_pc_apply(cudaStream_t st, ufe_nd_solver *S, const double *r, double *z) {
+  if (S->nranks == 1) return mf_apply_device(S, st, r, z, 0, 1);
+  std::vector<size_t> bytes(S->nranks);
+  size_t r0 = 0;
+  for (int q = 0; q < S->nranks; q++) { bytes[q] = S->row_counts[q] * sizeof(double); if (q < S->rank) r0 += S->row_counts[q]; }
+  UFE_TRY(mf_gatherv(S->nccl, st, S->rank, r, bytes, reinterpret_cast<char *>(S->b)));
+  UFE_CUDA(cudaMemsetAsync(S->x, 0, (size_t)S->N * sizeof(double), st));
+  UFE_TRY(mf_apply_device(S, st, S->b, S->x, 0, 1));
+  UFE_NCCL(ncclAllReduce(S->x, S->x, (size_t)S->N, ncclDouble, ncclSum, S->nccl, st));
+  g_launch_count++;
+  const int n = (int)S->row_counts[S->rank];
+  if (n > 0) { k_mf_copy_slice<<<(n + 255) / 256, 256, 0, st>>>(n, S->x + r0, z); UFE_LAUNCH_CHECK(); }
+  return UFE_OK;
+}
+
+// storage and flop count of this rank's part of the factorisation
+void ufe_nd_pc_info(const ufe_nd_solver *S, double *front_bytes, double *flops, int *n_fronts) {
+  if (front_bytes) *front_bytes = 8.0 * (double)S->f_doubles;
+  if (flops) *flops = S->flops;
+  if (n_fronts) *n_fronts = S->n_fronts;
+}

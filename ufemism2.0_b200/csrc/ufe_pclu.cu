@@ -548,13 +548,13 @@ int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int replicate, size_t ma
 }
 
 // wide meshes: the banded blocks do not fit, the nested-dissection multifrontal solver does (ufe_nd_numeric.cu)
-int ufe_pclu_setup_nd(cudaStream_t st, const DevSystem &S, int nT, const double *gcx, const double *gcy, PcLU **out) {
+int ufe_pclu_setup_nd(cudaStream_t st, const DevSystem &S, const Comm *comm, int nT, const double *gcx, const double *gcy, PcLU **out) {
   *out = nullptr;
   const char *e = getenv("UFE_ND_LEAF");
-  const int leaf = e && atoi(e) > 0 ? atoi(e) : 96;
+  const int leaf = e && atoi(e) > 0 ? atoi(e) : 64;
   PcLU *pc = new PcLU();
   pc->n_loc = S.m_loc;
-  const int rc = ufe_nd_pc_create(st, S, nT, gcx, gcy, leaf, &pc->nd);
+  const int rc = ufe_nd_pc_create(st, S, comm, nT, gcx, gcy, leaf, &pc->nd);
   if (rc != UFE_OK) { delete pc; return rc; }
   *out = pc;
   return UFE_OK;

@@ -1,6 +1,15 @@
 """Named workloads (BASELINE.json ``configs``): synthetic mesh + geometry + the config keys
 of the reference's own ``.cfg`` for that experiment (values cited; the ``.cfg`` files
 themselves are not read at run time -- /root/reference does not exist on the GPU box).
+
+All meshes are Delaunay triangulations of the jittered lattice points (``delaunay=True``), like
+the reference's own Delaunay-refined meshes.  The alternating-diagonal ("union jack") lattice
+triangulation of round 1 has vertices with 4 and 8 neighbours alternately; on it the reference's
+least-squares operators carry checkerboard-like near-null modes, the Picard iteration of the
+reference algorithm does not converge on any case with an ice shelf or ice-free part (oracle and
+GPU alike; profiles/r2_notes.md) and GMRES(30)/ILU(0) runs into its 10 000 cap.  On the Delaunay
+meshes the same algorithm converges monotonically and the oracle's GMRES needs ~100-400
+iterations per solve -- the reference's own operating point (BASELINE.md scoreboard).
 """
 from __future__ import annotations
 
@@ -17,11 +26,11 @@ def _periodic(C: Config):
     return C
 
 
-def ISMIP_HOM(exp: str, L: float, n: int = 41, seed=synthetic.SEED):
+def ISMIP_HOM(exp: str, L: float, n: int = 41, seed=synthetic.SEED, delaunay=True):
     """automated_testing/integrated_tests/idealised/ISMIP-HOM/config_ISMIP_HOM_{A,C}_<L>_DIVA.cfg:
     domain [-L,L]^2, resolution L/20, periodic BCs, uniform A = 1e-16, eps0^2 = 1e-12,
     Picard tol 5e-7 / <= 5000 its / relax 0.4, Krylov 1e-6 / 1e-4."""
-    mesh = synthetic.lattice_mesh(-L, L, -L, L, n, n, seed=seed)
+    mesh = synthetic.lattice_mesh(-L, L, -L, L, n, n, seed=seed, delaunay=delaunay)
     C = _periodic(Config(visc_it_norm_dUV_tol=5e-7, visc_it_nit=5000, visc_it_relax=0.4,
                          stress_balance_PETSc_rtol=1e-6, stress_balance_PETSc_abstol=1e-4,
                          choice_ice_rheology_Glen="uniform", uniform_Glens_flow_factor=1e-16,
@@ -38,11 +47,11 @@ def ISMIP_HOM(exp: str, L: float, n: int = 41, seed=synthetic.SEED):
     return mesh, C, ice
 
 
-def SSA_icestream(nx=21, ny=81):
+def SSA_icestream(nx=21, ny=81, delaunay=True):
     """automated_testing/integrated_tests/idealised/SSA_icestream/config_04_4km.cfg:65-68,150-153,
     253-254,468: domain +-400 km, A = 1e-18, H = 2000, dh/dx = -3e-4, L = 150 km, m = 1,
     Krylov 1e-7 / 1e-5; BC_u west/east 'infinite_SSA_icestream', v 'zero' (SSA solve)."""
-    mesh = synthetic.lattice_mesh(-400e3, 400e3, -400e3, 400e3, nx, ny)
+    mesh = synthetic.lattice_mesh(-400e3, 400e3, -400e3, 400e3, nx, ny, delaunay=delaunay)
     C = Config(choice_stress_balance_approximation="SSA", choice_sliding_law="idealised",
                choice_idealised_sliding_law="SSA_icestream", choice_ice_rheology_Glen="uniform",
                uniform_Glens_flow_factor=1e-18, refgeo_idealised_SSA_icestream_Hi=2000.0,
@@ -57,13 +66,13 @@ def SSA_icestream(nx=21, ny=81):
     return mesh, C, ice
 
 
-def MISMIP_8km(h=8e3, seed=synthetic.SEED):
+def MISMIP_8km(h=8e3, seed=synthetic.SEED, delaunay=True):
     """config-files/config_MISMIP_8km_spinup_for_scaling.cfg: 2000x2000 km, Zoet-Iverson
     phi = 10 deg, Martin2011 hydrology, A = 1e-16, Picard 5e-5 / 50 / relax 0.4,
     Krylov 1e-4 / 1e-3.  Geometry: MISMIP_mod bed (idealised_geometries.f90:214-241)
     with a synthetic dome (the reference spins up from 100 m of ice)."""
     n = int(round(2000e3 / h)) + 1
-    mesh = synthetic.lattice_mesh(-1000e3, 1000e3, -1000e3, 1000e3, n, n, seed=seed)
+    mesh = synthetic.lattice_mesh(-1000e3, 1000e3, -1000e3, 1000e3, n, n, seed=seed, delaunay=delaunay)
     x, y = mesh.V[:, 0], mesh.V[:, 1]
     r = np.sqrt(x * x + y * y)
     Hb = 150.0 - 400.0 * r / 750000.0
@@ -78,15 +87,15 @@ def MISMIP_8km(h=8e3, seed=synthetic.SEED):
     return mesh, C, ice
 
 
-def MISMIPplus(h=2e3, seed=synthetic.SEED, calving_front=None):
+def MISMIPplus(h=2e3, seed=synthetic.SEED, calving_front=None, delaunay=True, profile="surface"):
     """config-files/benchmarks/MISMIP+/config_MISMIPplus_2km_spinup.cfg: 800x80 km,
     Schoof2005 (alpha^2 = 0.5, beta^2 = 1e4), A = 1.428e-17, Picard 5e-5 / 50 / relax 0.2,
     Krylov 1e-7 / 1e-5, BC u: west zero, others infinite; v: zero everywhere.  Uniform
     resolution h (the reference refines to 2 km only near the grounding line)."""
     nx = int(round(800e3 / h)) + 1
     ny = int(round(80e3 / h)) + 1
-    mesh = synthetic.lattice_mesh(0.0, 800e3, -40e3, 40e3, nx, ny, seed=seed)
-    ice = synthetic.geometry_MISMIPplus(mesh, calving_front=calving_front)
+    mesh = synthetic.lattice_mesh(0.0, 800e3, -40e3, 40e3, nx, ny, seed=seed, delaunay=delaunay)
+    ice = synthetic.geometry_MISMIPplus(mesh, calving_front=calving_front, profile=profile)
     C = Config(visc_it_norm_dUV_tol=5e-5, visc_it_nit=50, visc_it_relax=0.2,
                stress_balance_PETSc_rtol=1e-7, stress_balance_PETSc_abstol=1e-5,
                choice_sliding_law="Schoof2005", choice_ice_rheology_Glen="uniform",
@@ -98,13 +107,13 @@ def MISMIPplus(h=2e3, seed=synthetic.SEED, calving_front=None):
     return mesh, C, ice
 
 
-def antarctic(n_vertices=1_000_000, seed=synthetic.SEED):
+def antarctic(n_vertices=1_000_000, seed=synthetic.SEED, delaunay=True):
     """Synthetic Antarctic-scale case: config-files/config_ant_template.cfg domain
     (6080x6080 km) and solver keys (Zoet-Iverson phi = 45 deg, Huybrechts1992 rheology with
     m_enh_shelf = 0.58, Picard 1e-3 / 500 / relax 0.2, Krylov 1e-5 / 1e-5, vel_max 4000,
     beta_max 1e9, delta_v 1e-2, eps0^2 = 1e-12, subgrid exponent 0), synthetic dome."""
     n = int(round(np.sqrt(n_vertices)))
-    mesh = synthetic.lattice_mesh(-3040e3, 3040e3, -3040e3, 3040e3, n, n, seed=seed)
+    mesh = synthetic.lattice_mesh(-3040e3, 3040e3, -3040e3, 3040e3, n, n, seed=seed, delaunay=delaunay)
     ice = synthetic.geometry_antarctic_dome(mesh, seed=seed)
     ice.till_friction_angle[:] = 45.0
     # synthetic temperature: cold surface, warmer base

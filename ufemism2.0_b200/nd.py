@@ -80,7 +80,9 @@ def block_pattern(ptr: np.ndarray, ind: np.ndarray, nT: int):
 
 
 class Solver:
-    """Exact multifrontal solve of a stiffness system on the device.  ptr / ind: 0-based scalar CSR pattern (N = 2 nT)."""
+    """Exact multifrontal solve of a stiffness system on the device.  ptr / ind: scalar CSR pattern (N = 2 nT) in the
+    reference's 1-based convention (type_sparse_matrix_CSR_dp: ptr(1) = 1, column indices from 1), as every other entry
+    point of the C ABI takes it."""
 
     def __init__(self, centroids: np.ndarray, ptr: np.ndarray, ind: np.ndarray, leaf_triangles: int = 96):
         self._lib = capi.lib()
@@ -89,7 +91,9 @@ class Solver:
         self.N = 2 * nT
         ptr = np.ascontiguousarray(ptr, dtype=np.int32)
         ind = np.ascontiguousarray(ind, dtype=np.int32)
-        bptr, bind = block_pattern(ptr, ind, nT)
+        if ptr[0] != 1:
+            raise ValueError("nd.Solver: ptr / ind must be 1-based (ptr[0] == 1)")
+        bptr, bind = block_pattern(ptr - 1, ind - 1, nT)
         x = np.ascontiguousarray(centroids[:, 0], dtype=np.float64)
         y = np.ascontiguousarray(centroids[:, 1], dtype=np.float64)
         check(self._lib.ufe_nd_analyse(nT, vp(x), vp(y), vp(bptr), vp(bind), int(leaf_triangles), ct.byref(self._T)))

@@ -200,26 +200,47 @@ def mismipplus_bed(x, y):
     return np.maximum(Bx + By, zbdeep)
 
 
-def geometry_MISMIPplus(mesh: Mesh, x_gl=450e3, H0=1500.0, H_shelf=300.0, calving_front=None) -> IceInputs:
-    """MISMIP+ bed with a synthetic Vialov-like grounded profile to x_gl and a shelf
-    thinning to ``H_shelf`` at x = 640 km.  ``calving_front=None`` (default):
-    the shelf continues at ``H_shelf`` to the domain edge, so there is no ice-free ocean;
-    ``calving_front=640e3`` removes the ice beyond it.  With an ice-free part of the domain the
-    cold-start Picard iteration of the reference algorithm never reaches
-    ``visc_it_norm_dUV_tol`` (the velocities of the ice-free triangles keep oscillating at the
-    ``vel_max`` cap; the oracle's direct-solve loop shows the same), which makes a poor
-    benchmark step; without it the loop converges in 46 iterations at 4 km."""
+def geometry_MISMIPplus(mesh: Mesh, x_gl=450e3, H0=1500.0, H_shelf=300.0, calving_front=None, profile="surface",
+                        s0=1350.0) -> IceInputs:
+    """MISMIP+ bed (idealised_geometries.f90:357-401) with a synthetic ice body.
+
+    ``profile="surface"`` (default, round 2): the ice SURFACE is prescribed as a function of x only --
+    a parabola from ``s0`` at the divide to the floatation surface at ``x_gl`` (zero slope at the divide,
+    finite slope at the grounding line), then the surface of a shelf thinning linearly to ``H_shelf`` at
+    x = 640 km and flat beyond -- and the thickness follows from it: ``Hi = min(s - Hb, s / (1 - rho_i /
+    rho_w))``, i.e. grounded where the bed is above the floating draft (the channel walls), floating
+    elsewhere.  The surface is level across the channel, so the driving stress is along the flow as in a
+    MISMIP+ steady state (speeds up to ~100 m/yr).
+
+    ``profile="vialov"`` (round 1): thickness a function of x only, Vialov shape with an infinite slope at
+    the grounding line; on the 500 m high channel walls this gives 500 m of surface relief across 8 km,
+    velocities pinned at the ``vel_max`` cap and a Picard iteration that never converges.  Kept for the
+    round-1 test cases.
+
+    ``calving_front=640e3`` removes the ice beyond it (ice-free ocean)."""
     x, y = mesh.V[:, 0], mesh.V[:, 1]
     Hb = mismipplus_bed(x, y)
     SL = np.zeros(mesh.nV)
-    # floatation thickness at the grounding line keeps the profile continuous there
     Hb_gl = mismipplus_bed(np.array([x_gl]), np.array([0.0]))[0]
-    H_gl = max(H_shelf + 50.0, -Hb_gl * seawater_density / ice_density + 20.0)
-    s = np.clip(x / x_gl, 0.0, 1.0)
-    Hg = H_gl + (H0 - H_gl) * (1.0 - s ** (4.0 / 3.0)) ** (3.0 / 8.0)
-    t = np.clip((x - x_gl) / (640e3 - x_gl), 0.0, 1.0)
-    Hf = H_gl + (H_shelf - H_gl) * t
-    Hi = np.where(x <= x_gl, Hg, Hf)
+    if profile == "surface":
+        r = 1.0 - ice_density / seawater_density
+        s_gl = -Hb_gl * (seawater_density / ice_density) * r + 4.0     # just grounded on the centre line at x_gl
+        s_sh = H_shelf * r
+        sg = s_gl + (s0 - s_gl) * (1.0 - np.clip(x / x_gl, 0.0, 1.0) ** 2)
+        t = np.clip((x - x_gl) / (640e3 - x_gl), 0.0, 1.0)
+        sf = s_gl + (s_sh - s_gl) * t
+        s = np.where(x <= x_gl, sg, sf)
+        Hi = np.minimum(s - Hb, s / r)
+    elif profile == "vialov":
+        # floatation thickness at the grounding line keeps the profile continuous there
+        H_gl = max(H_shelf + 50.0, -Hb_gl * seawater_density / ice_density + 20.0)
+        s = np.clip(x / x_gl, 0.0, 1.0)
+        Hg = H_gl + (H0 - H_gl) * (1.0 - s ** (4.0 / 3.0)) ** (3.0 / 8.0)
+        t = np.clip((x - x_gl) / (640e3 - x_gl), 0.0, 1.0)
+        Hf = H_gl + (H_shelf - H_gl) * t
+        Hi = np.where(x <= x_gl, Hg, Hf)
+    else:
+        raise ValueError(profile)
     if calving_front is not None:
         Hi = np.where(x > calving_front, 0.0, Hi)
     return _finish_inputs(mesh, Hi, Hb, SL, hydrology="Martin2011")
