@@ -29,10 +29,14 @@
 #include "ufe_internal.cuh"
 #include "ufe_nd.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <numeric>
 
 #define MFB 32    // pivot block width
+// dynamic shared memory of k_mf_update: two pivot-block buffers of [T][33] + [32][T] doubles
+#define MF_UPD_SMEM(T) (2 * ((T) * (MFB + 1) + MFB * (T)) * sizeof(double))
 
 struct MfStep { int n_active, max_trail; };
 struct MfLevel {
@@ -84,7 +88,7 @@ struct ufe_nd_solver {
   float factor_ms = 0.f, solve_ms = 0.f;
   double flops = 0.0;
   bool factored = false;
-  int use_graphs = 1, k64 = 1;
+  int use_graphs = 1, k64 = 1, cl_max_fronts = 32;      // levels with at most this many (large) fronts use the cluster sweeps
   MfGraph g_factor, g_apply[6];
 };
 
@@ -202,6 +206,7 @@ __device__ __forceinline__ void mf_invert32(double (*S)[MFB + 1], double (*I2)[M
 
 // pivot step b of the fronts [first, first + gridDim.y): D_b^-1 (every CTA of a front inverts the 32 x 32 block itself;
 // it is not written here, the inverse goes to the side buffer) and the L panel rows of this CTA:  A_ib <- A_ib D_b^-1.
+// After the inversion the warps work on their own rows, two rows in flight each, without block-level barriers.
 __global__ void __launch_bounds__(1024)
 k_mf_panel(int first, int b, int rows_per_cta, const int *__restrict__ G_, const int *__restrict__ ld_,
            const long long *__restrict__ foff, const int *__restrict__ dioff, double *__restrict__ F, double *__restrict__ Dinv) {
@@ -210,7 +215,7 @@ k_mf_panel(int first, int b, int rows_per_cta, const int *__restrict__ G_, const
   const int r0 = (b + 1) * MFB;
   const int rbeg = r0 + blockIdx.x * rows_per_cta;
   if (blockIdx.x > 0 && rbeg >= G) return;
-  __shared__ double W1[MFB][MFB + 1], W2[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1];
+  __shared__ double W1[MFB][MFB + 1], W2[MFB][MFB + 1], Ip[MFB][MFB + 1], Xw[32][2][MFB];
   __shared__ int perm[MFB];
   const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
   double *A = F + foff[f];
@@ -219,16 +224,18 @@ k_mf_panel(int first, int b, int rows_per_cta, const int *__restrict__ G_, const
   mf_invert32(W1, W2, Ip, perm, i, j);
   if (blockIdx.x == 0) Dinv[((size_t)dioff[f] + b) * (MFB * MFB) + i * MFB + j] = Ip[i][j];
   const int rend = min(G, rbeg + rows_per_cta);
-  for (int r = rbeg; r < rend; r += MFB) {
-    const int row = r + i;
-    double *T = A + (size_t)row * ld + b * MFB;
-    X[i][j] = row < rend ? T[j] : 0.0;
-    __syncthreads();
-    double sum = 0.0;
+  for (int r = rbeg + i; r < rend; r += 64) {
+    double *T0 = A + (size_t)r * ld + b * MFB, *T1 = T0 + (size_t)32 * ld;
+    const bool two = r + 32 < rend;
+    const double x0 = T0[j], x1 = two ? T1[j] : 0.0;
+    Xw[i][0][j] = x0; Xw[i][1][j] = x1;
+    __syncwarp();
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < MFB; k++) sum += X[i][k] * Ip[k][j];
-    if (row < rend) T[j] = sum;
-    __syncthreads();
+    for (int k = 0; k < MFB; k++) { const double ip = Ip[k][j]; s0 += Xw[i][0][k] * ip; s1 += Xw[i][1][k] * ip; }
+    T0[j] = s0;
+    if (two) T1[j] = s1;
+    __syncwarp();
   }
 }
 
@@ -236,7 +243,7 @@ k_mf_panel(int first, int b, int rows_per_cta, const int *__restrict__ G_, const
 //   column part (blockIdx.x < nx_col):  D1 = A_11 - L_10 U_01,  D1^-1 -> side buffer,
 //                                       L_i1 = (A_i1 - L_i0 U_01) D1^-1   for the rows i > b1 of this CTA,
 //   row part (blockIdx.x >= nx_col):    U_1j = A_1j - L_10 U_0j            for the columns j > b1 of this CTA.
-// The two parts read and write disjoint blocks, so they share one launch.
+// The two parts read and write disjoint blocks, so they share one launch.  Warps work independently after the set-up.
 __global__ void __launch_bounds__(1024)
 k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_, const int *__restrict__ ld_,
             const long long *__restrict__ foff, const int *__restrict__ dioff, double *__restrict__ F, double *__restrict__ Dinv) {
@@ -246,13 +253,15 @@ k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_
   const bool colpart = (int)blockIdx.x < nx_col;
   const int cbeg = r1 + (colpart ? (int)blockIdx.x : (int)blockIdx.x - nx_col) * chunk;
   if (cbeg >= G && !(colpart && blockIdx.x == 0)) return;
-  __shared__ double W1[MFB][MFB + 1], W2[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1];
+  __shared__ double Wb[2 * MFB * (MFB + 1)], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1];
   __shared__ int perm[MFB];
+  double(*W1)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(Wb), (*W2)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(Wb + MFB * (MFB + 1));
+  double(*Xw)[2][MFB] = reinterpret_cast<double(*)[2][MFB]>(Wb);      // per-warp staging rows; reuses the inversion work space
   const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
   double *A = F + foff[f];
   const int cend = min(G, cbeg + chunk);
+  X[i][j] = A[(size_t)(b1 * MFB + i) * ld + b0 * MFB + j];            // L_10
   if (colpart) {
-    X[i][j] = A[(size_t)(b1 * MFB + i) * ld + b0 * MFB + j];          // L_10
     Y[i][j] = A[(size_t)(b0 * MFB + i) * ld + b1 * MFB + j];          // U_01
     __syncthreads();
     double d = A[(size_t)(b1 * MFB + i) * ld + b1 * MFB + j];
@@ -262,33 +271,42 @@ k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_
     __syncthreads();
     mf_invert32(W1, W2, Ip, perm, i, j);
     if (blockIdx.x == 0) Dinv[((size_t)dioff[f] + b1) * (MFB * MFB) + i * MFB + j] = Ip[i][j];
-    for (int r = cbeg; r < cend; r += MFB) {
-      const int row = r + i;
-      double *T = A + (size_t)row * ld;
-      __syncthreads();
-      X[i][j] = row < cend ? T[b0 * MFB + j] : 0.0;                   // L_i0
-      __syncthreads();
-      double v = row < cend ? T[b1 * MFB + j] : 0.0;
+    for (int r = cbeg + i; r < cend; r += 32) {
+      double *T = A + (size_t)r * ld;
+      const double l0 = T[b0 * MFB + j];
+      double v = T[b1 * MFB + j];
+      Xw[i][0][j] = l0;
+      __syncwarp();
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) v -= X[i][k] * Y[k][j];
-      W1[i][j] = v;
-      __syncthreads();
+      for (int k = 0; k < MFB; k++) v -= Xw[i][0][k] * Y[k][j];
+      Xw[i][1][j] = v;
+      __syncwarp();
       double sum = 0.0;
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) sum += W1[i][k] * Ip[k][j];
-      if (row < cend) T[b1 * MFB + j] = sum;
+      for (int k = 0; k < MFB; k++) sum += Xw[i][1][k] * Ip[k][j];
+      T[b1 * MFB + j] = sum;
+      __syncwarp();
     }
   } else {
-    X[i][j] = A[(size_t)(b1 * MFB + i) * ld + b0 * MFB + j];          // L_10
-    for (int c = cbeg; c < cend; c += MFB) {
-      const int col = c + j;
-      __syncthreads();
-      Y[i][j] = col < cend ? A[(size_t)(b0 * MFB + i) * ld + col] : 0.0;   // U_0j
-      __syncthreads();
-      double sum = 0.0;
+    __syncthreads();
+    // work item = (32-column chunk, group of 8 rows of block b1); lane = column
+    const int nch = (cend - cbeg + MFB - 1) / MFB;
+    for (int it = i; it < nch * 4; it += 32) {
+      const int col = cbeg + (it >> 2) * MFB + j, ig = (it & 3) * 8;
+      if (col >= cend) continue;
+      double acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) acc[q] = 0.0;
+      const double *U0 = A + (size_t)(b0 * MFB) * ld + col;
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) sum += X[i][k] * Y[k][j];
-      if (col < cend) A[(size_t)(b1 * MFB + i) * ld + col] -= sum;
+      for (int k = 0; k < MFB; k++) {
+        const double u = U0[(size_t)k * ld];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] += X[ig + q][k] * u;
+      }
+      double *U1 = A + (size_t)(b1 * MFB + ig) * ld + col;
+#pragma unroll
+      for (int q = 0; q < 8; q++) U1[(size_t)q * ld] -= acc[q];
     }
   }
 }
@@ -297,11 +315,26 @@ k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_
 // Tile (8 TG) x (8 TG), TG x TG threads, 8 x 8 register micro-tile made of 2 x 2 sub-blocks (rows 2 ty + 2 TG p + {0,1},
 // columns 2 tx + 2 TG q + {0,1}): the L values are broadcast loads, the U values and all accesses to A are 16-byte
 // accesses of adjacent columns.  With nkb = 2 the tile of A is read and written once per 64 pivots.
+// Both operand tiles of both pivot blocks are fetched with cp.async up front (one buffer per pivot block, all loads in
+// flight at once, no staging registers), the lines of the A tile are prefetched into L2 meanwhile, and the read-modify-
+// write of the A tile is issued in batches of eight 16-byte loads -- with one CTA of 8 warps per SM (208 registers per
+// thread) there is nothing else to hide the memory latency behind.
+__device__ __forceinline__ void mf_cp_async8(double *dst, const double *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n));
+}
+__device__ __forceinline__ void mf_cp_async16(double *dst, const double *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n));
+}
+
 template <int TG>
-__global__ void __launch_bounds__(TG * TG, TG == 16 ? 1 : 4)
+__global__ void __launch_bounds__(TG * TG, TG == 16 ? 1 : 2)
 k_mf_update(int first, int b, int nkb, const int *__restrict__ G_, const int *__restrict__ ld_, const long long *__restrict__ foff,
             double *__restrict__ F) {
-  constexpr int T = 8 * TG, NT = TG * TG;
+  constexpr int T = 8 * TG, NT = TG * TG, BUFA = T * (MFB + 1) + MFB * T;    // doubles per pivot-block buffer (even: T is even)
   const int f = first + blockIdx.z;
   const int G = G_[f], ld = ld_[f];
   const int r0 = (b + nkb) * MFB;
@@ -309,36 +342,49 @@ k_mf_update(int first, int b, int nkb, const int *__restrict__ G_, const int *__
   if (i0 >= G || j0 >= G) return;
   double *A = F + foff[f];
   extern __shared__ __align__(16) double mf_sm[];
-  double(*sL)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(mf_sm);          // [T][33]
-  double(*sU)[T] = reinterpret_cast<double(*)[T]>(mf_sm + T * (MFB + 1));      // [32][T]
   const int t = threadIdx.x;
   const int tx = t % TG, ty = t / TG;
+  for (int kk = 0; kk < nkb; kk++) {
+    const int kb = b + kk;
+    double *sLb = mf_sm + kk * BUFA;                 // [T][33]
+    double *sUb = sLb + T * (MFB + 1);               // [32][T], 16-byte aligned: T * 33 is even
+#pragma unroll 4
+    for (int q = t; q < T * MFB; q += NT) {
+      const int row = q >> 5, k = q & 31;
+      const bool ok = i0 + row < G;
+      mf_cp_async8(sLb + row * (MFB + 1) + k, ok ? A + (size_t)(i0 + row) * ld + kb * MFB + k : A, ok);
+    }
+#pragma unroll 4
+    for (int q = t; q < MFB * (T / 2); q += NT) {
+      const int k = q / (T / 2), c = 2 * (q % (T / 2));
+      const bool ok = j0 + c < G;
+      mf_cp_async16(sUb + k * T + c, ok ? A + (size_t)(kb * MFB + k) * ld + j0 + c : A, ok);
+    }
+    asm volatile("cp.async.commit_group;");
+  }
+  // L2 prefetch of this thread's share of the A tile (128-byte lines; T rows x T / 16 lines)
+  for (int q = t; q < T * (T / 16); q += NT) {
+    const int row = q / (T / 16), c = 16 * (q % (T / 16));
+    if (i0 + row < G && j0 + c < G) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(i0 + row) * ld + j0 + c));
+  }
   double acc[8][8];
 #pragma unroll
   for (int p = 0; p < 8; p++)
 #pragma unroll
     for (int q = 0; q < 8; q++) acc[p][q] = 0.0;
-  for (int kb = b; kb < b + nkb; kb++) {
-    if (kb > b) __syncthreads();
-    for (int q = t; q < T * MFB; q += NT) {
-      const int row = q >> 5, k = q & 31;
-      sL[row][k] = (i0 + row < G) ? A[(size_t)(i0 + row) * ld + kb * MFB + k] : 0.0;
-    }
-    for (int q = t; q < MFB * (T / 2); q += NT) {
-      const int k = q / (T / 2), c = 2 * (q % (T / 2));
-      double2 v = make_double2(0.0, 0.0);
-      if (j0 + c < G) v = *reinterpret_cast<const double2 *>(A + (size_t)(kb * MFB + k) * ld + j0 + c);
-      *reinterpret_cast<double2 *>(&sU[k][c]) = v;
-    }
+  for (int kk = 0; kk < nkb; kk++) {
+    if (kk == 0 && nkb == 2) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
     __syncthreads();
+    const double *sLb = mf_sm + kk * BUFA;
+    const double *sUb = sLb + T * (MFB + 1);
 #pragma unroll 2
     for (int k = 0; k < MFB; k++) {
       double a[8], u[8];
 #pragma unroll
-      for (int p = 0; p < 4; p++) { a[2 * p] = sL[2 * ty + 2 * TG * p][k]; a[2 * p + 1] = sL[2 * ty + 2 * TG * p + 1][k]; }
+      for (int p = 0; p < 4; p++) { a[2 * p] = sLb[(2 * ty + 2 * TG * p) * (MFB + 1) + k]; a[2 * p + 1] = sLb[(2 * ty + 2 * TG * p + 1) * (MFB + 1) + k]; }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const double2 v = *reinterpret_cast<const double2 *>(&sU[k][2 * tx + 2 * TG * q]);
+        const double2 v = *reinterpret_cast<const double2 *>(sUb + k * T + 2 * tx + 2 * TG * q);
         u[2 * q] = v.x; u[2 * q + 1] = v.y;
       }
 #pragma unroll
@@ -348,27 +394,56 @@ k_mf_update(int first, int b, int nkb, const int *__restrict__ G_, const int *__
     }
   }
 #pragma unroll
-  for (int p = 0; p < 8; p++) {
-    const int i = i0 + 2 * ty + 2 * TG * (p >> 1) + (p & 1);
-    if (i >= G) continue;
+  for (int pp = 0; pp < 4; pp++) {                   // two rows (8 x 16 bytes) per batch
+    double2 v[2][4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int j = j0 + 2 * tx + 2 * TG * q;
-      if (j >= G) continue;
-      double2 *c = reinterpret_cast<double2 *>(A + (size_t)i * ld + j);
-      double2 v = *c;
-      v.x -= acc[p][2 * q]; v.y -= acc[p][2 * q + 1];
-      *c = v;
+    for (int h = 0; h < 2; h++) {
+      const int i = i0 + 2 * ty + 2 * TG * pp + h;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = j0 + 2 * tx + 2 * TG * q;
+        v[h][q] = (i < G && j < G) ? *reinterpret_cast<const double2 *>(A + (size_t)i * ld + j) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int i = i0 + 2 * ty + 2 * TG * pp + h;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = j0 + 2 * tx + 2 * TG * q;
+        if (i < G && j < G) {
+          double2 w = v[h][q];
+          w.x -= acc[2 * pp + h][2 * q]; w.y -= acc[2 * pp + h][2 * q + 1];
+          *reinterpret_cast<double2 *>(A + (size_t)i * ld + j) = w;
+        }
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// solve kernels: one CTA (1024 threads) per front, one launch per level and direction
+// solve kernels: one CTA (1024 threads = 32 warps) per front, one launch per level and direction; the front's vector
+// lives in shared memory during the sweep, the factors are streamed row-wise (row-major fronts: every dot product is
+// a coalesced read of one row segment).
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mf_rowdot(const double *__restrict__ Ar, const double *sw, int j0, int j1, int lane) {
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  int j = j0 + lane;
+  for (; j + 96 < j1; j += 128) {
+    const double a0 = Ar[j], a1 = Ar[j + 32], a2 = Ar[j + 64], a3 = Ar[j + 96];
+    v0 += a0 * sw[j]; v1 += a1 * sw[j + 32]; v2 += a2 * sw[j + 64]; v3 += a3 * sw[j + 96];
+  }
+  for (; j < j1; j += 32) v0 += Ar[j] * sw[j];
+  double v = (v0 + v1) + (v2 + v3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // forward:  w = [scaled rhs of the own unknowns ; 0] + the boundary vectors of the children, then  y = L^-1 w  block by
-// block; the boundary rows end up holding this front's contribution to its parent.  dself != nullptr: the right-hand
-// side is first multiplied by the 2x2 diagonal blocks of A (the solver then applies (B A)^-1, B = block-Jacobi scaling).
+// block (left-looking: block b needs the rows of block b only), then the boundary rows  w_b -= L21 y, which are this
+// front's contribution to its parent.  dself != nullptr: the right-hand side is first multiplied by the 2x2 diagonal
+// blocks of A (the solver then applies (B A)^-1, B = block-Jacobi scaling).
 __global__ void __launch_bounds__(1024)
 k_mf_fwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, const int *__restrict__ G_,
          const int *__restrict__ ld_, const long long *__restrict__ foff, const int *__restrict__ woff_,
@@ -376,14 +451,13 @@ k_mf_fwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, con
          const int *__restrict__ sep_off, const int *__restrict__ sepdof, const double *__restrict__ scale,
          const double *__restrict__ rhs, const double *__restrict__ dself, const double *__restrict__ dpair,
          const double *__restrict__ F, double *__restrict__ W) {
+  extern __shared__ double mf_sw[];
   const int f = first + blockIdx.x;
   const int ns = ns_[f], p = p_[f], G = G_[f], ld = ld_[f], wo = woff_[f];
   const double *A = F + foff[f];
-  double *w = W + wo;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int w0 = cw0[f], w1 = cw1[f];
-  __shared__ double ys[MFB];
-  for (int i = t; i < G; i += blockDim.x) {
+  for (int i = t; i < G; i += 1024) {
     double v = 0.0;
     if (i < ns) {
       const int d = sepdof[sep_off[f] + i];
@@ -391,26 +465,27 @@ k_mf_fwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, con
     }
     if (w0 >= 0) { const int a = pinv0[wo + i]; if (a >= 0) v += W[w0 + a]; }
     if (w1 >= 0) { const int a = pinv1[wo + i]; if (a >= 0) v += W[w1 + a]; }
-    w[i] = v;
+    mf_sw[i] = v;
   }
   __syncthreads();
   const int nblk = p / MFB;
-  for (int b = 0; b < nblk; b++) {
-    if (t < MFB) ys[t] = w[b * MFB + t];
-    __syncthreads();
-    const double yl = ys[lane];
-    for (int r = (b + 1) * MFB + warp; r < G; r += nwarps) {
-      double v = A[(size_t)r * ld + b * MFB + lane] * yl;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) w[r] -= v;
-    }
+  for (int b = 1; b < nblk; b++) {
+    const int row = b * MFB + warp;
+    const double v = mf_rowdot(A + (size_t)row * ld, mf_sw, 0, b * MFB, lane);
+    if (lane == 0) mf_sw[row] -= v;
     __syncthreads();
   }
+  for (int r = p + warp; r < G; r += 32) {
+    const double v = mf_rowdot(A + (size_t)r * ld, mf_sw, 0, p, lane);
+    if (lane == 0) mf_sw[r] -= v;
+  }
+  __syncthreads();
+  double *w = W + wo;
+  for (int i = t; i < G; i += 1024) w[i] = mf_sw[i];
 }
 
 // backward:  x_b from the parent's vector,  x_s = U11^-1 (y - U12 x_b)  block by block (D_b^-1 from the side buffer);
-// x_s stays in w (for the children) and goes, unscaled, to the global solution vector
+// [x_s; x_b] stays in w (for the children) and x_s goes, unscaled, to the global solution vector
 __global__ void __launch_bounds__(1024)
 k_mf_bwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, const int *__restrict__ nb_,
          const int *__restrict__ ld_, const long long *__restrict__ foff, const int *__restrict__ woff_,
@@ -418,39 +493,163 @@ k_mf_bwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, con
          const int *__restrict__ dioff, const int *__restrict__ sep_off, const int *__restrict__ sepdof,
          const double *__restrict__ scale, const double *__restrict__ F, const double *__restrict__ Dinv,
          double *__restrict__ W, double *__restrict__ x, int accumulate) {
+  extern __shared__ double mf_sw[];
+  __shared__ double ts[MFB];
   const int f = first + blockIdx.x;
   const int ns = ns_[f], p = p_[f], nb = nb_[f], ld = ld_[f], G = p + nb;
   const double *A = F + foff[f];
   double *w = W + woff_[f];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;      // 32 warps
-  __shared__ double ts[MFB];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < p; i += 1024) mf_sw[i] = w[i];
   if (nb > 0) {
     const double *pw = W + pwoff[f];
     const int *up = upmap + up_off[f];
-    for (int r = t; r < nb; r += blockDim.x) w[p + r] = pw[up[r]];
+    for (int r = t; r < nb; r += 1024) mf_sw[p + r] = pw[up[r]];
   }
   __syncthreads();
+  const double *Di = Dinv + (size_t)dioff[f] * (MFB * MFB) + warp * MFB + lane;
   for (int b = p / MFB - 1; b >= 0; b--) {
     const int row = b * MFB + warp;
-    const double *Ar = A + (size_t)row * ld;
-    double v = 0.0;
-    for (int j = (b + 1) * MFB + lane; j < G; j += 32) v += Ar[j] * w[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) ts[warp] = w[row] - v;
+    const double dv = Di[(size_t)b * (MFB * MFB)];
+    const double v = mf_rowdot(A + (size_t)row * ld, mf_sw, (b + 1) * MFB, G, lane);
+    if (lane == 0) ts[warp] = mf_sw[row] - v;
     __syncthreads();
-    double xv = Dinv[((size_t)dioff[f] + b) * (MFB * MFB) + warp * MFB + lane] * ts[lane];
+    double xv = dv * ts[lane];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) xv += __shfl_xor_sync(0xffffffffu, xv, o);
-    __syncthreads();
-    if (lane == 0) w[row] = xv;
+    if (lane == 0) mf_sw[row] = xv;
     __syncthreads();
   }
-  for (int i = t; i < ns; i += blockDim.x) {
+  for (int i = t; i < G; i += 1024) w[i] = mf_sw[i];
+  for (int i = t; i < ns; i += 1024) {
     const int d = sepdof[sep_off[f] + i];
-    const double xs = scale[d] * w[i];
+    const double xs = scale[d] * mf_sw[i];
     if (accumulate) x[d] += xs; else x[d] = xs;
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same sweeps for the few LARGE fronts near the root, where one SM cannot stream a front fast enough: a thread-block
+// cluster of MFCL CTAs per front.  Every CTA keeps the whole vector in its shared memory; a block step's 32 dot products
+// are split by columns over the CTAs, the partial sums are pushed to every CTA's shared memory (DSMEM), one cluster
+// barrier later every CTA adds them in rank order (bit-identical everywhere) and continues.  The boundary rows (forward)
+// are split by rows and need no exchange.
+// ------------------------------------------------------------------------------------------------------------------
+#define MFCL 8
+namespace cg = cooperative_groups;
+
+// columns [j0, j1) in 32-aligned pieces: piece c of CL
+__device__ __forceinline__ void mf_piece(int j0, int j1, int c, int CL, int *a, int *b) {
+  const int nblk = (j1 - j0 + MFB - 1) / MFB, per = (nblk + CL - 1) / CL;
+  *a = min(j1, j0 + c * per * MFB); *b = min(j1, j0 + (c + 1) * per * MFB);
+}
+
+__global__ void __cluster_dims__(MFCL, 1, 1) __launch_bounds__(1024)
+k_mf_fwd_cl(int first, const int *__restrict__ ns_, const int *__restrict__ p_, const int *__restrict__ G_,
+            const int *__restrict__ ld_, const long long *__restrict__ foff, const int *__restrict__ woff_,
+            const int *__restrict__ cw0, const int *__restrict__ cw1, const int *__restrict__ pinv0, const int *__restrict__ pinv1,
+            const int *__restrict__ sep_off, const int *__restrict__ sepdof, const double *__restrict__ scale,
+            const double *__restrict__ rhs, const double *__restrict__ dself, const double *__restrict__ dpair,
+            const double *__restrict__ F, double *__restrict__ W) {
+  extern __shared__ double mf_sw[];
+  __shared__ double part[2][MFCL][MFB];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int c = (int)cluster.block_rank();
+  const int f = first + blockIdx.x / MFCL;
+  const int ns = ns_[f], p = p_[f], G = G_[f], ld = ld_[f], wo = woff_[f];
+  const double *A = F + foff[f];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int w0 = cw0[f], w1 = cw1[f];
+  for (int i = t; i < G; i += 1024) {
+    double v = 0.0;
+    if (i < ns) {
+      const int d = sepdof[sep_off[f] + i];
+      v = scale[d] * (dself ? dself[d] * rhs[d] + dpair[d] * rhs[d ^ 1] : rhs[d]);
+    }
+    if (w0 >= 0) { const int a = pinv0[wo + i]; if (a >= 0) v += W[w0 + a]; }
+    if (w1 >= 0) { const int a = pinv1[wo + i]; if (a >= 0) v += W[w1 + a]; }
+    mf_sw[i] = v;
+  }
+  cluster.sync();
+  const int nblk = p / MFB;
+  for (int b = 1; b < nblk; b++) {
+    const int row = b * MFB + warp, par = b & 1;
+    int ja, jb;
+    mf_piece(0, b * MFB, c, MFCL, &ja, &jb);
+    const double v = mf_rowdot(A + (size_t)row * ld, mf_sw, ja, jb, lane);
+    if (lane < MFCL) cluster.map_shared_rank(&part[par][c][warp], lane)[0] = v;
+    cluster.sync();
+    if (t < MFB) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < MFCL; q++) s += part[par][q][t];
+      mf_sw[b * MFB + t] -= s;
+    }
+    __syncthreads();
+  }
+  double *w = W + wo;
+  for (int r = p + c * 32 + warp; r < G; r += 32 * MFCL) {
+    const double v = mf_rowdot(A + (size_t)r * ld, mf_sw, 0, p, lane);
+    if (lane == 0) w[r] = mf_sw[r] - v;
+  }
+  if (c == 0) for (int i = t; i < p; i += 1024) w[i] = mf_sw[i];
+  cluster.sync();            // nobody leaves while its shared memory may still be written by a peer
+}
+
+__global__ void __cluster_dims__(MFCL, 1, 1) __launch_bounds__(1024)
+k_mf_bwd_cl(int first, const int *__restrict__ ns_, const int *__restrict__ p_, const int *__restrict__ nb_,
+            const int *__restrict__ ld_, const long long *__restrict__ foff, const int *__restrict__ woff_,
+            const int *__restrict__ pwoff, const int *__restrict__ up_off, const int *__restrict__ upmap,
+            const int *__restrict__ dioff, const int *__restrict__ sep_off, const int *__restrict__ sepdof,
+            const double *__restrict__ scale, const double *__restrict__ F, const double *__restrict__ Dinv,
+            double *__restrict__ W, double *__restrict__ x, int accumulate) {
+  extern __shared__ double mf_sw[];
+  __shared__ double part[2][MFCL][MFB], ts[MFB];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int c = (int)cluster.block_rank();
+  const int f = first + blockIdx.x / MFCL;
+  const int ns = ns_[f], p = p_[f], nb = nb_[f], ld = ld_[f], G = p + nb;
+  const double *A = F + foff[f];
+  double *w = W + woff_[f];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < p; i += 1024) mf_sw[i] = w[i];
+  if (nb > 0) {
+    const double *pw = W + pwoff[f];
+    const int *up = upmap + up_off[f];
+    for (int r = t; r < nb; r += 1024) mf_sw[p + r] = pw[up[r]];
+  }
+  cluster.sync();
+  const double *Di = Dinv + (size_t)dioff[f] * (MFB * MFB) + warp * MFB + lane;
+  for (int b = p / MFB - 1; b >= 0; b--) {
+    const int row = b * MFB + warp, par = b & 1;
+    const double dv = Di[(size_t)b * (MFB * MFB)];
+    int ja, jb;
+    mf_piece((b + 1) * MFB, G, c, MFCL, &ja, &jb);
+    const double v = mf_rowdot(A + (size_t)row * ld, mf_sw, ja, jb, lane);
+    if (lane < MFCL) cluster.map_shared_rank(&part[par][c][warp], lane)[0] = v;
+    cluster.sync();
+    if (t < MFB) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < MFCL; q++) s += part[par][q][t];
+      ts[t] = mf_sw[b * MFB + t] - s;
+    }
+    __syncthreads();
+    double xv = dv * ts[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xv += __shfl_xor_sync(0xffffffffu, xv, o);
+    if (lane == 0) mf_sw[row] = xv;
+    __syncthreads();
+  }
+  if (c == 0) {
+    for (int i = t; i < G; i += 1024) w[i] = mf_sw[i];
+    for (int i = t; i < ns; i += 1024) {
+      const int d = sepdof[sep_off[f] + i];
+      const double xs = scale[d] * mf_sw[i];
+      if (accumulate) x[d] += xs; else x[d] = xs;
+    }
+  }
+  cluster.sync();
 }
 
 // r = b - A x, unscaled CSR (1-based), one thread per row
@@ -523,6 +722,7 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
   S->nT = T->nT; S->N = N; S->nnz = ptr[N] - 1; S->rank = rank; S->nranks = nranks; S->nccl = nccl;
   if (const char *e = getenv("UFE_ND_GRAPHS")) S->use_graphs = atoi(e);
   if (const char *e = getenv("UFE_ND_K64")) S->k64 = atoi(e);
+  if (const char *e = getenv("UFE_ND_CLUSTER_FRONTS")) S->cl_max_fronts = atoi(e);
   if (nranks > 1) S->use_graphs = 0;
   S->lev.resize(nl);
   // local fronts, level-major, p descending inside a level
@@ -631,6 +831,7 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
       }
       Lv.step[b] = st;
     }
+    if ((size_t)Lv.maxG * sizeof(double) > 200 * 1024) { ufe_set_error("ufe_nd_solver_create: a front of %d unknowns does not fit the solve kernels' shared memory", Lv.maxG); delete S; return UFE_ERR_INVALID; }
     if (Lv.n > 65535) { ufe_set_error("ufe_nd_solver_create: %d fronts in one level (limit 65535): use larger leaves", Lv.n); delete S; return UFE_ERR_INVALID; }
   }
   size_t free_b = 0, total_b = 0;
@@ -689,8 +890,12 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
       cudaEventCreate(&S->e1) != cudaSuccess) { ufe_set_error("ufe_nd_solver_create: stream / event creation failed"); return fail(UFE_ERR_CUDA); }
   static bool attr_set = false;
   if (!attr_set) {
-    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 * (MFB + 1) + MFB * 128) * sizeof(double))));
-    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((64 * (MFB + 1) + MFB * 64) * sizeof(double))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(128))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(64))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_fwd_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_bwd_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   UFE_CUDA(cudaDeviceSynchronize());
@@ -771,10 +976,10 @@ static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *d
       const long long big_ctas = (long long)((trail + 127) / 128) * ((trail + 127) / 128) * n_upd;
       if (trail >= 192 && big_ctas >= 120) {
         const int t = (trail + 127) / 128;
-        k_mf_update<16><<<dim3(t, t, n_upd), 256, (128 * (MFB + 1) + MFB * 128) * sizeof(double), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
+        k_mf_update<16><<<dim3(t, t, n_upd), 256, MF_UPD_SMEM(128), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
       } else {
         const int t = (trail + 63) / 64;
-        k_mf_update<8><<<dim3(t, t, n_upd), 64, (64 * (MFB + 1) + MFB * 64) * sizeof(double), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
+        k_mf_update<8><<<dim3(t, t, n_upd), 64, MF_UPD_SMEM(64), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
       }
       UFE_LAUNCH_CHECK();
     }
@@ -795,14 +1000,22 @@ static int mf_apply_launches(ufe_nd_solver *S, cudaStream_t st, const double *r,
       g_launch_count++;
     }
     if (L.n == 0) continue;
-    k_mf_fwd<<<L.n, 1024, 0, st>>>(L.first, S->ns, S->p, S->G, S->ld, S->foff, S->woff, S->c_w[0], S->c_w[1], S->pinv[0], S->pinv[1],
+    if (L.n <= S->cl_max_fronts && L.maxG >= 768)
+      k_mf_fwd_cl<<<L.n * MFCL, 1024, (size_t)L.maxG * sizeof(double), st>>>(L.first, S->ns, S->p, S->G, S->ld, S->foff, S->woff, S->c_w[0], S->c_w[1], S->pinv[0], S->pinv[1],
+                                        S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->dpair, S->F, S->W);
+    else
+      k_mf_fwd<<<L.n, 1024, (size_t)L.maxG * sizeof(double), st>>>(L.first, S->ns, S->p, S->G, S->ld, S->foff, S->woff, S->c_w[0], S->c_w[1], S->pinv[0], S->pinv[1],
                                    S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->dpair, S->F, S->W);
     UFE_LAUNCH_CHECK();
   }
   for (int l = 0; l < nl; l++) {                 // backward sweep, root first
     const MfLevel &L = S->lev[l];
     if (L.n > 0) {
-      k_mf_bwd<<<L.n, 1024, 0, st>>>(L.first, S->ns, S->p, S->nb, S->ld, S->foff, S->woff, S->pwoff, S->up_off, S->upmap, S->dioff,
+      if (L.n <= S->cl_max_fronts && L.maxG >= 768)
+        k_mf_bwd_cl<<<L.n * MFCL, 1024, (size_t)L.maxG * sizeof(double), st>>>(L.first, S->ns, S->p, S->nb, S->ld, S->foff, S->woff, S->pwoff, S->up_off, S->upmap, S->dioff,
+                                          S->sep_off, S->sepdof, S->scale, S->F, S->Dinv, S->W, x, accumulate);
+      else
+        k_mf_bwd<<<L.n, 1024, (size_t)L.maxG * sizeof(double), st>>>(L.first, S->ns, S->p, S->nb, S->ld, S->foff, S->woff, S->pwoff, S->up_off, S->upmap, S->dioff,
                                      S->sep_off, S->sepdof, S->scale, S->F, S->Dinv, S->W, x, accumulate);
       UFE_LAUNCH_CHECK();
     }
