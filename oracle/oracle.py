@@ -32,24 +32,44 @@ pi = 3.141592653589793   # :44
 R_gas = 8.314            # :56
 
 
-def build(force=False):
+def build(force=False, native=False):
+    """Compile the C restatement if it is missing or stale.  ``native=True`` (the timed CPU baseline of bench.py):
+    also build ``libufe_oracle_native.so`` with ``-O3 -march=native`` on THIS machine -- the reference's own
+    performance flags (compile_UFEMISM.csh:86-98) -- and load that one; falls back to the portable build."""
+    global _LIB
     so = os.path.join(_HERE, "libufe_oracle.so")
     src = os.path.join(_HERE, "ufe_oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libufe_oracle.so"])
+    if native:
+        nat = os.path.join(_HERE, "libufe_oracle_native.so")
+        try:
+            subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "libufe_oracle_native.so"])
+            ct.CDLL(nat)
+            if _LIB is None or getattr(_LIB, "_name", "") != nat:
+                _LIB = None
+                _load(nat)
+            return nat
+        except (subprocess.CalledProcessError, OSError):
+            pass
     return so
 
 
-def lib():
+def _load(path):
     global _LIB
+    _LIB = ct.CDLL(path)
+    _LIB.ora_calc_operators_a_b.restype = ct.c_int
+    _LIB.ora_calc_operators_b_a.restype = ct.c_int
+    _LIB.ora_calc_operators_b_b_2nd.restype = ct.c_int
+    _LIB.ora_assemble_stiffness.restype = ct.c_int
+    _LIB.ora_ksp_gmres_bjacobi_ilu0.restype = ct.c_int
+    _LIB.ora_jacobi.restype = ct.c_int
+    return _LIB
+
+
+def lib():
     if _LIB is None:
-        _LIB = ct.CDLL(build())
-        _LIB.ora_calc_operators_a_b.restype = ct.c_int
-        _LIB.ora_calc_operators_b_a.restype = ct.c_int
-        _LIB.ora_calc_operators_b_b_2nd.restype = ct.c_int
-        _LIB.ora_assemble_stiffness.restype = ct.c_int
-        _LIB.ora_ksp_gmres_bjacobi_ilu0.restype = ct.c_int
-        _LIB.ora_jacobi.restype = ct.c_int
+        _load(build())
     return _LIB
 
 
