@@ -792,7 +792,7 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
                                kw.dots_local, kw.sc, sarg(), rtol, abstol);
   UFE_LAUNCH_CHECK();
   UFE_TRY(allreduce_stage(st, comm, kw, ST_INIT, 2, rtol, abstol));
-  int launched = 0, batch = (pc && single) ? 1 : 4;     // an exact block solve converges in the first (half) step
+  int launched = 0, batch = pc ? 1 : 4;     // an exact block solve converges in the first (half) step
   while (true) {
     for (int b = 0; b < batch; b++, launched++) {
       int ep = 0;
@@ -807,6 +807,10 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
         UFE_TRY(allreduce_stage(st, comm, kw, ST_S, 1, rtol, abstol));
         k_bicg_xhalf<<<G, B, 0, st>>>(n, r0, xg, kw.pg, kw.sc); UFE_LAUNCH_CHECK();
         k_half_ack<<<1, 1, 0, st>>>(kw.sc); UFE_LAUNCH_CHECK();
+        // an exact block solve converges in this half step: look before paying for the second operator application
+        // (SpMV + forward / backward sweep over the whole factorisation; the sweeps run from a replayed graph and
+        // cannot return early on the device-side `done` flag)
+        if (launched == 0) { UFE_TRY(poll(st, kw)); if (kw.sc_host->done) return UFE_OK; }     // same decision on every rank
       } else { ep = sig(); k_bicg_s<<<G, B, 0, st>>>(n, r0, kw.r, kw.v, kw.sg, kw.sc, kw.counter, ep); UFE_LAUNCH_CHECK(); }
       UFE_TRY(sync_input(st, comm, halo, kw.sg, &pv, &use_pv, ep));
       UFE_TRY(apply_op<2>(st, S, pc, kw.sg, kw.t, nullptr, ST_B, kw, sarg(), rtol, abstol, use_pv ? &pv : nullptr));

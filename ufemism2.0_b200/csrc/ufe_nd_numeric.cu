@@ -215,8 +215,10 @@ k_mf_panel(int first, int b, int rows_per_cta, const int *__restrict__ G_, const
   const int r0 = (b + 1) * MFB;
   const int rbeg = r0 + blockIdx.x * rows_per_cta;
   if (blockIdx.x > 0 && rbeg >= G) return;
-  __shared__ double W1[MFB][MFB + 1], W2[MFB][MFB + 1], Ip[MFB][MFB + 1], Xw[32][2][MFB];
+  __shared__ double Wb[2 * MFB * (MFB + 1)], Ip[MFB][MFB + 1];
   __shared__ int perm[MFB];
+  double(*W1)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(Wb), (*W2)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(Wb + MFB * (MFB + 1));
+  double(*Xw)[2][MFB] = reinterpret_cast<double(*)[2][MFB]>(Wb);      // per-warp staging rows; reuse the inversion work space
   const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
   double *A = F + foff[f];
   W1[i][j] = A[(size_t)(b * MFB + i) * ld + b * MFB + j];
@@ -253,10 +255,9 @@ k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_
   const bool colpart = (int)blockIdx.x < nx_col;
   const int cbeg = r1 + (colpart ? (int)blockIdx.x : (int)blockIdx.x - nx_col) * chunk;
   if (cbeg >= G && !(colpart && blockIdx.x == 0)) return;
-  __shared__ double Wb[2 * MFB * (MFB + 1)], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1];
+  __shared__ double W1[MFB][MFB + 1], W2[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1];
   __shared__ int perm[MFB];
-  double(*W1)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(Wb), (*W2)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(Wb + MFB * (MFB + 1));
-  double(*Xw)[2][MFB] = reinterpret_cast<double(*)[2][MFB]>(Wb);      // per-warp staging rows; reuses the inversion work space
+  double(*Xr)[MFB] = reinterpret_cast<double(*)[MFB]>(&W1[0][0]);      // per-warp staging row; reuses the inversion input
   const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
   double *A = F + foff[f];
   const int cend = min(G, cbeg + chunk);
@@ -275,15 +276,16 @@ k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_
       double *T = A + (size_t)r * ld;
       const double l0 = T[b0 * MFB + j];
       double v = T[b1 * MFB + j];
-      Xw[i][0][j] = l0;
+      Xr[i][j] = l0;
       __syncwarp();
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) v -= Xw[i][0][k] * Y[k][j];
-      Xw[i][1][j] = v;
+      for (int k = 0; k < MFB; k++) v -= Xr[i][k] * Y[k][j];
+      __syncwarp();
+      Xr[i][j] = v;
       __syncwarp();
       double sum = 0.0;
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) sum += Xw[i][1][k] * Ip[k][j];
+      for (int k = 0; k < MFB; k++) sum += Xr[i][k] * Ip[k][j];
       T[b1 * MFB + j] = sum;
       __syncwarp();
     }
@@ -426,18 +428,39 @@ k_mf_update(int first, int b, int nkb, const int *__restrict__ G_, const int *__
 // lives in shared memory during the sweep, the factors are streamed row-wise (row-major fronts: every dot product is
 // a coalesced read of one row segment).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double mf_rowdot(const double *__restrict__ Ar, const double *sw, int j0, int j1, int lane) {
-  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-  int j = j0 + lane;
-  for (; j + 96 < j1; j += 128) {
-    const double a0 = Ar[j], a1 = Ar[j + 32], a2 = Ar[j + 64], a3 = Ar[j + 96];
-    v0 += a0 * sw[j]; v1 += a1 * sw[j + 32]; v2 += a2 * sw[j + 64]; v3 += a3 * sw[j + 96];
-  }
-  for (; j < j1; j += 32) v0 += Ar[j] * sw[j];
-  double v = (v0 + v1) + (v2 + v3);
+// dot products of NR rows (row r at Ar + r * rstride, rows >= nrows skipped) with sw over the columns [j0, j1): all
+// NR x 4 loads of a 128-column slab are issued before the first multiply (the sweeps are latency-bound)
+template <int NR>
+__device__ __forceinline__ void mf_rowdots(const double *__restrict__ Ar, size_t rstride, int nrows, const double *sw, int j0, int j1,
+                                           int lane, double (&out)[NR]) {
+  double acc[NR];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int r = 0; r < NR; r++) acc[r] = 0.0;
+  for (int j = j0 + lane; j < j1; j += 128) {
+    double a[NR][4], x[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int jj = j + 32 * q;
+      const bool ok = jj < j1;
+      x[q] = ok ? sw[jj] : 0.0;
+#pragma unroll
+      for (int r = 0; r < NR; r++) a[r][q] = (ok && r < nrows) ? Ar[(size_t)r * rstride + jj] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < NR; r++) acc[r] += (a[r][0] * x[0] + a[r][1] * x[1]) + (a[r][2] * x[2] + a[r][3] * x[3]);
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    double v = acc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    out[r] = v;
+  }
+}
+__device__ __forceinline__ double mf_rowdot(const double *__restrict__ Ar, const double *sw, int j0, int j1, int lane) {
+  double o[1];
+  mf_rowdots<1>(Ar, 0, 1, sw, j0, j1, lane, o);
+  return o[0];
 }
 
 // forward:  w = [scaled rhs of the own unknowns ; 0] + the boundary vectors of the children, then  y = L^-1 w  block by
@@ -475,9 +498,11 @@ k_mf_fwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, con
     if (lane == 0) mf_sw[row] -= v;
     __syncthreads();
   }
-  for (int r = p + warp; r < G; r += 32) {
-    const double v = mf_rowdot(A + (size_t)r * ld, mf_sw, 0, p, lane);
-    if (lane == 0) mf_sw[r] -= v;
+  for (int r = p + warp; r < G; r += 128) {           // rows r, r + 32, r + 64, r + 96 together
+    double v[4];
+    const int nr = (G - r + 31) / 32;
+    mf_rowdots<4>(A + (size_t)r * ld, (size_t)32 * ld, nr, mf_sw, 0, p, lane, v);
+    if (lane < 4 && lane < nr) mf_sw[r + 32 * lane] -= v[lane];
   }
   __syncthreads();
   double *w = W + wo;
@@ -588,9 +613,11 @@ k_mf_fwd_cl(int first, const int *__restrict__ ns_, const int *__restrict__ p_, 
     __syncthreads();
   }
   double *w = W + wo;
-  for (int r = p + c * 32 + warp; r < G; r += 32 * MFCL) {
-    const double v = mf_rowdot(A + (size_t)r * ld, mf_sw, 0, p, lane);
-    if (lane == 0) w[r] = mf_sw[r] - v;
+  for (int r = p + c * 32 + warp; r < G; r += 128 * MFCL) {       // rows r, r + 32 MFCL, ... (4 together)
+    double v[4];
+    const int nr = (G - r + 32 * MFCL - 1) / (32 * MFCL);
+    mf_rowdots<4>(A + (size_t)r * ld, (size_t)32 * MFCL * ld, nr, mf_sw, 0, p, lane, v);
+    if (lane < 4 && lane < nr) w[r + 32 * MFCL * lane] = mf_sw[r + 32 * MFCL * lane] - v[lane];
   }
   if (c == 0) for (int i = t; i < p; i += 1024) w[i] = mf_sw[i];
   cluster.sync();            // nobody leaves while its shared memory may still be written by a peer
