@@ -33,12 +33,16 @@ for pc_name, meth in (('auto', 'bicgstab'), ('bjacobi2', 'bicgstab'), ('bjacobi2
 cases.append(('ISMIP-HOM C', experiments.ISMIP_HOM('C', 160e3, 31), 'auto', 'bicgstab'))
 cases.append(('MISMIP+ 8km', experiments.MISMIPplus(8e3), 'auto', 'bicgstab'))
 cases.append(('MISMIP+ 8km strip-only', experiments.MISMIPplus(8e3), 'bjacobi_lu', 'bicgstab'))
+# the multifrontal solver with its elimination sub-trees distributed over the ranks (explicitly, and on a wide mesh)
+cases.append(('MISMIP+ 8km nd', experiments.MISMIPplus(8e3), 'nd_lu', 'gmres'))
+cases.append(('Antarctic 2e4', experiments.antarctic(20000), 'nd_lu', 'bicgstab'))
 oracle_cache = {}
 for name, (mesh, C, ice), pc_name, meth in cases:
     C.stress_balance_PETSc_rtol, C.stress_balance_PETSc_abstol = 1e-12, 1e-11
     C.b200_krylov_pc, C.b200_krylov_method = pc_name, meth
     C.b200_krylov_pc_strip_only = name.endswith('strip-only')
     if name.startswith('MISMIP'): C.visc_it_nit = 8
+    if name.startswith('Antarctic'): C.visc_it_nit = 4
     S = diva.initialise_DIVA_solver(mesh, C, make_comm())
     t = time.time(); info = S.solve_DIVA(ice); wall = time.time() - t
     sec = S.calc_secondary_velocities()
@@ -46,7 +50,7 @@ for name, (mesh, C, ice), pc_name, meth in cases:
     if rank == 0:
         import oracle as O
         O.build()
-        key = name.split(' strip')[0]
+        key = name.split(' strip')[0].split(' nd')[0]
         if key not in oracle_cache:
             O.calc_all_matrix_operators_mesh(mesh)
             D = O.new_DIVA_state(mesh); nv, _ = O.solve_DIVA(mesh, ice, C, D, 'direct')
@@ -59,7 +63,8 @@ for name, (mesh, C, ice), pc_name, meth in cases:
         rs = max(np.abs(sec[k] - w).max() / max(np.abs(w).max(), 1e-300) for k, w in want.items())
         good = max(ru + rv) < 1e-6 and abs(info.n_visc_its - nv) <= 1 and r3 < 1e-6 and rs < 1e-12
         ok &= good
-        print(f'{name} [{meth}+{pc_name}]: ranks {world} comm {"peer" if info.reserved else "nccl"} Picard {info.n_visc_its} (oracle {nv}) '
+        if pc_name == 'nd_lu' or (pc_name == 'auto' and world in (1, 2, 4, 8)): good = good and info.krylov_pc_used == 4
+        print(f'{name} [{meth}+{pc_name} -> pc {info.krylov_pc_used}]: ranks {world} comm {"peer" if info.reserved else "nccl"} Picard {info.n_visc_its} (oracle {nv}) '
               f'Krylov {info.n_Axb_its} flags {info.flags} u {ru[1]:.2e} v {rv[1]:.2e} u3D {r3:.2e} secondary {rs:.1e} wall {wall:.3f}s '
               f'{"OK" if good else "MISMATCH"}', flush=True)
     thk = None
