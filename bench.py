@@ -275,24 +275,25 @@ def main():
         """NCCL unique id broadcast through torch.distributed -> (rank, nranks, device, id) for ufe_diva_create"""
         if world == 1:
             return None
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        dev = torch.device("cuda", local)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             buf = (capi.ct.c_char * 128)()
             capi.check(capi.lib().ufe_comm_get_unique_id(buf))
-            uid = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+            uid = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
         dist.broadcast(uid, 0)
         return (rank, world, local, bytes(uid.cpu().tolist()))
 
     def barrier():
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(local)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
 
     def max_over_ranks(x):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -307,7 +308,8 @@ def main():
     mesh, C, ice, label = make_workload(args.workload)
     big_workload = 2 * mesh.nTri > 131072            # large systems are one partitioned solve, small ones N replicas
     t0 = time.perf_counter()
-    S = diva.initialise_DIVA_solver(mesh, C, new_comm() if big_workload else None)
+    # replicas: a one-rank handle on THIS rank's GPU (comm = (rank 0 of 1, device))
+    S = diva.initialise_DIVA_solver(mesh, C, new_comm() if big_workload else (0, 1, local, None))
     t_create = time.perf_counter() - t0
 
     # ---------------- leg 1: resident (value) ----------------
@@ -510,7 +512,7 @@ def main():
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary and args.workload != "ismip_hom_a":
         meshS, CS, iceS, labelS = make_workload("ismip_hom_a")
-        SS = diva.initialise_DIVA_solver(meshS, CS)
+        SS = diva.initialise_DIVA_solver(meshS, CS, (0, 1, local, None))
         SS.upload(iceS, state=True)
         for _ in range(2):
             SS.reset_state_resident(); SS.solve_DIVA_resident()

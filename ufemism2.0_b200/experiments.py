@@ -47,7 +47,7 @@ def ISMIP_HOM(exp: str, L: float, n: int = 41, seed=synthetic.SEED, delaunay=Tru
     return mesh, C, ice
 
 
-def SSA_icestream(nx=21, ny=81, delaunay=True):
+def SSA_icestream(nx=41, ny=41, delaunay=True):
     """automated_testing/integrated_tests/idealised/SSA_icestream/config_04_4km.cfg:65-68,150-153,
     253-254,468: domain +-400 km, A = 1e-18, H = 2000, dh/dx = -3e-4, L = 150 km, m = 1,
     Krylov 1e-7 / 1e-5; BC_u west/east 'infinite_SSA_icestream', v 'zero' (SSA solve)."""
