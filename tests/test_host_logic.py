@@ -182,10 +182,13 @@ def test_bench_reference_arm_contract():
     with the keys the driver reads; small workload so that it runs in seconds."""
     import json
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "ismip_hom_a",
-                        "--steps", "1", "--warmup", "1", "--cpu-seconds", "2"], capture_output=True, text=True, timeout=300)
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "solves/s" and line["value"] > 0
+    # the whole solve, run to completion and converged: no extrapolation, no linear solve at the iteration cap
+    cb = line["cpu_baseline"]
+    assert cb["extrapolated"] is False and cb["picard_converged"] is True and cb["krylov_its_per_solve_max"] < 10000
     assert line["higher_is_better"] is True and line["n_gpus"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
