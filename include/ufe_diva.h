@@ -215,17 +215,35 @@ typedef struct ufe_handle ufe_handle;
 const char *ufe_last_error_string(void);
 int ufe_comm_get_unique_id(char id_out[128]);
 int ufe_version(void);
+/* sizeof(ufe_solve_info) as this library was built: a binding asserts it against its own declaration of the struct
+ * (the entry points memset and fill the whole struct) */
+int ufe_sizeof_solve_info(void);
 
 /* partition_list (src/UPSY/basic/mpi_parallelisation/mpi_distributed_memory.f90:42-68) */
 void ufe_partition_list(int32_t ntot, int32_t i, int32_t n, int32_t *i1, int32_t *i2);
 
 /* L0 -- replaces solve_matrix_equation_CSR_PETSc (src/UPSY/basic/petsc_basic.f90:32-64;
- * call site solve_linearised_SSA_DIVA.f90:159).  Single-GPU (A holds all rows).
+ * call site solve_linearised_SSA_DIVA.f90:159) without a handle: one GPU, A holds all rows, point Jacobi
+ * (ufe_solve_matrix_equation_CSR below is the distributed form with every preconditioner).
  * x in: initial guess (used only if guess_nonzero), out: solution.
  * method/pc: UFE_KRYLOV_* / UFE_PC_JACOBI. */
 int ufe_krylov_solve(const ufe_csr *A, const double *b, double *x, double rtol, double abstol,
                      int32_t method, int32_t maxits, int32_t guess_nonzero, int32_t *n_its,
                      int32_t *flags);
+
+/* L0 as the reference calls it -- replaces solve_matrix_equation_CSR_PETSc( A_CSR, bb, xx, rtol, abstol, n_Axb_its)
+ * (petsc_basic.f90:32-64; call sites solve_linearised_SSA_DIVA.f90:159 and conservation_of_mass_semiimplicit.f90:155)
+ * on the ranks of a handle: every rank passes ITS rows of A (i1..i2; ptr: m_loc + 1 local 1-based offsets; ind: global
+ * 1-based columns), its slice bb(m_loc) and its slice xx(m_loc) (in: initial guess, used only with
+ * krylov_guess_nonzero; out: solution).  The row ranges must tile 1..m in rank order (partition_list does).  Krylov
+ * method, preconditioner, maxits come from the handle's ufe_config: for the stiffness system of the handle's mesh
+ * (m = 2 nTri, the rank's rows = its triangle range) every preconditioner is available, including the exact
+ * multifrontal one (UFE_PC_AUTO, UFE_PC_ND_LU); other systems get the banded block solve or point Jacobi.
+ * Collective; 'matrix and vector sub-sizes dont match!' (petsc_basic.f90:91) for inconsistent sizes.
+ * ufe_last_l0_preconditioner: the UFE_PC_* the last call applied (resolves UFE_PC_AUTO). */
+int ufe_solve_matrix_equation_CSR(ufe_handle *h, const ufe_csr *A, const double *bb, double *xx, double rtol, double abstol,
+                                  int32_t *n_Axb_its, int32_t *flags);
+int ufe_last_l0_preconditioner(const ufe_handle *h);
 
 /* multiply_CSR_matrix_with_vector_1D / _2D
  * (src/UPSY/basic/CSR_matrix_algebra/CSR_matrix_vector_multiplication.f90:198,336).

@@ -655,3 +655,85 @@ def test_DIVA_with_nd_lu_preconditioner(oracle, workload, method, lag):
         _check_uv(S, D)
     finally:
         S.close()
+
+
+# ------------------------------------------------------------------------------------------
+# L0 as the reference calls it: solve_matrix_equation_CSR on the ranks of a handle (one rank here; the two-rank row
+# blocks are exercised by tests/tools/multi_gpu_check.py)
+# ------------------------------------------------------------------------------------------
+def _scipy_csr(A):
+    import scipy.sparse as sp
+    return sp.csr_matrix((A.val, A.ind - 1, A.ptr - 1), shape=(A.i2 - A.i1 + 1, A.n))
+
+
+@pytest.mark.parametrize("pc", ["auto", "nd_lu", "bjacobi_lu", "jacobi"])
+def test_L0_handle_solves_the_DIVA_stiffness_system(pc):
+    """solve_matrix_equation_CSR_PETSc( A_CSR, bb, xx, ...) (petsc_basic.f90:32-64, call site
+    solve_linearised_SSA_DIVA.f90:159) with the stiffness matrix the reference would pass: every preconditioner is
+    reachable from the handle's config; x equals the sparse-LU solution of the same system."""
+    import scipy.sparse.linalg as spla
+    mesh, C, ice = experiments.MISMIPplus(8e3)
+    C.visc_it_nit = 3
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        S.solve_DIVA(ice)
+        A, bb = S.get_stiffness_matrix()
+        want = spla.splu(_scipy_csr(A).tocsc()).solve(bb)
+        C2 = copy.deepcopy(C)
+        C2.b200_krylov_pc = pc
+        if pc == "jacobi":
+            C2.b200_krylov_maxits = 200          # point Jacobi does not converge on this operator: the cap must be reported
+        S.set_config(C2)
+        x, its, fl, used = S.solve_matrix_equation_CSR(A, bb, np.zeros_like(bb), 1e-12, 1e-11)
+        if pc == "jacobi":
+            assert used == 0 and its <= 200 and (fl != 0 or rel(x, want)[1] < 1e-6), (its, fl)
+            return
+        assert used == (2 if pc == "bjacobi_lu" else 4), used
+        assert fl == 0 and its <= 3, (its, fl)
+        assert rel(x, want)[1] < 1e-9
+    finally:
+        S.close()
+
+
+@pytest.mark.parametrize("method", ["bicgstab", "gmres"])
+def test_L0_handle_generic_systems(method):
+    """Systems that are not the handle's stiffness matrix (the thickness system of conservation_of_mass_semiimplicit.f90:155,
+    the reference's tridiagonal known answer ut_mpi_CSR_matrix_solving.f90:217-270): banded block solve or point Jacobi."""
+    mesh, C, ice = experiments.ISMIP_HOM("A", 160e3, 11)
+    C.b200_krylov_method = method
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        n = 7
+        D = np.zeros((n, n))
+        for i in range(n):
+            if i in (0, n - 1):
+                D[i, i] = 1.0
+            else:
+                D[i, i - 1:i + 2] = [-1.0, 2.0, -1.0]
+        x, its, fl, used = S.solve_matrix_equation_CSR(_csr(D), np.ones(n), np.zeros(n), 1e-12, 1e-14)
+        assert fl == 0 and its <= 7 and used in (0, 2)
+        assert np.abs(x - np.array([1, 3.5, 5, 5.5, 5, 3.5, 1.0])).max() < 1e-10
+        # a random diagonally dominant banded system, unsorted columns
+        rng = np.random.default_rng(5)
+        n = 3000
+        rows = []
+        for i in range(n):
+            cols = sorted(set(int(c) for c in np.clip(i + rng.integers(-40, 41, 8), 0, n - 1)) - {i})
+            r = [(c + 1, float(rng.standard_normal())) for c in cols]
+            rng.shuffle(r)
+            r.insert(len(r) // 2, (i + 1, 10.0 + float(rng.random())))
+            rows.append(r)
+        A = _csr_rows(rows, n)
+        b = rng.standard_normal(n)
+        import scipy.sparse.linalg as spla
+        want = spla.splu(_scipy_csr(A).tocsc()).solve(b)
+        x, its, fl, used = S.solve_matrix_equation_CSR(A, b, np.zeros(n), 1e-13, 1e-14)
+        assert fl == 0 and rel(x, want)[1] < 1e-10, (its, fl, used)
+        # the reference's size check (petsc_basic.f90:91)
+        with pytest.raises(UfeError, match="sub-sizes"):
+            S.solve_matrix_equation_CSR(A, b[:-1], np.zeros(n - 1), 1e-13, 1e-14)
+        half = diva.CSRMatrix(n, n, 1, n // 2, A.ptr[:n // 2 + 1], A.ind, A.val)
+        with pytest.raises(UfeError, match="all rows"):
+            S.solve_matrix_equation_CSR(half, b[:n // 2], np.zeros(n // 2), 1e-13, 1e-14)
+    finally:
+        S.close()

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     assert declared == set(capi.EXPORTS)
-    assert lib.ufe_version() == 100
+    assert lib.ufe_version() == 200
 
 
 def test_partition_list_matches_oracle(oracle):

@@ -89,6 +89,64 @@ for name, (mesh, C, ice), pc_name, meth in cases:
             print(f'{name} thickness update (calc_dHi_dt, replicated on {world} ranks): identical on all ranks {same}, Hi_tplusdt vs oracle {rt:.2e} '
                   f'Krylov {thk["n_Axb_its"]} {"OK" if good_t else "MISMATCH"}', flush=True)
     S.close()
+# L0 as the reference calls it (solve_matrix_equation_CSR_PETSc, petsc_basic.f90:32-64): every rank passes its row block
+import scipy.sparse as sp, scipy.sparse.linalg as spla
+def gather_rows(local, n_total, i1):
+    """all ranks' slices -> the full vector on every rank (slices tile 1..n in rank order)"""
+    sizes = [torch.zeros(1, dtype=torch.int64, device='cuda') for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([local.size], dtype=torch.int64, device='cuda'))
+    parts = [torch.zeros(int(s.item()), dtype=torch.float64, device='cuda') for s in sizes]
+    full = torch.zeros(n_total, dtype=torch.float64, device='cuda')
+    full[i1 - 1:i1 - 1 + local.size] = torch.from_numpy(np.ascontiguousarray(local)).cuda()
+    dist.all_reduce(full)
+    return full.cpu().numpy()
+mesh, C, ice = experiments.MISMIPplus(8e3)
+C.visc_it_nit = 3
+C.b200_krylov_pc = 'auto'
+S = diva.initialise_DIVA_solver(mesh, C, make_comm())
+S.solve_DIVA(ice)
+A, bb = S.get_stiffness_matrix()                       # this rank's rows, exactly what the reference holds
+loc = sp.csr_matrix((A.val, A.ind - 1, A.ptr - 1), shape=(A.i2 - A.i1 + 1, A.n))
+x, its, fl, used = S.solve_matrix_equation_CSR(A, bb, np.zeros_like(bb), 1e-12, 1e-11)
+xf, bf = gather_rows(x, A.m, A.i1), gather_rows(bb, A.m, A.i1)
+# residual of the rank's own rows against the gathered solution; the exact solution through a gathered matrix on rank 0
+r_loc = np.abs(loc @ xf - bb).max() / np.abs(bf).max()
+r_all = torch.tensor([r_loc], dtype=torch.float64, device='cuda'); dist.all_reduce(r_all, op=dist.ReduceOp.MAX)
+good = fl == 0 and its <= 3 and r_all.item() < 1e-10 and (used == 4 if world in (1, 2, 4, 8) else used in (0, 2))
+ok &= good
+if rank == 0:
+    print(f'L0 solve_matrix_equation_CSR, DIVA stiffness rows of {world} ranks [auto -> pc {used}]: Krylov {its} flags {fl} residual {r_all.item():.2e} '
+          f'{"OK" if good else "MISMATCH"}', flush=True)
+# a generic system (not the stiffness matrix): banded, diagonally dominant, row blocks by partition_list
+n = 6000
+i1, i2 = diva.partition_list(n, rank, world)
+rng = np.random.default_rng(11)
+rows_all = []
+for i in range(n):
+    cols = sorted(set(int(c) for c in np.clip(i + rng.integers(-30, 31, 6), 0, n - 1)) - {i})
+    rows_all.append([(i + 1, 8.0 + float(rng.random()))] + [(c + 1, float(rng.standard_normal())) for c in cols])
+b_all = rng.standard_normal(n)
+ptr, ind, val = [1], [], []
+for r in rows_all[i1 - 1:i2]:
+    for c, v in r: ind.append(c); val.append(v)
+    ptr.append(len(ind) + 1)
+Ag = diva.CSRMatrix(n, n, i1, i2, np.array(ptr, np.int32), np.array(ind, np.int32), np.array(val))
+for pc_name in ('jacobi', 'auto'):
+    C2 = __import__('copy').deepcopy(C); C2.b200_krylov_pc = pc_name
+    S.set_config(C2)
+    x, its, fl, used = S.solve_matrix_equation_CSR(Ag, b_all[i1 - 1:i2], np.zeros(i2 - i1 + 1), 1e-13, 1e-14)
+    xf = gather_rows(x, n, i1)
+    if rank == 0:
+        full = sp.lil_matrix((n, n))
+        for i, r in enumerate(rows_all):
+            for c, v in r: full[i, c - 1] = v
+        want = spla.splu(full.tocsc()).solve(b_all)
+        e = np.abs(xf - want).max() / np.abs(want).max()
+        good = fl == 0 and e < 1e-10
+        ok &= good
+        print(f'L0 solve_matrix_equation_CSR, generic banded system n={n} on {world} ranks [{pc_name} -> pc {used}]: Krylov {its} flags {fl} '
+              f'x vs sparse LU {e:.2e} {"OK" if good else "MISMATCH"}', flush=True)
+S.close()
 # the default for small systems: not partitioned, every rank solves the whole system, bit-identical results
 del os.environ['UFE_REDUNDANT_MAX_UNKNOWNS']
 mesh, C, ice = experiments.MISMIPplus(8e3)

@@ -131,7 +131,7 @@ class ufe_comm(ct.Structure):
 
 
 EXPORTS = [
-    "ufe_last_error_string", "ufe_comm_get_unique_id", "ufe_version", "ufe_partition_list",
+    "ufe_last_error_string", "ufe_comm_get_unique_id", "ufe_version", "ufe_sizeof_solve_info", "ufe_partition_list",
     "ufe_krylov_solve", "ufe_spmv", "ufe_diva_create", "ufe_diva_destroy", "ufe_diva_set_config",
     "ufe_diva_solve", "ufe_ssa_solve", "ufe_diva_upload", "ufe_diva_solve_resident",
     "ufe_diva_download", "ufe_diva_reset_state", "ufe_calc_secondary_velocities", "ufe_ssa_diva_linearised", "ufe_mesh_get_operator",
@@ -139,6 +139,7 @@ EXPORTS = [
     "ufe_mesh_set_edges", "ufe_calc_dHi_dt", "ufe_calc_dHi_dt_explicit", "ufe_calc_dHi_dt_semiimplicit", "ufe_get_thickness_csr",
     "ufe_get_thickness_timing", "ufe_calc_vertical_velocities", "ufe_mesh_get_operator_a_a",
     "ufe_nd_analyse", "ufe_nd_tree_info", "ufe_nd_tree_node", "ufe_nd_tree_entry_map", "ufe_nd_tree_free",
+    "ufe_solve_matrix_equation_CSR", "ufe_last_l0_preconditioner",
     "ufe_nd_solver_create", "ufe_nd_solver_factor", "ufe_nd_solver_solve", "ufe_nd_solver_info", "ufe_nd_solver_free",
 ]
 

@@ -17,6 +17,7 @@ int ufe_build_operators(cudaStream_t st, const DevMesh &dm, int vi1, int vi2, in
 int ufe_colrange(cudaStream_t st, int nnz, const int *ind, int *jmin, int *jmax);
 int ufe_kspmv_plain(cudaStream_t st, const DevSystem &S, const double *xg, double *y, KrylovWork &kw);
 int ufe_kspmv_only(cudaStream_t st, const DevSystem &S, const double *xg, double *y, KrylovWork &kw);
+static int make_plan(struct ufe_handle *h, HaloPlan &plan, int ntot, int own_lo, int own_hi, int need_lo, int need_hi);
 
 // ------------------------------------------------------------------------------------
 // errors, counters
@@ -31,7 +32,8 @@ void ufe_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 extern "C" const char *ufe_last_error_string(void) { return g_err; }
-extern "C" int ufe_version(void) { return 100; }
+extern "C" int ufe_version(void) { return 200; }
+extern "C" int ufe_sizeof_solve_info(void) { return (int)sizeof(ufe_solve_info); }
 
 extern "C" void ufe_partition_list(int32_t ntot, int32_t i, int32_t n, int32_t *i1, int32_t *i2) {
   // mpi_distributed_memory.f90:42-68
@@ -122,6 +124,7 @@ struct ufe_handle {
   int last_is_diva = 1;
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
   int pc_used = -1;                            // resolved preconditioner for the cached pattern (-1 = undecided)
+  int pc_used_l0 = -1;                         // ... of the last ufe_solve_matrix_equation_CSR call
   int pc_age = -1, pc_last_its = 0;            // bjacobi_lu reuse: solves since the last factorisation (-1 = never), its of the last solve
   int64_t pc_factorisations = 0;
   // reductions for the Picard residual
@@ -749,7 +752,7 @@ static int linearised_resident(ufe_handle *h, double rtol, double abstol, int *n
     if (h->pc_age < 0 || lag <= 0 || h->pc_last_its > lag) {
       UFE_TRY(ufe_pclu_factor(h->st, h->S, h->pclu));
       h->pc_age = 0; h->pc_factorisations++; fresh = true;
-    } else h->pc_age++;
+    } else { h->pc_age++; ufe_pclu_mark_reused(h->pclu); }
     pc = h->pclu;
     int its1 = 0, fl1 = 0;
     const int cap = fresh ? h->cfg.krylov_maxits : std::max(4 * lag, 8);
@@ -1131,6 +1134,86 @@ extern "C" int ufe_bench_spmv(ufe_handle *h, int32_t reps, int32_t flush_l2, dou
   *algorithmic_bytes = 12.0 * S.nnz + 4.0 * (S.m_loc + 1) + 8.0 * ncols + 8.0 * S.m_loc;
   return UFE_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// L0 with the handle's communicator: the drop-in for solve_matrix_equation_CSR_PETSc as the reference calls it --
+// every rank passes ITS rows of A (type_sparse_matrix_CSR_dp: rows i1..i2, local 1-based ptr, global 1-based ind),
+// its slice of bb and of xx (petsc_basic.f90:32-64; call sites solve_linearised_SSA_DIVA.f90:159,
+// conservation_of_mass_semiimplicit.f90:155).  Method / preconditioner / maxits / initial guess come from the handle's
+// config: for the stiffness system of the handle's mesh (m = 2 nTri, rows = the rank's triangle range) every
+// preconditioner is available, including the exact multifrontal one (auto, nd_lu); other systems get point Jacobi or
+// the banded block solve.  Collective over the ranks of the handle.
+// ------------------------------------------------------------------------------------
+extern "C" int ufe_solve_matrix_equation_CSR(ufe_handle *h, const ufe_csr *A, const double *bb, double *xx, double rtol,
+                                             double abstol, int32_t *n_Axb_its, int32_t *flags) {
+  if (!h || !A || !bb || !xx || !A->ptr || (A->nnz > 0 && (!A->ind || !A->val))) { ufe_set_error("null argument"); return UFE_ERR_INVALID; }
+  if (A->m != A->n || A->m_loc < 0 || A->i1 < 1 || A->i1 - 1 + A->m_loc > A->m) { ufe_set_error("matrix and vector sub-sizes dont match!"); return UFE_ERR_INVALID; }
+  UFE_CUDA(cudaSetDevice(h->device));
+  const int N = A->m, m_loc = A->m_loc, r0 = A->i1 - 1, P = h->comm.nranks;
+  if (P == 1 && m_loc != N) { ufe_set_error("one rank must hold all rows of the matrix"); return UFE_ERR_INVALID; }
+  cudaStream_t st = h->st;
+  DevSystem T;
+  T.N = N; T.m_loc = m_loc; T.r1 = A->i1; T.nnz = A->nnz;
+  KrylovWork kw;
+  PcLU *pc = nullptr;
+  int rc = UFE_OK;
+  auto cleanup = [&]() {
+    ufe_pclu_free(pc); ufe_krylov_free(kw);
+    cudaFree(T.ptr); cudaFree(T.ind); cudaFree(T.val); cudaFree(T.valS); cudaFree(T.bb); cudaFree(T.bS); cudaFree(T.x);
+  };
+#define L0_TRY(call) do { rc = (call); if (rc != UFE_OK) { cleanup(); return rc; } } while (0)
+  L0_TRY(dupload(&T.ptr, A->ptr, (size_t)m_loc + 1)); L0_TRY(dupload(&T.ind, A->ind, (size_t)A->nnz));
+  L0_TRY(dupload(&T.val, A->val, (size_t)A->nnz)); L0_TRY(dalloc(&T.valS, (size_t)A->nnz));
+  L0_TRY(dupload(&T.bb, bb, (size_t)m_loc)); L0_TRY(dalloc(&T.bS, (size_t)m_loc));
+  L0_TRY(dalloc(&T.x, (size_t)N));
+  if (m_loc > 0 && cudaMemcpy(T.x + r0, xx, sizeof(double) * m_loc, cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); ufe_set_error("upload of xx failed"); return UFE_ERR_CUDA; }
+  int lo = A->i1, hi = A->i1 - 1;
+  if (A->nnz > 0) L0_TRY(ufe_colrange(st, A->nnz, T.ind, &lo, &hi));
+  T.jmin = lo; T.jmax = hi;
+  HaloPlan plan;
+  L0_TRY(make_plan(h, plan, N, r0, r0 + m_loc, lo - 1, hi));
+  plan.mult = 1;
+  if (P > 1) {                      // the strips must tile 1..m in rank order
+    int next = 0;
+    for (int q = 0; q < P; q++) { if (plan.own_lo[q] != next) { cleanup(); ufe_set_error("the row ranges of the ranks must be contiguous and in rank order"); return UFE_ERR_INVALID; } next = plan.own_hi[q]; }
+    if (next != N) { cleanup(); ufe_set_error("the row ranges of the ranks do not cover the matrix"); return UFE_ERR_INVALID; }
+  }
+  Comm c2 = h->comm;                // generic CSR rows: NCCL halo exchange + all-reduce (the peer-memory path reads the blocked layout)
+  c2.peer.on = 0;
+  L0_TRY(ufe_krylov_alloc(kw, N, m_loc, true));
+  L0_TRY(ufe_launch_scale_generic(st, T));
+  const int want = h->cfg.krylov_pc;
+  const bool stiff = N == 2 * h->dm.nTri && A->i1 == 2 * h->ti1 - 1 && m_loc == 2 * (h->ti2 - h->ti1 + 1);
+  const bool pow2 = (P & (P - 1)) == 0;
+  int used = UFE_PC_JACOBI;
+  if ((want == UFE_PC_AUTO || want == UFE_PC_ND_LU) && stiff && pow2) {
+    rc = ufe_pclu_setup_nd(st, T, &c2, h->dm.nTri, h->hGC.data(), h->hGC.data() + h->dm.nTri, &pc);
+    if (rc == UFE_OK) { ufe_pclu_set_point_scaling(pc); used = UFE_PC_ND_LU; }
+    else if (rc == UFE_ERR_CUDA || want == UFE_PC_ND_LU) { cleanup(); return rc; }
+    else pc = nullptr;
+  } else if (want == UFE_PC_ND_LU) {
+    cleanup(); ufe_set_error("krylov_pc nd_lu needs the stiffness system of the handle's mesh (2 nTri unknowns, the rank's triangle rows)"); return UFE_ERR_INVALID;
+  }
+  if (!pc && (want == UFE_PC_AUTO || want == UFE_PC_BJACOBI_LU)) {
+    rc = ufe_pclu_setup(st, T, 0, (size_t)24 << 30, &pc);
+    if (rc == UFE_OK) used = UFE_PC_BJACOBI_LU;
+    else if (rc == UFE_ERR_CUDA || want == UFE_PC_BJACOBI_LU) { cleanup(); return rc; }
+    else pc = nullptr;
+  }
+  if (pc) L0_TRY(ufe_pclu_factor(st, T, pc));
+  int its = 0, fl = 0;
+  L0_TRY(ufe_krylov_run(st, T, kw, c2, P > 1 ? &plan : nullptr, h->cfg.krylov_method, rtol, abstol, h->cfg.krylov_maxits,
+                        h->cfg.krylov_guess_nonzero, &its, &fl, pc));
+  if (m_loc > 0 && (cudaMemcpyAsync(xx, T.x + r0, sizeof(double) * m_loc, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                    cudaStreamSynchronize(st) != cudaSuccess)) { cleanup(); ufe_set_error("copy back of xx failed"); return UFE_ERR_CUDA; }
+#undef L0_TRY
+  cleanup();
+  h->pc_used_l0 = used;
+  if (n_Axb_its) *n_Axb_its = its;
+  if (flags) *flags = fl;
+  return UFE_OK;
+}
+extern "C" int ufe_last_l0_preconditioner(const ufe_handle *h) { return h ? h->pc_used_l0 : -1; }
 
 // ------------------------------------------------------------------------------------
 // L0: generic CSR entry points (single GPU)

@@ -165,10 +165,15 @@ int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int replicate, size_t ma
 int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc);
 int ufe_pclu_apply(cudaStream_t st, PcLU *pc, const double *r, double *z);
 void ufe_pclu_free(PcLU *pc);
+bool ufe_pclu_exact_and_fresh(const PcLU *pc);   // whole-matrix factorisation of the current values: M^-1 b is the solution up to round-off
+void ufe_pclu_mark_reused(PcLU *pc);
 // multifrontal nested-dissection solver as the exact preconditioner (ufe_nd_numeric.cu; krylov_pc = UFE_PC_ND_LU)
 int ufe_pclu_setup_nd(cudaStream_t st, const DevSystem &S, const Comm *comm, int nT, const double *gcx, const double *gcy, PcLU **out);
 int ufe_nd_pc_create(cudaStream_t st, const DevSystem &S, const Comm *comm, int nT, const double *gcx, const double *gcy, int leaf, ufe_nd_solver **out);
 void ufe_nd_pc_info(const ufe_nd_solver *S, double *front_bytes, double *flops, int *n_fronts);
+void ufe_nd_pc_set_point_scaling(ufe_nd_solver *S);     // the Krylov operator is diag(A)^-1 A (generic L0 systems) instead of the 2x2-block scaling
+void ufe_pclu_set_point_scaling(PcLU *pc);
+int ufe_launch_scale_generic(cudaStream_t st, const DevSystem &S);
 int ufe_nd_pc_factor(cudaStream_t st, ufe_nd_solver *S, const double *dval);
 int ufe_nd_pc_apply(cudaStream_t st, ufe_nd_solver *S, const double *r, double *z);
 int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm,
@@ -180,6 +185,7 @@ struct HaloPlan {
   int nranks = 1, rank = 0;
   std::vector<int> own_lo, own_hi;     // 0-based [lo,hi) owned by each rank
   std::vector<int> need_lo, need_hi;   // 0-based [lo,hi) each rank needs (own + halo)
+  int mult = 2;                        // vector entries per index (2: the (u,v) pair of a triangle; 1: generic systems)
 };
 int ufe_halo_exchange(cudaStream_t st, const Comm &comm, const HaloPlan &plan, double *x, long long ld,
                       int nlayers, int mult);

@@ -39,7 +39,7 @@
 #define GM_INVHN(gm) ((gm) + 31 * 30 + 60 + 31 + 30 + 32)
 #define GM_SIZE (31 * 30 + 60 + 31 + 30 + 32 + 1)
 
-enum { ST_INIT = 0, ST_A = 1, ST_B = 2, ST_C = 3, ST_GM_INIT = 4, ST_GM_H = 5, ST_GM_NORM = 6, ST_S = 7 };
+enum { ST_INIT = 0, ST_A = 1, ST_B = 2, ST_C = 3, ST_GM_INIT = 4, ST_GM_H = 5, ST_GM_NORM = 6, ST_S = 7, ST_RICH = 8 };
 
 __device__ void gmres_givens(KrylovScalars *sc, double *gm, double hn);
 
@@ -53,6 +53,13 @@ __device__ void post_reduce(int stage, KrylovScalars *sc, double *gm, double rto
       sc->rho = sc->dots[0];
       sc->alpha = 1.0; sc->omega = 1.0; sc->beta = 0.0;
       if (sc->rnorm <= sc->ttol) { sc->done = 1; sc->reason = (sc->rnorm <= abstol) ? 3 : 2; }
+      break;
+    }
+    case ST_RICH: {   // dots: (r,r), (b,b) after the Richardson step x = M^-1 b with an exact M: one iteration if it passes
+      sc->bnorm = sqrt(sc->dots[1]);
+      sc->ttol = fmax(rtol * sc->bnorm, abstol);
+      sc->rnorm = sqrt(sc->dots[0]);
+      if (sc->rnorm <= sc->ttol) { sc->its = 1; sc->done = 1; sc->reason = (sc->rnorm <= abstol) ? 3 : 2; }
       break;
     }
     case ST_A: {      // dots: (rhat, v)
@@ -462,7 +469,7 @@ static int apply_op(cudaStream_t st, const DevSystem &S, PcLU *pc, const double 
 __global__ void __launch_bounds__(UFE_RED_THREADS)
 k_bicg_init(int n, int r0, const double *__restrict__ b, double *__restrict__ r, double *__restrict__ rhat,
             double *__restrict__ pg, double *__restrict__ xg, int have_ax, double *partials, unsigned *counter,
-            double *dots_local, KrylovScalars *sc, int single, double rtol, double abstol) {
+            double *dots_local, KrylovScalars *sc, int single, double rtol, double abstol, int stage = ST_INIT) {
   double acc[2] = {0.0, 0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double bi = b[i];
@@ -471,7 +478,7 @@ k_bicg_init(int n, int r0, const double *__restrict__ b, double *__restrict__ r,
     r[i] = ri; rhat[i] = ri; pg[r0 + i] = ri;
     acc[0] += ri * ri; acc[1] += bi * bi;
   }
-  finish_stage<2>(acc, ST_INIT, partials, counter, dots_local, sc, nullptr, single, rtol, abstol);
+  finish_stage<2>(acc, stage, partials, counter, dots_local, sc, nullptr, single, rtol, abstol);
 }
 
 // p = r + beta (p - omega v)
@@ -729,7 +736,7 @@ static int sync_input(cudaStream_t st, const Comm &comm, const HaloPlan *halo, d
   *use_pv = false;
   if (!halo || comm.nranks <= 1) return UFE_OK;
   PeerComm &pc = comm.peer;
-  if (!pc.on) return ufe_halo_exchange(st, comm, *halo, vec, 0, 1, 2);
+  if (!pc.on) return ufe_halo_exchange(st, comm, *halo, vec, 0, 1, halo->mult);
   int epoch = pre_epoch;          // > 0: the producing kernel has published this epoch itself
   if (epoch <= 0) {
     epoch = (int)(++pc.halo_epoch);
@@ -827,6 +834,29 @@ static int run_bicgstab(cudaStream_t st, const DevSystem &S, KrylovWork &kw, con
   return UFE_OK;
 }
 
+// An exact, fresh factorisation M = A: x = M^-1 b IS the solution up to round-off, so before any Krylov machinery take
+// that one Richardson step from x = 0 and test the reference's stopping rule on the true residual of the scaled system,
+// |B (b - A x)| <= max(rtol |B b|, abstol) (petsc_basic.f90:106-128 with B the Jacobi scaling) -- one preconditioner
+// application and one SpMV per linear solve.  If the test fails (a perturbed pivot, an ill-conditioned front) the Krylov
+// method continues from this x as a non-zero initial guess.  *done: the system is solved.
+static int richardson_first(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm, const HaloPlan *halo,
+                            double rtol, double abstol, int maxits, PcLU *pc, bool *done) {
+  const int n = S.m_loc, r0 = S.r1 - 1, single = comm.nranks <= 1;
+  const bool peer = !single && comm.peer.on && halo;
+  PeerView pv; bool use_pv = false;
+  k_sc_reset<<<1, 1, 0, st>>>(kw.sc, maxits, abstol); UFE_LAUNCH_CHECK();
+  UFE_TRY(ufe_pclu_apply(st, pc, S.bS, S.x + r0));
+  UFE_TRY(sync_input(st, comm, halo, S.x, &pv, &use_pv));
+  UFE_TRY(launch_kspmv<0>(st, S, S.x, kw.r, nullptr, 0, kw, single, rtol, abstol, use_pv ? &pv : nullptr));
+  k_bicg_init<<<UFE_RED_BLOCKS, UFE_RED_THREADS, 0, st>>>(n, r0, S.bS, kw.r, kw.rhat, kw.pg, S.x, 1, kw.partials, kw.counter, kw.dots_local, kw.sc,
+                                                          single ? 1 : (peer ? -(int)(++comm.peer.red_epoch) : 0), rtol, abstol, ST_RICH);
+  UFE_LAUNCH_CHECK();
+  UFE_TRY(allreduce_stage(st, comm, kw, ST_RICH, 2, rtol, abstol));
+  UFE_TRY(poll(st, kw));
+  *done = kw.sc_host->done != 0;
+  return UFE_OK;
+}
+
 static int run_gmres(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Comm &comm, const HaloPlan *halo,
                      double rtol, double abstol, int maxits, int guess_nonzero, bool reset, PcLU *pc) {
   const int n = S.m_loc, r0 = S.r1 - 1, single = comm.nranks <= 1;
@@ -895,7 +925,14 @@ int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Co
                    PcLU *pc) {
   if (maxits <= 0) maxits = 10000;
   int fl = 0;
-  if (method == UFE_KRYLOV_GMRES) {
+  static const bool rich_off = getenv("UFE_RICHARDSON_FIRST") && atoi(getenv("UFE_RICHARDSON_FIRST")) == 0;
+  bool solved = false;
+  if (pc && !guess_nonzero && !rich_off && ufe_pclu_exact_and_fresh(pc)) {
+    UFE_TRY(richardson_first(st, S, kw, comm, halo, rtol, abstol, maxits, pc, &solved));
+    guess_nonzero = 1;
+  }
+  if (solved) {
+  } else if (method == UFE_KRYLOV_GMRES) {
     if (!kw.Vb) { ufe_set_error("GMRES workspace not allocated"); return UFE_ERR_INVALID; }
     UFE_TRY(run_gmres(st, S, kw, comm, halo, rtol, abstol, maxits, guess_nonzero, true, pc));
   } else {

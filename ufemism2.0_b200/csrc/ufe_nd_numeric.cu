@@ -88,6 +88,7 @@ struct ufe_nd_solver {
   float factor_ms = 0.f, solve_ms = 0.f;
   double flops = 0.0;
   bool factored = false;
+  int premul_pair = 1;                       // preconditioner mode: the right-hand side is multiplied by the 2x2 (1) or 1x1 (0) diagonal blocks
   int use_graphs = 1, k64 = 1, cl_max_fronts = 32;      // levels with at most this many (large) fronts use the cluster sweeps
   MfGraph g_factor, g_apply[6];
 };
@@ -166,75 +167,132 @@ __global__ void k_mf_pack(int nb, int ld, const double *__restrict__ src, double
 // ------------------------------------------------------------------------------------------------------------------
 // factorisation kernels
 // ------------------------------------------------------------------------------------------------------------------
-// 32 x 32 inverse in shared memory by 1024 threads (i, j): Gauss-Jordan on [S | I2], partial pivoting as a row
-// permutation, searched only when the natural pivot is small (the fronts are Jacobi-scaled); vanishing pivots are
-// perturbed statically -- the refinement / Krylov iteration around the solver absorbs that.
-__device__ __forceinline__ void mf_invert32(double (*S)[MFB + 1], double (*I2)[MFB + 1], double (*Ip)[MFB + 1], int *perm,
-                                            int i, int j) {
-  I2[i][j] = (i == j) ? 1.0 : 0.0;
-  if (i == 0) perm[j] = j;
+// 32 x 32 inverse by the 8 warps of a CTA, matrix in registers: warp w holds the columns 4 w .. 4 w + 3, lane = row.
+// In-place Gauss-Jordan -- at step p column p of the work matrix is replaced by the column of the inverse that belongs to
+// the pivot row, so there is no [S | I] pair.  The warp that owns the columns 4 g .. 4 g + 3 runs those four steps on its
+// own: per step it picks the pivot row P, forms the multipliers m_i = a_ip / a_Pp, updates its four columns and leaves
+// (m, P) in shared memory (double-buffered by the parity of g: ONE block barrier per four steps); every other warp then
+// applies the four steps to its columns, broadcasting its entries of the pivot rows with shuffles.
+// Threshold partial pivoting as an implicit row permutation (perm_s[k] = the row that eliminates column k), searched
+// only when the natural pivot is small (the fronts are Jacobi-scaled); vanishing pivots are perturbed statically -- the
+// refinement / Krylov iteration around the solver absorbs that.  Rows are scaled lazily: a pivot row keeps its
+// unscaled values and its factor 1 / pivot (row scalings commute with the later row operations, whose multipliers are
+// formed from the same stored values), one multiply per entry at the end.
+// Result: Ip = inverse, Ip[pinv[i]][perm[q]] = a_i[q] s_i.  All MF_PANEL_THREADS threads must call this.
+#define MF_PANEL_THREADS 256
+struct MfInvScratch { double m[2][4][MFB]; double s[MFB]; int perm[MFB], pinv[MFB], P[2][4]; };
+
+__device__ __forceinline__ void mf_inv32_cta(double (&a)[4], int lane, int w, double (*Ip)[MFB + 1], MfInvScratch &sc) {
+  const unsigned FULL = 0xffffffffu;
+  if (w == 0) { sc.perm[lane] = lane; sc.s[lane] = 1.0; }
   __syncthreads();
-  for (int p = 0; p < MFB; p++) {
-    if (fabs(S[perm[p]][p]) < 0.05) {
-      __syncthreads();
-      if (i == 0) {
-        double v = (j >= p) ? fabs(S[perm[j]][p]) : -1.0;
-        int r = j;
-        for (int o = 16; o > 0; o >>= 1) {
-          const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
-          const int r2 = __shfl_xor_sync(0xffffffffu, r, o);
-          if (v2 > v || (v2 == v && r2 < r)) { v = v2; r = r2; }
+#pragma unroll 1
+  for (int g = 0; g < MFB / 4; g++) {
+    const int par = g & 1;
+    if (w == g) {
+      // the owner of the columns 4 g .. 4 g + 3 runs its four steps back to back on its own registers (the block barrier
+      // is paid once per four steps) and leaves the multipliers and pivot rows for the other warps
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int p = 4 * g + t;
+        const double c = a[t];
+        int P = sc.perm[p];
+        double piv = __shfl_sync(FULL, c, P);
+        if (fabs(piv) < 0.05) {                       // uniform: the largest candidate among the unused rows
+          const int mine = sc.perm[lane];
+          double v = __shfl_sync(FULL, c, mine);      // lane k: pivot-column entry of row perm[k]
+          v = lane >= p ? fabs(v) : -1.0;
+          int k = lane;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double v2 = __shfl_xor_sync(FULL, v, o);
+            const int k2 = __shfl_xor_sync(FULL, k, o);
+            if (v2 > v || (v2 == v && k2 < k)) { v = v2; k = k2; }
+          }
+          const int pk = __shfl_sync(FULL, mine, k);
+          __syncwarp();
+          if (lane == 0) { sc.perm[k] = P; sc.perm[p] = pk; }
+          __syncwarp();
+          P = pk;
+          piv = __shfl_sync(FULL, c, P);
         }
-        if (j == 0) { const int t = perm[p]; perm[p] = perm[r]; perm[r] = t; }
+        if (fabs(piv) < 1e-13) piv = piv < 0.0 ? -1e-13 : 1e-13;
+        const double d = 1.0 / piv;
+        const bool isP = lane == P;
+        const double m = isP ? 0.0 : c * d;
+        sc.m[par][t][lane] = m;
+        if (isP) sc.s[lane] = d;
+        if (lane == 0) sc.P[par][t] = P;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const double x = __shfl_sync(FULL, a[k], P);
+          a[k] = fma(-m, x, a[k]);
+        }
+        a[t] = isP ? 1.0 : -m;                        // the inverse's column takes the place of column p
       }
       __syncthreads();
+    } else {
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const double m = sc.m[par][t][lane];
+        const int P = sc.P[par][t];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const double x = __shfl_sync(FULL, a[k], P);
+          a[k] = fma(-m, x, a[k]);
+        }
+      }
     }
-    const int P = perm[p];
-    double piv = S[P][p];
-    if (fabs(piv) < 1e-13) piv = piv < 0.0 ? -1e-13 : 1e-13;
-    const double d = 1.0 / piv;
-    const double f = S[i][p];
-    const double sp = S[P][j] * d, ip = I2[P][j] * d;
-    __syncthreads();
-    if (i == P) { S[i][j] = sp; I2[i][j] = ip; }
-    else { S[i][j] -= f * sp; I2[i][j] -= f * ip; }
-    __syncthreads();
   }
-  Ip[i][j] = I2[perm[i]][j];
+  if (w == 0) sc.pinv[sc.perm[lane]] = lane;
+  __syncthreads();
+  const int row = sc.pinv[lane];
+  const double s = sc.s[lane];
+#pragma unroll
+  for (int k = 0; k < 4; k++) Ip[row][sc.perm[4 * w + k]] = a[k] * s;
   __syncthreads();
 }
 
-// pivot step b of the fronts [first, first + gridDim.y): D_b^-1 (every CTA of a front inverts the 32 x 32 block itself;
-// it is not written here, the inverse goes to the side buffer) and the L panel rows of this CTA:  A_ib <- A_ib D_b^-1.
-// After the inversion the warps work on their own rows, two rows in flight each, without block-level barriers.
-__global__ void __launch_bounds__(1024)
+// pivot step b of the fronts [first, first + gridDim.y): D_b^-1 (warp 0 of every CTA of a front inverts the 32 x 32 block
+// itself while the other warps already fetch their first rows; the block is not written here, the inverse goes to the
+// side buffer) and the L panel rows of this CTA:  A_ib <- A_ib D_b^-1, two rows in flight per warp.
+__global__ void __launch_bounds__(MF_PANEL_THREADS)
 k_mf_panel(int first, int b, int rows_per_cta, const int *__restrict__ G_, const int *__restrict__ ld_,
            const long long *__restrict__ foff, const int *__restrict__ dioff, double *__restrict__ F, double *__restrict__ Dinv) {
+  constexpr int NW = MF_PANEL_THREADS / 32;
   const int f = first + blockIdx.y;
   const int G = G_[f], ld = ld_[f];
   const int r0 = (b + 1) * MFB;
   const int rbeg = r0 + blockIdx.x * rows_per_cta;
   if (blockIdx.x > 0 && rbeg >= G) return;
-  __shared__ double Wb[2 * MFB * (MFB + 1)], Ip[MFB][MFB + 1];
-  __shared__ int perm[MFB];
-  double(*W1)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(Wb), (*W2)[MFB + 1] = reinterpret_cast<double(*)[MFB + 1]>(Wb + MFB * (MFB + 1));
-  double(*Xw)[2][MFB] = reinterpret_cast<double(*)[2][MFB]>(Wb);      // per-warp staging rows; reuse the inversion work space
-  const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
+  __shared__ double Ip[MFB][MFB + 1], Xw[NW][2][MFB];
+  __shared__ MfInvScratch isc;
+  const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
   double *A = F + foff[f];
-  W1[i][j] = A[(size_t)(b * MFB + i) * ld + b * MFB + j];
-  __syncthreads();
-  mf_invert32(W1, W2, Ip, perm, i, j);
-  if (blockIdx.x == 0) Dinv[((size_t)dioff[f] + b) * (MFB * MFB) + i * MFB + j] = Ip[i][j];
   const int rend = min(G, rbeg + rows_per_cta);
-  for (int r = rbeg + i; r < rend; r += 64) {
-    double *T0 = A + (size_t)r * ld + b * MFB, *T1 = T0 + (size_t)32 * ld;
-    const bool two = r + 32 < rend;
-    const double x0 = T0[j], x1 = two ? T1[j] : 0.0;
-    Xw[i][0][j] = x0; Xw[i][1][j] = x1;
+  int r = rbeg + w;
+  double x0 = 0.0, x1 = 0.0;
+  if (r < rend) x0 = A[(size_t)r * ld + b * MFB + j];
+  if (r + NW < rend) x1 = A[(size_t)(r + NW) * ld + b * MFB + j];
+  {
+    double a[4];
+    const double2 *row = reinterpret_cast<const double2 *>(A + (size_t)(b * MFB + j) * ld + b * MFB + 4 * w);
+    const double2 v0 = row[0], v1 = row[1];
+    a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
+    mf_inv32_cta(a, j, w, Ip, isc);
+  }
+  if (blockIdx.x == 0)
+    for (int q = threadIdx.x; q < MFB * MFB; q += MF_PANEL_THREADS) Dinv[((size_t)dioff[f] + b) * (MFB * MFB) + q] = Ip[q >> 5][q & 31];
+  for (bool firstpass = true; r < rend; r += 2 * NW, firstpass = false) {
+    double *T0 = A + (size_t)r * ld + b * MFB, *T1 = T0 + (size_t)NW * ld;
+    const bool two = r + NW < rend;
+    if (!firstpass) { x0 = T0[j]; x1 = two ? T1[j] : 0.0; }
+    Xw[w][0][j] = x0; Xw[w][1][j] = x1;
     __syncwarp();
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < MFB; k++) { const double ip = Ip[k][j]; s0 += Xw[i][0][k] * ip; s1 += Xw[i][1][k] * ip; }
+    for (int k = 0; k < MFB; k++) { const double ip = Ip[k][j]; s0 += Xw[w][0][k] * ip; s1 += Xw[w][1][k] * ip; }
     T0[j] = s0;
     if (two) T1[j] = s1;
     __syncwarp();
@@ -246,46 +304,54 @@ k_mf_panel(int first, int b, int rows_per_cta, const int *__restrict__ G_, const
 //                                       L_i1 = (A_i1 - L_i0 U_01) D1^-1   for the rows i > b1 of this CTA,
 //   row part (blockIdx.x >= nx_col):    U_1j = A_1j - L_10 U_0j            for the columns j > b1 of this CTA.
 // The two parts read and write disjoint blocks, so they share one launch.  Warps work independently after the set-up.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(MF_PANEL_THREADS)
 k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_, const int *__restrict__ ld_,
             const long long *__restrict__ foff, const int *__restrict__ dioff, double *__restrict__ F, double *__restrict__ Dinv) {
+  constexpr int NW = MF_PANEL_THREADS / 32;
   const int f = first + blockIdx.y;
   const int G = G_[f], ld = ld_[f];
   const int b0 = b1 - 1, r1 = (b1 + 1) * MFB;
   const bool colpart = (int)blockIdx.x < nx_col;
   const int cbeg = r1 + (colpart ? (int)blockIdx.x : (int)blockIdx.x - nx_col) * chunk;
   if (cbeg >= G && !(colpart && blockIdx.x == 0)) return;
-  __shared__ double W1[MFB][MFB + 1], W2[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1];
-  __shared__ int perm[MFB];
-  double(*Xr)[MFB] = reinterpret_cast<double(*)[MFB]>(&W1[0][0]);      // per-warp staging row; reuses the inversion input
-  const int j = threadIdx.x & 31, i = threadIdx.x >> 5;
+  __shared__ double W1[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1], Xr[NW][MFB];
+  __shared__ MfInvScratch isc;
+  const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
   double *A = F + foff[f];
   const int cend = min(G, cbeg + chunk);
-  X[i][j] = A[(size_t)(b1 * MFB + i) * ld + b0 * MFB + j];            // L_10
+  for (int i = w; i < MFB; i += NW) X[i][j] = A[(size_t)(b1 * MFB + i) * ld + b0 * MFB + j];            // L_10
   if (colpart) {
-    Y[i][j] = A[(size_t)(b0 * MFB + i) * ld + b1 * MFB + j];          // U_01
+    for (int i = w; i < MFB; i += NW) Y[i][j] = A[(size_t)(b0 * MFB + i) * ld + b1 * MFB + j];          // U_01
     __syncthreads();
-    double d = A[(size_t)(b1 * MFB + i) * ld + b1 * MFB + j];
+    for (int i = w; i < MFB; i += NW) {
+      double d = A[(size_t)(b1 * MFB + i) * ld + b1 * MFB + j];
 #pragma unroll 8
-    for (int k = 0; k < MFB; k++) d -= X[i][k] * Y[k][j];
-    W1[i][j] = d;
+      for (int k = 0; k < MFB; k++) d -= X[i][k] * Y[k][j];
+      W1[i][j] = d;
+    }
     __syncthreads();
-    mf_invert32(W1, W2, Ip, perm, i, j);
-    if (blockIdx.x == 0) Dinv[((size_t)dioff[f] + b1) * (MFB * MFB) + i * MFB + j] = Ip[i][j];
-    for (int r = cbeg + i; r < cend; r += 32) {
+    {
+      double a[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) a[q] = W1[j][4 * w + q];
+      mf_inv32_cta(a, j, w, Ip, isc);
+    }
+    if (blockIdx.x == 0)
+      for (int q = threadIdx.x; q < MFB * MFB; q += MF_PANEL_THREADS) Dinv[((size_t)dioff[f] + b1) * (MFB * MFB) + q] = Ip[q >> 5][q & 31];
+    for (int r = cbeg + w; r < cend; r += NW) {
       double *T = A + (size_t)r * ld;
       const double l0 = T[b0 * MFB + j];
       double v = T[b1 * MFB + j];
-      Xr[i][j] = l0;
+      Xr[w][j] = l0;
       __syncwarp();
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) v -= Xr[i][k] * Y[k][j];
+      for (int k = 0; k < MFB; k++) v -= Xr[w][k] * Y[k][j];
       __syncwarp();
-      Xr[i][j] = v;
+      Xr[w][j] = v;
       __syncwarp();
       double sum = 0.0;
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) sum += Xr[i][k] * Ip[k][j];
+      for (int k = 0; k < MFB; k++) sum += Xr[w][k] * Ip[k][j];
       T[b1 * MFB + j] = sum;
       __syncwarp();
     }
@@ -293,7 +359,7 @@ k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_
     __syncthreads();
     // work item = (32-column chunk, group of 8 rows of block b1); lane = column
     const int nch = (cend - cbeg + MFB - 1) / MFB;
-    for (int it = i; it < nch * 4; it += 32) {
+    for (int it = w; it < nch * 4; it += NW) {
       const int col = cbeg + (it >> 2) * MFB + j, ig = (it & 3) * 8;
       if (col >= cend) continue;
       double acc[8];
@@ -484,7 +550,7 @@ k_mf_fwd(int first, const int *__restrict__ ns_, const int *__restrict__ p_, con
     double v = 0.0;
     if (i < ns) {
       const int d = sepdof[sep_off[f] + i];
-      v = scale[d] * (dself ? dself[d] * rhs[d] + dpair[d] * rhs[d ^ 1] : rhs[d]);
+      v = scale[d] * (dself ? dself[d] * rhs[d] + (dpair ? dpair[d] * rhs[d ^ 1] : 0.0) : rhs[d]);
     }
     if (w0 >= 0) { const int a = pinv0[wo + i]; if (a >= 0) v += W[w0 + a]; }
     if (w1 >= 0) { const int a = pinv1[wo + i]; if (a >= 0) v += W[w1 + a]; }
@@ -589,7 +655,7 @@ k_mf_fwd_cl(int first, const int *__restrict__ ns_, const int *__restrict__ p_, 
     double v = 0.0;
     if (i < ns) {
       const int d = sepdof[sep_off[f] + i];
-      v = scale[d] * (dself ? dself[d] * rhs[d] + dpair[d] * rhs[d ^ 1] : rhs[d]);
+      v = scale[d] * (dself ? dself[d] * rhs[d] + (dpair ? dpair[d] * rhs[d ^ 1] : 0.0) : rhs[d]);
     }
     if (w0 >= 0) { const int a = pinv0[wo + i]; if (a >= 0) v += W[w0 + a]; }
     if (w1 >= 0) { const int a = pinv1[wo + i]; if (a >= 0) v += W[w1 + a]; }
@@ -986,7 +1052,7 @@ static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *d
       };
       int chunk = 0;
       const int nx = split(sp.n_active, sp.max_trail, &chunk);
-      k_mf_panel<<<dim3(nx, sp.n_active), 1024, 0, st>>>(L.first, b, chunk, S->G, S->ld, S->foff, S->dioff, S->F, S->Dinv);
+      k_mf_panel<<<dim3(nx, sp.n_active), MF_PANEL_THREADS, 0, st>>>(L.first, b, chunk, S->G, S->ld, S->foff, S->dioff, S->F, S->Dinv);
       UFE_LAUNCH_CHECK();
       // second block of a 64-wide outer step: only when the same fronts are active in it (they are a prefix, too)
       int nkb = 1, n_upd = sp.n_active, trail = sp.max_trail;
@@ -994,7 +1060,7 @@ static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *d
         const MfStep &s2 = L.step[b + 1];
         int ch2 = 0;
         const int nx2 = split(s2.n_active, s2.max_trail, &ch2);
-        k_mf_panel2<<<dim3(2 * nx2, s2.n_active), 1024, 0, st>>>(L.first, b + 1, nx2, ch2, S->G, S->ld, S->foff, S->dioff, S->F, S->Dinv);
+        k_mf_panel2<<<dim3(2 * nx2, s2.n_active), MF_PANEL_THREADS, 0, st>>>(L.first, b + 1, nx2, ch2, S->G, S->ld, S->foff, S->dioff, S->F, S->Dinv);
         UFE_LAUNCH_CHECK();
         nkb = 2; n_upd = s2.n_active; trail = s2.max_trail;
       }
@@ -1029,10 +1095,10 @@ static int mf_apply_launches(ufe_nd_solver *S, cudaStream_t st, const double *r,
     if (L.n == 0) continue;
     if (L.n <= S->cl_max_fronts && L.maxG >= 768)
       k_mf_fwd_cl<<<L.n * MFCL, 1024, (size_t)L.maxG * sizeof(double), st>>>(L.first, S->ns, S->p, S->G, S->ld, S->foff, S->woff, S->c_w[0], S->c_w[1], S->pinv[0], S->pinv[1],
-                                        S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->dpair, S->F, S->W);
+                                        S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->premul_pair ? S->dpair : nullptr, S->F, S->W);
     else
       k_mf_fwd<<<L.n, 1024, (size_t)L.maxG * sizeof(double), st>>>(L.first, S->ns, S->p, S->G, S->ld, S->foff, S->woff, S->c_w[0], S->c_w[1], S->pinv[0], S->pinv[1],
-                                   S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->dpair, S->F, S->W);
+                                   S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->premul_pair ? S->dpair : nullptr, S->F, S->W);
     UFE_LAUNCH_CHECK();
   }
   for (int l = 0; l < nl; l++) {                 // backward sweep, root first
@@ -1265,6 +1331,8 @@ int ufe_nd_pc_apply(cudaStream_t st, ufe_nd_solver *S, const double *r, double *
   if (n > 0) { k_mf_copy_slice<<<(n + 255) / 256, 256, 0, st>>>(n, S->x + r0, z); UFE_LAUNCH_CHECK(); }
   return UFE_OK;
 }
+
+void ufe_nd_pc_set_point_scaling(ufe_nd_solver *S) { S->premul_pair = 0; }
 
 // storage and flop count of this rank's part of the factorisation
 void ufe_nd_pc_info(const ufe_nd_solver *S, double *front_bytes, double *flops, int *n_fronts) {

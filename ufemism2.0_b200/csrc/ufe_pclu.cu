@@ -51,7 +51,12 @@ struct PcLU {
   double *c = nullptr;                       // 2*K*g work vectors (rhs -> solution, staging)
   size_t bytes = 0;
   ufe_nd_solver *nd = nullptr;               // UFE_PC_ND_LU: the multifrontal solver replaces everything above
+  bool exact = false;                        // the factorisation covers the whole matrix (not one strip block per rank)
+  bool fresh = false;                        // factorised with the current matrix values (cleared when a factorisation is reused)
 };
+
+bool ufe_pclu_exact_and_fresh(const PcLU *pc) { return pc && pc->exact && pc->fresh; }
+void ufe_pclu_mark_reused(PcLU *pc) { if (pc) pc->fresh = false; }
 
 // operand addressing for the batched kernels: item z of a level works on node
 //   node(z) = (2z + 1 + kept) * s - 1 ;   operand block = node + off   (mode 0)
@@ -509,6 +514,7 @@ int ufe_pclu_setup(cudaStream_t st, const DevSystem &S, int replicate, size_t ma
   PcLU *pc = new PcLU();
   pc->n_loc = n_cover;
   pc->replicated = repl ? 1 : 0; pc->own_n = S.m_loc; pc->own_r0 = S.r1 - 1; pc->comm = comm;
+  pc->exact = repl || S.m_loc == S.N;
   if (repl) pc->gather = *gather_all;
   int g = ((bw > 0 ? bw : 1) + GT - 1) / GT * GT;
   if (g > n_cover) g = (n_cover + GT - 1) / GT * GT;
@@ -556,11 +562,15 @@ int ufe_pclu_setup_nd(cudaStream_t st, const DevSystem &S, const Comm *comm, int
   pc->n_loc = S.m_loc;
   const int rc = ufe_nd_pc_create(st, S, comm, nT, gcx, gcy, leaf, &pc->nd);
   if (rc != UFE_OK) { delete pc; return rc; }
+  pc->exact = true;
   *out = pc;
   return UFE_OK;
 }
 
+void ufe_pclu_set_point_scaling(PcLU *pc) { if (pc && pc->nd) ufe_nd_pc_set_point_scaling(pc->nd); }
+
 int ufe_pclu_factor(cudaStream_t st, const DevSystem &S, PcLU *pc) {
+  pc->fresh = true;
   if (pc->nd) return ufe_nd_pc_factor(st, pc->nd, S.val);
   const int g = pc->g, K = pc->K;
   const size_t blk = (size_t)g * g * K * sizeof(double);

@@ -444,6 +444,22 @@ class DIVASolver:
                                                  ct.byref(its), vp(m), vp(bu), vp(bv)))
         return u, v, up, vpv, its.value
 
+    # ---- L0 on the ranks of this handle
+    def solve_matrix_equation_CSR(self, A: CSRMatrix, bb, xx, rtol, abstol):
+        """solve_matrix_equation_CSR_PETSc( A_CSR, bb, xx, rtol, abstol, n_Axb_its) as the reference calls it
+        (petsc_basic.f90:32-64): every rank passes ITS rows of A and its slices of bb / xx; method, preconditioner,
+        maxits and the initial-guess switch come from the solver's config.  Returns (xx, n_Axb_its, flags, pc_used)."""
+        keep = []
+        s = capi.csr_struct(A.m, A.n, A.i1, A.i2, A.ptr, A.ind, A.val, keep)
+        b = np.ascontiguousarray(bb, dtype=np.float64)
+        x = np.array(xx, dtype=np.float64, copy=True)
+        if b.size != A.i2 - A.i1 + 1 or x.size != b.size:
+            raise UfeError(1, "matrix and vector sub-sizes dont match!")
+        its, fl = ct.c_int32(), ct.c_int32()
+        check(capi.lib().ufe_solve_matrix_equation_CSR(self._h, ct.byref(s), vp(b), vp(x), ct.c_double(rtol),
+                                                       ct.c_double(abstol), ct.byref(its), ct.byref(fl)))
+        return x, its.value, fl.value, capi.lib().ufe_last_l0_preconditioner(self._h)
+
     # ---- operators (mesh%M_*), as held on the device
     def get_operator(self, family: str, which: str) -> CSRMatrix:
         fid, names = FAMILIES[family]

@@ -139,6 +139,29 @@ module diva_gpu_bindings
       integer(c_int32_t), intent(out)   :: n_its, flags
     end function ufe_krylov_solve
 
+    ! L0 as the reference calls it: every process passes ITS rows of A_CSR (i1..i2) and its slices of bb / xx; collective
+    ! over the ranks of the handle; method / preconditioner / maxits from the handle's ufe_config
+    integer(c_int) function ufe_solve_matrix_equation_CSR( handle, A, bb, xx, rtol, abstol, n_Axb_its, flags) &
+        bind(C, name='ufe_solve_matrix_equation_CSR')
+      import :: c_int, c_int32_t, c_double, c_ptr, ufe_csr
+      type(c_ptr),        value         :: handle
+      type(ufe_csr),      intent(in)    :: A
+      real(c_double),     intent(in)    :: bb(*)
+      real(c_double),     intent(inout) :: xx(*)
+      real(c_double),     value         :: rtol, abstol
+      integer(c_int32_t), intent(out)   :: n_Axb_its, flags
+    end function ufe_solve_matrix_equation_CSR
+
+    integer(c_int) function ufe_last_l0_preconditioner( handle) bind(C, name='ufe_last_l0_preconditioner')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+    end function ufe_last_l0_preconditioner
+
+    ! ABI check: c_sizeof( info) of type(ufe_solve_info) must equal this (96)
+    integer(c_int) function ufe_sizeof_solve_info() bind(C, name='ufe_sizeof_solve_info')
+      import :: c_int
+    end function ufe_sizeof_solve_info
+
     ! exact multifrontal nested-dissection solver for the b-grid (u,v) systems (csrc/ufe_nd.cu, ufe_nd_numeric.cu):
     ! analyse + create once per mesh, factor + solve per Picard iteration; also reachable as cfg%krylov_pc = 4 (nd_lu)
     integer(c_int) function ufe_nd_analyse( nT, gcx, gcy, bptr, bind_, leaf_triangles, tree) bind(C, name='ufe_nd_analyse')
