@@ -89,7 +89,7 @@ struct ufe_nd_solver {
   double flops = 0.0;
   bool factored = false;
   int premul_pair = 1;                       // preconditioner mode: the right-hand side is multiplied by the 2x2 (1) or 1x1 (0) diagonal blocks
-  int use_graphs = 1, k64 = 1, cl_max_fronts = 32;      // levels with at most this many (large) fronts use the cluster sweeps
+  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384;      // levels with at most this many (large) fronts use the cluster sweeps
   MfGraph g_factor, g_apply[6];
 };
 
@@ -314,7 +314,7 @@ k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_
   const bool colpart = (int)blockIdx.x < nx_col;
   const int cbeg = r1 + (colpart ? (int)blockIdx.x : (int)blockIdx.x - nx_col) * chunk;
   if (cbeg >= G && !(colpart && blockIdx.x == 0)) return;
-  __shared__ double W1[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1], Xr[NW][MFB];
+  __shared__ double W1[MFB][MFB + 1], Ip[MFB][MFB + 1], X[MFB][MFB + 1], Y[MFB][MFB + 1], Xr[NW][2][MFB];
   __shared__ MfInvScratch isc;
   const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
   double *A = F + foff[f];
@@ -338,21 +338,23 @@ k_mf_panel2(int first, int b1, int nx_col, int chunk, const int *__restrict__ G_
     }
     if (blockIdx.x == 0)
       for (int q = threadIdx.x; q < MFB * MFB; q += MF_PANEL_THREADS) Dinv[((size_t)dioff[f] + b1) * (MFB * MFB) + q] = Ip[q >> 5][q & 31];
-    for (int r = cbeg + w; r < cend; r += NW) {
-      double *T = A + (size_t)r * ld;
-      const double l0 = T[b0 * MFB + j];
-      double v = T[b1 * MFB + j];
-      Xr[w][j] = l0;
+    for (int r = cbeg + w; r < cend; r += 2 * NW) {        // two rows in flight per warp
+      double *T0 = A + (size_t)r * ld, *T1 = T0 + (size_t)NW * ld;
+      const bool two = r + NW < cend;
+      const double l0 = T0[b0 * MFB + j], l1 = two ? T1[b0 * MFB + j] : 0.0;
+      double v0 = T0[b1 * MFB + j], v1 = two ? T1[b1 * MFB + j] : 0.0;
+      Xr[w][0][j] = l0; Xr[w][1][j] = l1;
       __syncwarp();
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) v -= Xr[w][k] * Y[k][j];
+      for (int k = 0; k < MFB; k++) { const double y = Y[k][j]; v0 -= Xr[w][0][k] * y; v1 -= Xr[w][1][k] * y; }
       __syncwarp();
-      Xr[w][j] = v;
+      Xr[w][0][j] = v0; Xr[w][1][j] = v1;
       __syncwarp();
-      double sum = 0.0;
+      double s0 = 0.0, s1 = 0.0;
 #pragma unroll 8
-      for (int k = 0; k < MFB; k++) sum += Xr[w][k] * Ip[k][j];
-      T[b1 * MFB + j] = sum;
+      for (int k = 0; k < MFB; k++) { const double ip = Ip[k][j]; s0 += Xr[w][0][k] * ip; s1 += Xr[w][1][k] * ip; }
+      T0[b1 * MFB + j] = s0;
+      if (two) T1[b1 * MFB + j] = s1;
       __syncwarp();
     }
   } else {
@@ -816,6 +818,7 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
   if (const char *e = getenv("UFE_ND_GRAPHS")) S->use_graphs = atoi(e);
   if (const char *e = getenv("UFE_ND_K64")) S->k64 = atoi(e);
   if (const char *e = getenv("UFE_ND_CLUSTER_FRONTS")) S->cl_max_fronts = atoi(e);
+  if (const char *e = getenv("UFE_ND_CLUSTER_MING")) S->cl_min_g = atoi(e);
   if (nranks > 1) S->use_graphs = 0;
   S->lev.resize(nl);
   // local fronts, level-major, p descending inside a level
@@ -1093,7 +1096,7 @@ static int mf_apply_launches(ufe_nd_solver *S, cudaStream_t st, const double *r,
       g_launch_count++;
     }
     if (L.n == 0) continue;
-    if (L.n <= S->cl_max_fronts && L.maxG >= 768)
+    if (L.n <= S->cl_max_fronts && L.maxG >= S->cl_min_g)
       k_mf_fwd_cl<<<L.n * MFCL, 1024, (size_t)L.maxG * sizeof(double), st>>>(L.first, S->ns, S->p, S->G, S->ld, S->foff, S->woff, S->c_w[0], S->c_w[1], S->pinv[0], S->pinv[1],
                                         S->sep_off, S->sepdof, S->scale, r, premul ? S->dself : nullptr, S->premul_pair ? S->dpair : nullptr, S->F, S->W);
     else
@@ -1104,7 +1107,7 @@ static int mf_apply_launches(ufe_nd_solver *S, cudaStream_t st, const double *r,
   for (int l = 0; l < nl; l++) {                 // backward sweep, root first
     const MfLevel &L = S->lev[l];
     if (L.n > 0) {
-      if (L.n <= S->cl_max_fronts && L.maxG >= 768)
+      if (L.n <= S->cl_max_fronts && L.maxG >= S->cl_min_g)
         k_mf_bwd_cl<<<L.n * MFCL, 1024, (size_t)L.maxG * sizeof(double), st>>>(L.first, S->ns, S->p, S->nb, S->ld, S->foff, S->woff, S->pwoff, S->up_off, S->upmap, S->dioff,
                                           S->sep_off, S->sepdof, S->scale, S->F, S->Dinv, S->W, x, accumulate);
       else
