@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libufe_diva.so")
+LIB_PATH = os.environ.get("UFE_LIB_PATH") or os.path.join(_HERE, "libufe_diva.so")   # UFE_LIB_PATH: A/B runs of two builds
 
 c_i32, c_f64 = ct.c_int32, ct.c_double
 P_i32, P_f64 = ct.POINTER(ct.c_int32), ct.POINTER(ct.c_double)

@@ -138,6 +138,40 @@ __device__ __forceinline__ double sliding_beta(const ClosureParams &P, const Ver
 }
 
 // ---------------------------------------------------------------------------------
+// b-grid gather record of a triangle: the four 2-D velocities the a-grid closures map, and
+// calc_vertical_shear_strain_rates on the b-grid (DIVA_main.f90:375-410), du/dz_b = tau_bx zeta / max(eta_min, eta_3D_b).
+// The reference evaluates that quotient per (triangle, layer) and maps it to the a-grid; evaluating it inside the vertex
+// gather would repeat every fp64 division once per adjacent vertex, so it is done here, once, on the owned triangles.
+// ---------------------------------------------------------------------------------
+// a warp packs 32 consecutive triangles: lane = triangle while the layers are read (coalesced) and the quotients are
+// formed, then the 32 records -- contiguous in memory -- leave through shared memory with coalesced stores
+__global__ void __launch_bounds__(128)
+k_pack_b(int t0, int nt, int nTri, int nz, ClosureParams P, DivaFields F) {
+  extern __shared__ double pack_sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, RB = F.RB;
+  const int tb = (blockIdx.x * 4 + w) * 32;              // first local triangle of this warp
+  if (tb >= nt) return;
+  double *tile = pack_sm + (size_t)w * 32 * RB;
+  const int tl = tb + lane;
+  if (tl < nt) {
+    const int tj = t0 + tl;
+    double *rec = tile + lane * RB;
+    rec[0] = F.u_vav_b[tj]; rec[1] = F.v_vav_b[tj]; rec[2] = F.u_base_b[tj]; rec[3] = F.v_base_b[tj];
+    const double tbx = F.tau_bx_b[tj], tby = F.tau_by_b[tj];
+    for (int l = 0; l < nz; l++) {
+      const double den = fmax(P.visc_eff_min, F.eta_3D_b[(size_t)l * nTri + tj]);
+      rec[4 + 2 * l] = tbx * P.zeta[l] / den;
+      rec[5 + 2 * l] = tby * P.zeta[l] / den;
+    }
+    for (int e = 4 + 2 * nz; e < RB; e++) rec[e] = 0.0;
+  }
+  __syncwarp();
+  const int n = min(32, nt - tb) * RB;
+  double *dst = F.rec_b + (size_t)(t0 + tb) * RB;
+  for (int q = lane; q < n; q += 32) dst[q] = tile[q];
+}
+
+// ---------------------------------------------------------------------------------
 // DIVA, a-grid: one thread per owned vertex
 // ---------------------------------------------------------------------------------
 template <int NZ>
@@ -156,16 +190,16 @@ k_vertex_diva(int v0, int nv, int nV, int nTri, int nz_rt, ClosureParams P, DevF
   for (int k = ba.ptr[vl] - 1; k < ba.ptr[vl + 1] - 1; k++) {
     const int tj = ba.ind[k] - 1;
     const double wm = ba.v0[k], wx = ba.v1[k], wy = ba.v2[k];
-    const double uj = F.u_vav_b[tj], vj = F.v_vav_b[tj];
-    du_dx += wx * uj; du_dy += wy * uj; dv_dx += wx * vj; dv_dy += wy * vj;
-    u_a += wm * F.u_base_b[tj]; v_a += wm * F.v_base_b[tj];
-    const double tbx = F.tau_bx_b[tj], tby = F.tau_by_b[tj];
+    const double2 *rec = reinterpret_cast<const double2 *>(F.rec_b + (size_t)tj * F.RB);
+    const double2 uv = rec[0], ub = rec[1];
+    du_dx += wx * uv.x; du_dy += wy * uv.x; dv_dx += wx * uv.y; dv_dy += wy * uv.y;
+    u_a += wm * ub.x; v_a += wm * ub.y;
 #pragma unroll
     for (int l = 0; l < NZA; l++) {
       if (l < nz) {
-        const double den = fmax(P.visc_eff_min, F.eta_3D_b[(size_t)l * nTri + tj]);
-        duz[l] += wm * (tbx * P.zeta[l] / den);
-        dvz[l] += wm * (tby * P.zeta[l] / den);
+        const double2 sh = rec[2 + l];
+        duz[l] += wm * sh.x;
+        dvz[l] += wm * sh.y;
       }
     }
   }
@@ -174,17 +208,19 @@ k_vertex_diva(int v0, int nv, int nV, int nTri, int nz_rt, ClosureParams P, DevF
   const double nexp = P.n_Glen;
   const double enh = enhancement(P, I, vi);
   const double e1 = -1.0 / nexp, e2 = (1.0 - nexp) / (2.0 * nexp);
+  const bool uniform = P.rheology == UFE_RHEO_UNIFORM;
+  const double Apow_uniform = uniform ? pow(flow_factor(P, 0.0, enh), e1) : 0.0;      // the same for every layer
   double eta[NZA];
 #pragma unroll
   for (int l = 0; l < NZA; l++) {
     if (l < nz) {
       F.du_dz_3D_a[(size_t)l * nV + vi] = duz[l];
       F.dv_dz_3D_a[(size_t)l * nV + vi] = dvz[l];
-      const double A = flow_factor(P, (P.rheology == UFE_RHEO_UNIFORM) ? 0.0 : I.Ti[(size_t)l * nV + vi], enh);
+      const double Apow = uniform ? Apow_uniform : pow(flow_factor(P, I.Ti[(size_t)l * nV + vi], enh), e1);
       const double eps_sq = du_dx * du_dx + dv_dy * dv_dy + du_dx * dv_dy +
                             0.25 * ((du_dy + dv_dx) * (du_dy + dv_dx)) +
                             0.25 * (duz[l] * duz[l] + dvz[l] * dvz[l]) + P.eps_sq_0;
-      double e = 0.5 * pow(A, e1) * pow(eps_sq, e2);
+      double e = 0.5 * Apow * pow(eps_sq, e2);
       e = fmin(fmax(e, P.visc_eff_min), P.eta_max);
       eta[l] = e;
       F.eta_3D_a[(size_t)l * nV + vi] = e;
@@ -196,30 +232,35 @@ k_vertex_diva(int v0, int nv, int nV, int nTri, int nz_rt, ClosureParams P, DevF
   for (int l = 0; l < NZA - 1; l++)
     if (l < nz - 1) eta_vav = eta_vav + 0.5 * (eta[l + 1] + eta[l]) * (P.zeta[l + 1] - P.zeta[l]);
   const double Hi = I.Hi[vi];
-  F.N_a[vi] = eta_vav * fmax((double)0.1f, Hi);      // max(0.1, Hi): default-real literal, DIVA_main.f90:468
+  double *ra = F.rec_a + (size_t)vi * F.RA;
+  const double N_a = eta_vav * fmax((double)0.1f, Hi);      // max(0.1, Hi): default-real literal, DIVA_main.f90:468
+  F.N_a[vi] = N_a;
   // F-integrals (DIVA_main.f90:481-520; integrate_from_zeta_is_one_to_zeta_is_zetap)
   const double Hd = -fmax(0.1, Hi);
   double i1 = 0.0, i2 = 0.0, F2_surf = 0.0;
-  F.F1_3D_a[(size_t)(nz - 1) * nV + vi] = Hd * i1;
-  F.F2_3D_a[(size_t)(nz - 1) * nV + vi] = Hd * i2;
+  ra[4 + 3 * (nz - 1)] = eta[nz - 1]; ra[5 + 3 * (nz - 1)] = Hd * i1; ra[6 + 3 * (nz - 1)] = Hd * i2;
   if (nz == 1) F2_surf = Hd * i2;
+  // the integrands zeta / eta and zeta^2 / eta of a layer enter two trapezoids: each quotient is evaluated once
+  double f1a = P.zeta[nz - 1] / eta[nz - 1], f2a = (P.zeta[nz - 1] * P.zeta[nz - 1]) / eta[nz - 1];
 #pragma unroll
   for (int l = NZA - 2; l >= 0; l--) {
     if (l < nz - 1) {
       const double dz = P.zeta[l + 1] - P.zeta[l];
-      const double f1a = P.zeta[l + 1] / eta[l + 1], f1b = P.zeta[l] / eta[l];
-      const double f2a = (P.zeta[l + 1] * P.zeta[l + 1]) / eta[l + 1], f2b = (P.zeta[l] * P.zeta[l]) / eta[l];
+      const double f1b = P.zeta[l] / eta[l];
+      const double f2b = (P.zeta[l] * P.zeta[l]) / eta[l];
       i1 = i1 - 0.5 * (f1a + f1b) * dz;
       i2 = i2 - 0.5 * (f2a + f2b) * dz;
-      F.F1_3D_a[(size_t)l * nV + vi] = Hd * i1;
-      F.F2_3D_a[(size_t)l * nV + vi] = Hd * i2;
+      f1a = f1b; f2a = f2b;
+      ra[4 + 3 * l] = eta[l]; ra[5 + 3 * l] = Hd * i1; ra[6 + 3 * l] = Hd * i2;
       if (l == 0) F2_surf = Hd * i2;
     }
   }
   // basal friction (sliding_laws.f90:25-81) and beta_eff (DIVA_main.f90:538-550)
   const double beta = sliding_beta(P, I, vi, u_a, v_a, I.V[vi], I.V[(size_t)nV + vi]);
+  const double beta_eff = (P.sliding_law == UFE_SLID_NO_SLIDING) ? 1.0 / F2_surf : beta / (1.0 + beta * F2_surf);
   F.beta_a[vi] = beta;
-  F.beta_eff_a[vi] = (P.sliding_law == UFE_SLID_NO_SLIDING) ? 1.0 / F2_surf : beta / (1.0 + beta * F2_surf);
+  F.beta_eff_a[vi] = beta_eff;
+  ra[0] = N_a; ra[1] = beta; ra[2] = beta_eff; ra[3] = 0.0;
 }
 
 // rows with more than three entries (singular three-point fit -> widened neighbourhood): accumulate per layer.
@@ -235,16 +276,17 @@ __device__ __noinline__ void k_triangle_diva_general(int tl, int ti, int nV, int
   for (int k = ab.ptr[tl] - 1; k < ab.ptr[tl + 1] - 1; k++) {
     const int vj = ab.ind[k] - 1;
     const double wm = ab.v0[k], wx = ab.v1[k], wy = ab.v2[k];
-    const double Na = F.N_a[vj];
+    const double *ra = F.rec_a + (size_t)vj * F.RA;
+    const double Na = ra[0];
     N_b += wm * Na; dNx += wx * Na; dNy += wy * Na;
-    beta_b += wm * F.beta_a[vj];
-    beta_eff_b += wm * F.beta_eff_a[vj];
+    beta_b += wm * ra[1];
+    beta_eff_b += wm * ra[2];
 #pragma unroll 1
     for (int l = 0; l < NZA; l++) {
       if (l < nz) {
-        eb[l] += wm * F.eta_3D_a[(size_t)l * nV + vj];
-        f1[l] += wm * F.F1_3D_a[(size_t)l * nV + vj];
-        f2[l] += wm * F.F2_3D_a[(size_t)l * nV + vj];
+        eb[l] += wm * ra[4 + 3 * l];
+        f1[l] += wm * ra[5 + 3 * l];
+        f2[l] += wm * ra[6 + 3 * l];
       }
     }
   }
@@ -279,30 +321,48 @@ k_triangle_diva(int t0, int nt, int nV, int nTri, int nz_rt, ClosureParams P, De
     // kernel runs at twice the occupancy.  Same summation order as the general path: ((0 + w0 f0) + w1 f1) + w2 f2.
     const int v0 = ab.ind[k0] - 1, v1 = ab.ind[k0 + 1] - 1, v2 = ab.ind[k0 + 2] - 1;
     const double w0 = ab.v0[k0], w1 = ab.v0[k0 + 1], w2 = ab.v0[k0 + 2];
+    const double *r0 = F.rec_a + (size_t)v0 * F.RA, *r1 = F.rec_a + (size_t)v1 * F.RA, *r2 = F.rec_a + (size_t)v2 * F.RA;
     {
       const double x0 = ab.v1[k0], x1 = ab.v1[k0 + 1], x2 = ab.v1[k0 + 2];
       const double y0 = ab.v2[k0], y1 = ab.v2[k0 + 1], y2 = ab.v2[k0 + 2];
-      const double N0 = F.N_a[v0], N1 = F.N_a[v1], N2 = F.N_a[v2];
+      const double N0 = r0[0], N1 = r1[0], N2 = r2[0];
       double N_b = 0.0, dNx = 0.0, dNy = 0.0, beta_b = 0.0, beta_eff_b = 0.0;
       N_b += w0 * N0; N_b += w1 * N1; N_b += w2 * N2;
       dNx += x0 * N0; dNx += x1 * N1; dNx += x2 * N2;
       dNy += y0 * N0; dNy += y1 * N1; dNy += y2 * N2;
-      beta_b += w0 * F.beta_a[v0]; beta_b += w1 * F.beta_a[v1]; beta_b += w2 * F.beta_a[v2];
-      beta_eff_b += w0 * F.beta_eff_a[v0]; beta_eff_b += w1 * F.beta_eff_a[v1]; beta_eff_b += w2 * F.beta_eff_a[v2];
+      beta_b += w0 * r0[1]; beta_b += w1 * r1[1]; beta_b += w2 * r2[1];
+      beta_eff_b += w0 * r0[2]; beta_eff_b += w1 * r1[2]; beta_eff_b += w2 * r2[2];
       if (P.do_GL_subgrid_friction) beta_eff_b = beta_eff_b * pow(fraction_gr_b[ti], P.subgrid_exponent);
       F.N_b[ti] = N_b; F.dN_dx_b[ti] = dNx; F.dN_dy_b[ti] = dNy;
       F.beta_b[ti] = beta_b; F.beta_eff_b[ti] = beta_eff_b;
     }
-#pragma unroll 4
-    for (int l = 0; l < nz; l++) {
-      const size_t o = (size_t)l * nV;
-      const double e0 = F.eta_3D_a[o + v0], e1 = F.eta_3D_a[o + v1], e2 = F.eta_3D_a[o + v2];
-      const double a0 = F.F1_3D_a[o + v0], a1 = F.F1_3D_a[o + v1], a2 = F.F1_3D_a[o + v2];
-      const double b0 = F.F2_3D_a[o + v0], b1 = F.F2_3D_a[o + v1], b2 = F.F2_3D_a[o + v2];
+    // two layers = six doubles = three 16-byte loads per record
+    const double2 *q0 = reinterpret_cast<const double2 *>(r0 + 4), *q1 = reinterpret_cast<const double2 *>(r1 + 4), *q2 = reinterpret_cast<const double2 *>(r2 + 4);
+#pragma unroll 2
+    for (int l = 0; l + 1 < nz; l += 2) {
+      const int o = 3 * (l >> 1);
+      const double2 A0 = q0[o], B0 = q0[o + 1], C0 = q0[o + 2];      // (eta_l, F1_l) (F2_l, eta_l+1) (F1_l+1, F2_l+1)
+      const double2 A1 = q1[o], B1 = q1[o + 1], C1 = q1[o + 2];
+      const double2 A2 = q2[o], B2 = q2[o + 1], C2 = q2[o + 2];
       double e = 0.0, a = 0.0, b = 0.0;
-      e += w0 * e0; e += w1 * e1; e += w2 * e2;
-      a += w0 * a0; a += w1 * a1; a += w2 * a2;
-      b += w0 * b0; b += w1 * b1; b += w2 * b2;
+      e += w0 * A0.x; e += w1 * A1.x; e += w2 * A2.x;
+      a += w0 * A0.y; a += w1 * A1.y; a += w2 * A2.y;
+      b += w0 * B0.x; b += w1 * B1.x; b += w2 * B2.x;
+      size_t ob = (size_t)l * nTri + ti;
+      F.eta_3D_b[ob] = e; F.F1_3D_b[ob] = a; F.F2_3D_b[ob] = b;
+      e = 0.0; a = 0.0; b = 0.0;
+      e += w0 * B0.y; e += w1 * B1.y; e += w2 * B2.y;
+      a += w0 * C0.x; a += w1 * C1.x; a += w2 * C2.x;
+      b += w0 * C0.y; b += w1 * C1.y; b += w2 * C2.y;
+      ob += nTri;
+      F.eta_3D_b[ob] = e; F.F1_3D_b[ob] = a; F.F2_3D_b[ob] = b;
+    }
+    if (nz & 1) {
+      const int l = nz - 1, o = 4 + 3 * l;
+      double e = 0.0, a = 0.0, b = 0.0;
+      e += w0 * r0[o]; e += w1 * r1[o]; e += w2 * r2[o];
+      a += w0 * r0[o + 1]; a += w1 * r1[o + 1]; a += w2 * r2[o + 1];
+      b += w0 * r0[o + 2]; b += w1 * r1[o + 2]; b += w2 * r2[o + 2];
       const size_t ob = (size_t)l * nTri + ti;
       F.eta_3D_b[ob] = e; F.F1_3D_b[ob] = a; F.F2_3D_b[ob] = b;
     }
@@ -483,6 +543,16 @@ int ufe_launch_till(cudaStream_t st, int nV, const ClosureParams &P, const doubl
   UFE_LAUNCH_CHECK();
   return UFE_OK;
 }
+int ufe_launch_pack_b(cudaStream_t st, int t0, int nt, int nTri, int nz, const ClosureParams &P, const DivaFields &F) {
+  if (nt <= 0) return UFE_OK;
+  const size_t smem = (size_t)128 * F.RB * sizeof(double);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) { UFE_CUDA(cudaFuncSetAttribute(k_pack_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+  k_pack_b<<<ufe_div_up(nt, 128), 128, smem, st>>>(t0, nt, nTri, nz, P, F);
+  UFE_LAUNCH_CHECK();
+  return UFE_OK;
+}
+
 int ufe_launch_vertex(cudaStream_t st, int is_diva, int v0, int nv, int nV, int nTri, int nz,
                       const ClosureParams &P, DevFamilyView ba, const VertexInputs &I, const DivaFields &F) {
   if (nv <= 0) return UFE_OK;

@@ -31,9 +31,15 @@ struct VertexInputs {
 struct DivaFields {
   double *u_vav_b, *v_vav_b, *u_base_b, *v_base_b, *tau_bx_b, *tau_by_b, *eta_3D_b, *u_3D_b, *v_3D_b;
   double *du_dx_a, *du_dy_a, *dv_dx_a, *dv_dy_a, *du_dz_3D_a, *dv_dz_3D_a, *eta_3D_a, *N_a;
-  double *F1_3D_a, *F2_3D_a, *beta_a, *beta_eff_a;
+  double *beta_a, *beta_eff_a;
   double *N_b, *dN_dx_b, *dN_dy_b, *F1_3D_b, *F2_3D_b, *beta_b, *beta_eff_b, *tau_dx_b, *tau_dy_b;
   double *u_b_prev, *v_b_prev;
+  // DIVA gather records (one contiguous, sector-aligned record per triangle / vertex instead of nz strided layers: a
+  // gather touches whole 32-byte sectors, and a halo is ONE contiguous message per peer and stage):
+  //   rec_b [nTri][RB]: u_vav, v_vav, u_base, v_base, then per layer (du/dz, dv/dz) = tau_b zeta / max(eta_min, eta_3D_b)
+  //   rec_a [nV][RA]:   N_a, beta_a, beta_eff_a, 0, then per layer (eta, F1, F2)
+  double *rec_b, *rec_a;
+  int RB, RA;
 };
 
 // outputs of calc_secondary_velocities (full-length device arrays)
@@ -51,6 +57,7 @@ int ufe_launch_driving_stress(cudaStream_t st, int t0, int nt, DevFamilyView ab,
                               const double *Hs, double *tdx, double *tdy);
 int ufe_launch_till(cudaStream_t st, int nV, const ClosureParams &P, const double *Neff, const double *phi,
                     const int *mask_land, const int *mask_gr, const int *C, const int *nC, double *tys);
+int ufe_launch_pack_b(cudaStream_t st, int t0, int nt, int nTri, int nz, const ClosureParams &P, const DivaFields &F);
 int ufe_launch_vertex(cudaStream_t st, int is_diva, int v0, int nv, int nV, int nTri, int nz,
                       const ClosureParams &P, DevFamilyView ba, const VertexInputs &I, const DivaFields &F);
 int ufe_launch_triangle(cudaStream_t st, int is_diva, int t0, int nt, int nV, int nTri, int nz,

@@ -191,7 +191,9 @@ static AssemblyParams make_asm_params(const ufe_handle *h) {
 static int validate_config(const ufe_config *c) {
   for (int s = 0; s < 4; s++) {
     if (c->BC_u[s] < 1 || c->BC_u[s] > 4) { ufe_set_error("unknown choice_BC_u (code %d)!", c->BC_u[s]); return UFE_ERR_INVALID; }
-    if (c->BC_v[s] < 1 || c->BC_v[s] > 4) { ufe_set_error("unknown choice_BC_v (code %d)!", c->BC_v[s]); return UFE_ERR_INVALID; }
+    // solve_linearised_SSA_DIVA.f90:586-637 has no 'infinite_SSA_icestream' case for v: the reference crashes there
+    if (c->BC_v[s] == UFE_BC_INFINITE_SSA_ICESTREAM) { ufe_set_error("unknown choice_BC_v \"infinite_SSA_icestream\"!"); return UFE_ERR_INVALID; }
+    if (c->BC_v[s] < 1 || c->BC_v[s] > 3) { ufe_set_error("unknown choice_BC_v (code %d)!", c->BC_v[s]); return UFE_ERR_INVALID; }
   }
   if (c->choice_sliding_law < 0 || c->choice_sliding_law > 7) { ufe_set_error("unknown choice_sliding_law (code %d)", c->choice_sliding_law); return UFE_ERR_INVALID; }
   if (c->choice_sliding_law == UFE_SLID_IDEALISED &&
@@ -336,9 +338,11 @@ static int alloc_fields(ufe_handle *h) {
       {&F.eta_3D_b, nT * nz}, {&F.u_3D_b, nT * nz}, {&F.v_3D_b, nT * nz},
       {&F.du_dx_a, nV}, {&F.du_dy_a, nV}, {&F.dv_dx_a, nV}, {&F.dv_dy_a, nV},
       {&F.du_dz_3D_a, nV * nz}, {&F.dv_dz_3D_a, nV * nz}, {&F.eta_3D_a, nV * nz}, {&F.N_a, nV},
-      {&F.F1_3D_a, nV * nz}, {&F.F2_3D_a, nV * nz}, {&F.beta_a, nV}, {&F.beta_eff_a, nV},
+      {&F.beta_a, nV}, {&F.beta_eff_a, nV},
       {&F.N_b, nT}, {&F.dN_dx_b, nT}, {&F.dN_dy_b, nT}, {&F.F1_3D_b, nT * nz}, {&F.F2_3D_b, nT * nz},
-      {&F.beta_b, nT}, {&F.beta_eff_b, nT}, {&F.tau_dx_b, nT}, {&F.tau_dy_b, nT}, {&F.u_b_prev, nT}, {&F.v_b_prev, nT}};
+      {&F.beta_b, nT}, {&F.beta_eff_b, nT}, {&F.tau_dx_b, nT}, {&F.tau_dy_b, nT}, {&F.u_b_prev, nT}, {&F.v_b_prev, nT},
+      {&F.rec_b, nT * (size_t)((4 + 2 * nz + 3) / 4 * 4)}, {&F.rec_a, nV * (size_t)((4 + 3 * nz + 3) / 4 * 4)}};
+  F.RB = (int)((4 + 2 * nz + 3) / 4 * 4); F.RA = (int)((4 + 3 * nz + 3) / 4 * 4);
   for (auto &e : list) { UFE_TRY(dalloc(e.p, e.n)); h->owned_ptrs.push_back(*e.p); }
   UFE_TRY(dalloc(&h->Hi, nV)); UFE_TRY(dalloc(&h->Hs, nV)); UFE_TRY(dalloc(&h->Hib, nV)); UFE_TRY(dalloc(&h->SL, nV));
   UFE_TRY(dalloc(&h->fraction_gr, nV)); UFE_TRY(dalloc(&h->fraction_gr_b, nT)); UFE_TRY(dalloc(&h->Neff, nV));
@@ -824,26 +828,20 @@ static int picard_resident(ufe_handle *h, int is_diva, ufe_solve_info *info) {
   while (!converged) {
     it++;
     cudaEventRecord(h->ev[5], h->st);
-    if (multi) {
+    if (is_diva) {
+      // b-grid gather records of the owned triangles (velocities + du/dz, dv/dz per layer), then ONE halo message per peer
+      UFE_TRY(ufe_launch_pack_b(h->st, t0, nt, nTri, nz, P, F));
+      if (multi) UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, F.rec_b, 0, 1, F.RB));
+    } else if (multi) {
       UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, F.u_vav_b, 0, 1, 1));
       UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, F.v_vav_b, 0, 1, 1));
-      if (is_diva) {
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, F.u_base_b, 0, 1, 1));
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, F.v_base_b, 0, 1, 1));
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, F.tau_bx_b, 0, 1, 1));
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, F.tau_by_b, 0, 1, 1));
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_b_for_a, F.eta_3D_b, nTri, nz, 1));
-      }
     }
     UFE_TRY(ufe_launch_vertex(h->st, is_diva, v0, nv, nV, nTri, nz, P, view_of(h->fam[1]), VI, F));
     if (multi) {
-      UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.N_a, 0, 1, 1));
-      UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.beta_a, 0, 1, 1));
-      if (is_diva) {
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.beta_eff_a, 0, 1, 1));
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.eta_3D_a, nV, nz, 1));
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.F1_3D_a, nV, nz, 1));
-        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.F2_3D_a, nV, nz, 1));
+      if (is_diva) UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.rec_a, 0, 1, F.RA));   // N, beta, beta_eff, (eta, F1, F2) per layer
+      else {
+        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.N_a, 0, 1, 1));
+        UFE_TRY(ufe_halo_exchange(h->st, h->comm, h->plan_a_for_b, F.beta_a, 0, 1, 1));
       }
     }
     UFE_TRY(ufe_launch_triangle(h->st, is_diva, t0, nt, nV, nTri, nz, P, view_of(h->fam[0]), h->fraction_gr_b, F));
@@ -983,7 +981,10 @@ extern "C" int ufe_ssa_diva_linearised(ufe_handle *h, double *u_b, double *v_b, 
                                        const double *tau_dy_b, double *u_b_prev, double *v_b_prev, double rtol,
                                        double abstol, int32_t *n_Axb_its, const int32_t *bc_mask, const double *bc_u,
                                        const double *bc_v) {
-  if (!h || !u_b || !v_b || !N_b) { ufe_set_error("null argument"); return UFE_ERR_INVALID; }
+  if (!h || !u_b || !v_b || !N_b || !dN_dx_b || !dN_dy_b || !beta_b || !tau_dx_b || !tau_dy_b) {
+    ufe_set_error("null argument: every array of solve_SSA_DIVA_linearised is required"); return UFE_ERR_INVALID;
+  }
+  if (bc_mask && (!bc_u || !bc_v)) { ufe_set_error("BC_prescr_mask_b given without BC_prescr_u_b / BC_prescr_v_b"); return UFE_ERR_INVALID; }
   UFE_CUDA(cudaSetDevice(h->device));
   const size_t nT = h->dm.nTri;
   DivaFields &F = h->F;

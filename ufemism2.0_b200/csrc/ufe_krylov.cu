@@ -157,10 +157,18 @@ __global__ void k_gm_sethcol(const KrylovScalars *sc, double *gm, const double *
 // partial sums in dots_local for the all-reduce (multi GPU)
 // Bounded spin on a flag another GPU writes: a rank that died must not hang the others' GPUs.
 // ~2^26 polls of a local volatile word (tens of seconds); returns false on time-out.
+// time-out in wall time (%globaltimer, ns), not in polls: 20 s without the peer's flag means the peer is gone
 __device__ __forceinline__ bool peer_wait(const volatile int *flag, int epoch) {
-  for (long long spins = 0; spins < (1LL << 26); spins++)
+  unsigned long long t0 = 0;
+  for (long long spins = 0;; spins++) {
     if (*flag >= epoch) return true;
-  return false;
+    if ((spins & 1023) == 1023) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ULL) return false;
+    }
+  }
 }
 
 // `single`:  > 0 one rank: finish the stage here;  == 0 several ranks over NCCL: leave the local
@@ -925,6 +933,10 @@ int ufe_krylov_run(cudaStream_t st, const DevSystem &S, KrylovWork &kw, const Co
                    PcLU *pc) {
   if (maxits <= 0) maxits = 10000;
   int fl = 0;
+  if (kw.sc_host->reason == -9) {      // an earlier solve on this workspace timed out on a peer: blocks that started after
+    UFE_CUDA(cudaMemsetAsync(kw.counter, 0, sizeof(unsigned), st));    // the time-out left the block counter mid-count
+    kw.sc_host->reason = 0;
+  }
   static const bool rich_off = getenv("UFE_RICHARDSON_FIRST") && atoi(getenv("UFE_RICHARDSON_FIRST")) == 0;
   bool solved = false;
   if (pc && !guess_nonzero && !rich_off && ufe_pclu_exact_and_fresh(pc)) {

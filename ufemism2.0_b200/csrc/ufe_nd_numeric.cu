@@ -89,7 +89,7 @@ struct ufe_nd_solver {
   double flops = 0.0;
   bool factored = false;
   int premul_pair = 1;                       // preconditioner mode: the right-hand side is multiplied by the 2x2 (1) or 1x1 (0) diagonal blocks
-  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384;      // levels with at most this many (large) fronts use the cluster sweeps
+  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384, upd_big = 1;      // levels with at most this many (large) fronts use the cluster sweeps
   MfGraph g_factor, g_apply[6];
 };
 
@@ -819,6 +819,7 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
   if (const char *e = getenv("UFE_ND_K64")) S->k64 = atoi(e);
   if (const char *e = getenv("UFE_ND_CLUSTER_FRONTS")) S->cl_max_fronts = atoi(e);
   if (const char *e = getenv("UFE_ND_CLUSTER_MING")) S->cl_min_g = atoi(e);
+  if (const char *e = getenv("UFE_ND_UPD_BIG")) S->upd_big = atoi(e);
   if (nranks > 1) S->use_graphs = 0;
   S->lev.resize(nl);
   // local fronts, level-major, p descending inside a level
@@ -1070,7 +1071,7 @@ static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *d
       b += nkb;
       if (trail <= 0) continue;
       const long long big_ctas = (long long)((trail + 127) / 128) * ((trail + 127) / 128) * n_upd;
-      if (trail >= 192 && big_ctas >= 120) {
+      if (S->upd_big && trail >= 192 && big_ctas >= 120) {
         const int t = (trail + 127) / 128;
         k_mf_update<16><<<dim3(t, t, n_upd), 256, MF_UPD_SMEM(128), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
       } else {
