@@ -405,6 +405,10 @@ int ufe_nd_tree_info(const ufe_nd_tree *T, int32_t *n_nodes, int32_t *n_levels, 
 int ufe_nd_tree_node(const ufe_nd_tree *T, int32_t i, int32_t *level, int32_t *parent, int32_t *n_sep, int32_t *n_bnd,
                      const int32_t **sep, const int32_t **bnd, const int32_t **up);
 int ufe_nd_tree_entry_map(const ufe_nd_tree *T, const int32_t **node, const int32_t **row, const int32_t **col);
+/* distribution of the tree over nranks (1, 2, 4, 8, ...) ranks: owner[i] = rank that factorises node i (post-order index as
+ * in ufe_nd_tree_node); rank r owns the sub-tree below the r-th node of level log2(nranks) and the nodes above it on
+ * its left spine -- the tree analogue of the reference's strip partition (mesh_parallelisation.f90:90-127) */
+int ufe_nd_tree_owners(const ufe_nd_tree *T, int32_t nranks, int32_t *owner);
 void ufe_nd_tree_free(ufe_nd_tree *T);
 
 /* Numeric phase on the device (csrc/ufe_nd_numeric.cu): exact solve of A x = b, the system the reference hands to

@@ -402,3 +402,45 @@ def test_nd_analyse_rejects_bad_arguments():
         nd.analyse(gc, np.array([0, 1, 2, 3], dtype=np.int32), np.array([0, 1, 7], dtype=np.int32), 4)     # column out of range
     with pytest.raises(UfeError):
         nd.analyse(gc, np.array([0, 1, 2, 3], dtype=np.int32), np.array([0, 1, 2], dtype=np.int32), 0)     # leaf size < 1
+
+
+def test_nd_tree_distribution_over_ranks():
+    """Host logic of the multi-rank multifrontal solver (ufe_nd_tree_owners): rank r owns the sub-tree below the r-th node
+    of level log2(P) and the left spine above it, every rank gets about 1/P of the triangles, and every parent-child pair
+    on different ranks is a (left spine, child 1) pair -- the only place a Schur complement crosses ranks."""
+    import scipy.sparse as sp
+    from ufemism2_0_b200 import nd
+    mesh, C, ice = experiments.MISMIPplus(4e3)
+    nT = mesh.nTri
+    Tri = np.asarray(mesh.Tri) - 1
+    Pm = sp.csr_matrix((np.ones(3 * nT), (np.repeat(np.arange(nT), 3), Tri.ravel())), shape=(nT, mesh.nV))
+    B = (Pm @ Pm.T).tocsr(); B.sort_indices()
+    T = nd.analyse(np.asarray(mesh.TriGC), B.indptr.astype(np.int32), B.indices.astype(np.int32), 48, nranks=(1, 2, 4, 8))
+    nn = len(T.nodes)
+    children = [[] for _ in range(nn)]
+    for i, q in enumerate(T.nodes):
+        if q.parent >= 0:
+            children[q.parent].append(i)
+    assert np.all(T.owners[1] == 0)
+    for P in (2, 4, 8):
+        own = T.owners[P]
+        Ld = P.bit_length() - 1
+        assert own.min() == 0 and own.max() == P - 1
+        assert own[nn - 1] == 0                                     # the root (last in post-order) is rank 0's
+        cut = [i for i, q in enumerate(T.nodes) if q.level == Ld]
+        assert sorted(own[cut]) == list(range(P))                    # one sub-tree root per rank at level log2(P)
+        crossings = 0
+        for i, q in enumerate(T.nodes):
+            if q.level > Ld:
+                assert own[i] == own[q.parent]                       # below the cut a sub-tree stays on its rank
+            elif q.parent >= 0 and own[i] != own[q.parent]:
+                crossings += 1
+                assert children[q.parent].index(i) == 1 and own[i] > own[q.parent]
+        assert crossings == P - 1                                    # log2(P) exchange rounds, P - 1 links in all
+        tri_per_rank = np.zeros(P)
+        for i, q in enumerate(T.nodes):
+            tri_per_rank[own[i]] += q.sep.size
+        assert tri_per_rank.sum() == nT
+        assert tri_per_rank.max() < 1.35 * nT / P, tri_per_rank      # coordinate bisection balances the sub-trees
+    with pytest.raises(capi.UfeError, match="power of two"):
+        nd.analyse(np.asarray(mesh.TriGC), B.indptr.astype(np.int32), B.indices.astype(np.int32), 48, nranks=(3,))

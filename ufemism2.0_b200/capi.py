@@ -138,7 +138,7 @@ EXPORTS = [
     "ufe_mesh_apply_operator", "ufe_get_stiffness_csr", "ufe_bench_spmv", "ufe_get_ownership",
     "ufe_mesh_set_edges", "ufe_calc_dHi_dt", "ufe_calc_dHi_dt_explicit", "ufe_calc_dHi_dt_semiimplicit", "ufe_get_thickness_csr",
     "ufe_get_thickness_timing", "ufe_calc_vertical_velocities", "ufe_mesh_get_operator_a_a",
-    "ufe_nd_analyse", "ufe_nd_tree_info", "ufe_nd_tree_node", "ufe_nd_tree_entry_map", "ufe_nd_tree_free",
+    "ufe_nd_analyse", "ufe_nd_tree_info", "ufe_nd_tree_node", "ufe_nd_tree_entry_map", "ufe_nd_tree_owners", "ufe_nd_tree_free",
     "ufe_solve_matrix_equation_CSR", "ufe_last_l0_preconditioner",
     "ufe_nd_solver_create", "ufe_nd_solver_factor", "ufe_nd_solver_solve", "ufe_nd_solver_info", "ufe_nd_solver_free",
 ]

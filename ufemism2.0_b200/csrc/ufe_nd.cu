@@ -216,4 +216,29 @@ extern "C" int ufe_nd_tree_entry_map(const ufe_nd_tree *T, const int32_t **node,
   return UFE_OK;
 }
 
+// Owner rank of every tree node when the factorisation is distributed over `nranks` (a power of two) ranks: the
+// sub-tree below the r-th node of level log2(nranks) belongs to rank r, the nodes above it to the left spine of their
+// sub-tree (root: rank 0; level 1: ranks 0, nranks / 2; ...).  owner: n_nodes entries, post-order like ufe_nd_tree_node.
+int ufe_nd_owner_map(const ufe_nd_tree *T, int nranks, std::vector<int> &owner, std::vector<int> &span) {
+  const int nn = (int)T->nodes.size();
+  if (nranks < 1 || (nranks & (nranks - 1)) != 0) { ufe_set_error("nd_lu: the number of ranks must be a power of two (got %d)", nranks); return UFE_ERR_INVALID; }
+  owner.assign(nn, 0); span.assign(nn, 1);
+  for (int q = nn - 1; q >= 0; q--) {            // post-order: parents have larger indices than their children
+    const NdNode &nd = T->nodes[q];
+    if (nd.parent < 0) { owner[q] = 0; span[q] = nranks; }
+    if (nd.child[0] < 0) { if (span[q] > 1) { ufe_set_error("nd_lu: the elimination tree is too shallow for %d ranks", nranks); return UFE_ERR_INVALID; } continue; }
+    const int half = span[q] / 2;
+    owner[nd.child[0]] = owner[q]; span[nd.child[0]] = std::max(1, half);
+    owner[nd.child[1]] = owner[q] + half; span[nd.child[1]] = std::max(1, half);
+  }
+  return UFE_OK;
+}
+extern "C" int ufe_nd_tree_owners(const ufe_nd_tree *T, int32_t nranks, int32_t *owner) {
+  if (!T || !owner) { ufe_set_error("ufe_nd_tree_owners: null argument"); return UFE_ERR_INVALID; }
+  std::vector<int> o, sp;
+  UFE_TRY(ufe_nd_owner_map(T, nranks, o, sp));
+  for (size_t q = 0; q < o.size(); q++) owner[q] = o[q];
+  return UFE_OK;
+}
+
 extern "C" void ufe_nd_tree_free(ufe_nd_tree *T) { delete T; }

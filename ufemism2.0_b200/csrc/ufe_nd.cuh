@@ -17,3 +17,6 @@ struct ufe_nd_tree {
   std::vector<int> bptr, bind;        // the analysed block pattern (the numeric phase looks scalar entries up in it)
 };
 
+
+// owner rank / number of ranks below every node for a factorisation distributed over nranks ranks (ufe_nd.cu)
+int ufe_nd_owner_map(const ufe_nd_tree *T, int nranks, std::vector<int> &owner, std::vector<int> &span);

@@ -34,10 +34,12 @@ class NdTree:
     entry_node: np.ndarray
     entry_row: np.ndarray
     entry_col: np.ndarray
+    owners: dict = None
 
 
-def analyse(centroids: np.ndarray, bptr: np.ndarray, bind: np.ndarray, leaf_triangles: int = 96) -> NdTree:
-    """centroids: (nT,2); bptr / bind: 0-based block CSR pattern over triangles."""
+def analyse(centroids: np.ndarray, bptr: np.ndarray, bind: np.ndarray, leaf_triangles: int = 96, nranks=()) -> NdTree:
+    """centroids: (nT,2); bptr / bind: 0-based block CSR pattern over triangles.  nranks: rank counts for which the
+    owner of every node is also returned (tree.owners[n] = array over the nodes)."""
     nT = centroids.shape[0]
     x = np.ascontiguousarray(centroids[:, 0], dtype=np.float64)
     y = np.ascontiguousarray(centroids[:, 1], dtype=np.float64)
@@ -62,6 +64,11 @@ def analyse(centroids: np.ndarray, bptr: np.ndarray, bind: np.ndarray, leaf_tria
         nnzb = int(bptr[-1])
         tree = NdTree(nodes, nl.value, mf.value, pb.value, np.ctypeslib.as_array(en, shape=(nnzb,)).copy(),
                       np.ctypeslib.as_array(er, shape=(nnzb,)).copy(), np.ctypeslib.as_array(ec, shape=(nnzb,)).copy())
+        tree.owners = {}
+        for n in nranks:
+            o = np.zeros(nn.value, dtype=np.int32)
+            check(lib.ufe_nd_tree_owners(T, int(n), vp(o)))
+            tree.owners[int(n)] = o
     finally:
         lib.ufe_nd_tree_free.restype = None
         lib.ufe_nd_tree_free(T)
