@@ -125,6 +125,8 @@ struct ufe_handle {
   PcLU *pclu = nullptr;                        // UFE_PC_BJACOBI_LU workspace (tied to the cached pattern)
   int pc_used = -1;                            // resolved preconditioner for the cached pattern (-1 = undecided)
   int pc_used_l0 = -1;                         // ... of the last ufe_solve_matrix_equation_CSR call
+  double *op_x = nullptr, *op_y = nullptr;     // staging buffers of ufe_mesh_apply_operator, grown on demand and kept
+  size_t op_x_n = 0, op_y_n = 0;
   int pc_age = -1, pc_last_its = 0;            // bjacobi_lu reuse: solves since the last factorisation (-1 = never), its of the last solve
   int64_t pc_factorisations = 0;
   // reductions for the Picard residual
@@ -389,7 +391,7 @@ extern "C" int ufe_diva_destroy(ufe_handle *h) {
     cudaFree(h->fam[f].ptr); cudaFree(h->fam[f].ind);
     for (int q = 0; q < 5; q++) cudaFree(h->fam[f].val[q]);
   }
-  cudaFree(h->red_counter); cudaFree(h->flush_buf);
+  cudaFree(h->red_counter); cudaFree(h->flush_buf); cudaFree(h->op_x); cudaFree(h->op_y);
   if (h->red_host) cudaFreeHost(h->red_host);
   if (h->sec_alloc) { double **sp = reinterpret_cast<double **>(&h->sec); for (size_t i = 0; i < sizeof(SecondaryFields) / sizeof(double *); i++) cudaFree(sp[i]); }
   ufe_krylov_free(h->kw);
@@ -1083,16 +1085,16 @@ extern "C" int ufe_mesh_apply_operator(ufe_handle *h, int32_t family, int32_t wh
   if (family < 0 || family > 2 || which < 0 || which >= h->fam[family].nval) { ufe_set_error("bad operator id"); return UFE_ERR_INVALID; }
   UFE_CUDA(cudaSetDevice(h->device));
   const DevFamily &F = h->fam[family];
-  double *dx = nullptr, *dy = nullptr;
-  UFE_TRY(dupload(&dx, x, (size_t)F.n * nlayers));
-  UFE_TRY(dalloc(&dy, (size_t)F.m * nlayers));
-  int rc = ufe_spmv_launch(h->st, F.m_loc, F.nnz, F.ptr, F.ind, F.val[which], dx, F.n, dy + (F.i1 - 1), F.m, nlayers);
-  if (rc == UFE_OK) {
-    if (cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)F.m * nlayers, cudaMemcpyDeviceToHost, h->st) != cudaSuccess ||
-        cudaStreamSynchronize(h->st) != cudaSuccess) { ufe_set_error("apply_operator copy failed"); rc = UFE_ERR_CUDA; }
-  }
-  cudaFree(dx); cudaFree(dy);
-  return rc;
+  if (!x || !y || nlayers < 1) { ufe_set_error("apply_operator: null argument"); return UFE_ERR_INVALID; }
+  const size_t nx = (size_t)F.n * nlayers, ny = (size_t)F.m * nlayers;
+  if (nx > h->op_x_n) { cudaFree(h->op_x); h->op_x = nullptr; h->op_x_n = 0; UFE_TRY(dalloc(&h->op_x, nx)); h->op_x_n = nx; }
+  if (ny > h->op_y_n) { cudaFree(h->op_y); h->op_y = nullptr; h->op_y_n = 0; UFE_TRY(dalloc(&h->op_y, ny)); h->op_y_n = ny; }
+  UFE_CUDA(cudaMemcpyAsync(h->op_x, x, sizeof(double) * nx, cudaMemcpyHostToDevice, h->st));
+  UFE_CUDA(cudaMemsetAsync(h->op_y, 0, sizeof(double) * ny, h->st));
+  UFE_TRY(ufe_spmv_launch(h->st, F.m_loc, F.nnz, F.ptr, F.ind, F.val[which], h->op_x, F.n, h->op_y + (F.i1 - 1), F.m, nlayers));
+  if (cudaMemcpyAsync(y, h->op_y, sizeof(double) * ny, cudaMemcpyDeviceToHost, h->st) != cudaSuccess ||
+      cudaStreamSynchronize(h->st) != cudaSuccess) { ufe_set_error("apply_operator copy failed"); return UFE_ERR_CUDA; }
+  return UFE_OK;
 }
 
 extern "C" int ufe_get_stiffness_csr(ufe_handle *h, int32_t *m_loc, int32_t *nnz, int32_t *ptr, int32_t *ind, double *val,
