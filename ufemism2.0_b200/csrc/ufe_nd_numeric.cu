@@ -230,9 +230,9 @@ __device__ __forceinline__ void mf_inv32_cta(double (&a)[4], int lane, int w, do
         }
         a[t] = isP ? 1.0 : -m;                        // the inverse's column takes the place of column p
       }
-      __syncthreads();
-    } else {
-      __syncthreads();
+    }
+    __syncthreads();                                  // one barrier for the whole block, outside the divergent branches
+    if (w != g) {
 #pragma unroll
       for (int t = 0; t < 4; t++) {
         const double m = sc.m[par][t][lane];
