@@ -41,6 +41,8 @@
 struct MfStep { int n_active, max_trail; };
 struct MfLevel {
   int n = 0, first = 0, steps = 0, maxG = 0, n_internal = 0, max_nb = 0;
+  int pmax = 0;                  // largest pivot count of the level
+  bool late_schur = false;       // many pivots: the steps leave F22 alone, one K = p pass at the end (k_mf_update modes 1, 2)
   std::vector<MfStep> step;
 };
 // one NCCL exchange between a child-1 front (owned by `peer_child`) and its parent (owned by `peer_parent`)
@@ -89,7 +91,7 @@ struct ufe_nd_solver {
   double flops = 0.0;
   bool factored = false;
   int premul_pair = 1;                       // preconditioner mode: the right-hand side is multiplied by the 2x2 (1) or 1x1 (0) diagonal blocks
-  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384, upd_big = 1, upd_nq = 0;      // levels with at most this many (large) fronts use the cluster sweeps
+  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384, upd_big = 1, upd_nq = 0, schur_min_p = 256, upd_mma = 1, upd_mma_min_mode = 2;      // levels with at most this many (large) fronts use the cluster sweeps
   MfGraph g_factor, g_apply[6];
 };
 
@@ -400,39 +402,53 @@ __device__ __forceinline__ void mf_cp_async16(double *dst, const double *src, bo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n));
 }
 
-template <int TG, int NQ>
+// mode 0: the update of a step as described above.
+// Fronts with many pivots (mode 1 + mode 2): the Schur complement F22 (rows and columns >= p) is NOT touched by the
+// steps -- mode 1 updates only the L-shaped rest of the trailing matrix, i.e. the pivot square and the boundary panels,
+// entries of F22 inside a straddling tile are masked -- and is updated ONCE at the end, mode 2:  F22 -= L21 U12  with
+// K = p, the pivot blocks streamed through the same two buffers in pairs.  One pass over F22 instead of p / 64, and the
+// prologue / epilogue of a tile are amortised over K = p instead of 64.
+template <int TG, int NQ, bool LATE>      // LATE = false: mode 0 only (the compiler drops the masks and the K loop)
 __global__ void __launch_bounds__(TG * TG, (TG == 16 ? 1 : 2) * (NQ == 2 ? 2 : 1))
-k_mf_update(int first, int b, int nkb, const int *__restrict__ G_, const int *__restrict__ ld_, const long long *__restrict__ foff,
-            double *__restrict__ F) {
+k_mf_update(int first, int b, int nkb, int mode_rt, const int *__restrict__ p_, const int *__restrict__ G_, const int *__restrict__ ld_,
+            const long long *__restrict__ foff, double *__restrict__ F) {
   // tile TR x TC, TG x TG threads, 8 x (2 NQ) per thread (NQ = 4: 8 x 8, 208 registers; NQ = 2: 8 x 4, twice the warps per SM)
   constexpr int TR = 8 * TG, TC = 2 * NQ * TG, NT = TG * TG, BUFA = TR * (MFB + 1) + MFB * TC;    // doubles per pivot-block buffer (even)
+  const int mode = LATE ? mode_rt : 0;
   const int f = first + blockIdx.z;
   const int G = G_[f], ld = ld_[f];
-  const int r0 = (b + nkb) * MFB;
+  const int p = mode ? p_[f] : 0;
+  const int kb_begin = mode == 2 ? 0 : b, kb_end = mode == 2 ? p / MFB : b + nkb;
+  const int r0 = mode == 2 ? p : (b + nkb) * MFB;
   const int i0 = r0 + blockIdx.y * TR, j0 = r0 + blockIdx.x * TC;
   if (i0 >= G || j0 >= G) return;
+  if (mode == 1 && i0 >= p && j0 >= p) return;       // a tile of F22: left to the final pass
   double *A = F + foff[f];
   extern __shared__ __align__(16) double mf_sm[];
   const int t = threadIdx.x;
   const int tx = t % TG, ty = t / TG;
-  for (int kk = 0; kk < nkb; kk++) {
-    const int kb = b + kk;
-    double *sLb = mf_sm + kk * BUFA;                 // [TR][33]
-    double *sUb = sLb + TR * (MFB + 1);              // [32][TC], 16-byte aligned: TR * 33 is even
+  // both operand tiles of a pair of pivot blocks are fetched with cp.async up front (one buffer per pivot block)
+  auto fetch = [&](int kb0, int nk) {
+    for (int kk = 0; kk < nk; kk++) {
+      const int kb = kb0 + kk;
+      double *sLb = mf_sm + kk * BUFA;                 // [TR][33]
+      double *sUb = sLb + TR * (MFB + 1);              // [32][TC], 16-byte aligned: TR * 33 is even
 #pragma unroll 4
-    for (int q = t; q < TR * MFB; q += NT) {
-      const int row = q >> 5, k = q & 31;
-      const bool ok = i0 + row < G;
-      mf_cp_async8(sLb + row * (MFB + 1) + k, ok ? A + (size_t)(i0 + row) * ld + kb * MFB + k : A, ok);
-    }
+      for (int q = t; q < TR * MFB; q += NT) {
+        const int row = q >> 5, k = q & 31;
+        const bool ok = i0 + row < G;
+        mf_cp_async8(sLb + row * (MFB + 1) + k, ok ? A + (size_t)(i0 + row) * ld + kb * MFB + k : A, ok);
+      }
 #pragma unroll 4
-    for (int q = t; q < MFB * (TC / 2); q += NT) {
-      const int k = q / (TC / 2), c = 2 * (q % (TC / 2));
-      const bool ok = j0 + c < G;
-      mf_cp_async16(sUb + k * TC + c, ok ? A + (size_t)(kb * MFB + k) * ld + j0 + c : A, ok);
+      for (int q = t; q < MFB * (TC / 2); q += NT) {
+        const int k = q / (TC / 2), c = 2 * (q % (TC / 2));
+        const bool ok = j0 + c < G;
+        mf_cp_async16(sUb + k * TC + c, ok ? A + (size_t)(kb * MFB + k) * ld + j0 + c : A, ok);
+      }
+      asm volatile("cp.async.commit_group;");
     }
-    asm volatile("cp.async.commit_group;");
-  }
+  };
+  fetch(kb_begin, min(2, kb_end - kb_begin));
   // L2 prefetch of this thread's share of the A tile (128-byte lines; TR rows x TC / 16 lines)
   for (int q = t; q < TR * (TC / 16); q += NT) {
     const int row = q / (TC / 16), c = 16 * (q % (TC / 16));
@@ -440,40 +456,46 @@ k_mf_update(int first, int b, int nkb, const int *__restrict__ G_, const int *__
   }
   double acc[8][2 * NQ];
 #pragma unroll
-  for (int p = 0; p < 8; p++)
+  for (int pp = 0; pp < 8; pp++)
 #pragma unroll
-    for (int q = 0; q < 2 * NQ; q++) acc[p][q] = 0.0;
-  for (int kk = 0; kk < nkb; kk++) {
-    if (kk == 0 && nkb == 2) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
-    __syncthreads();
-    const double *sLb = mf_sm + kk * BUFA;
-    const double *sUb = sLb + TR * (MFB + 1);
+    for (int q = 0; q < 2 * NQ; q++) acc[pp][q] = 0.0;
+  for (int kb0 = kb_begin; kb0 < kb_end; kb0 += 2) {
+    const int nk = min(2, kb_end - kb0);
+    if (kb0 > kb_begin) { __syncthreads(); fetch(kb0, nk); }     // the buffers are free again
+    for (int kk = 0; kk < nk; kk++) {
+      if (kk == 0 && nk == 2) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
+      __syncthreads();
+      const double *sLb = mf_sm + kk * BUFA;
+      const double *sUb = sLb + TR * (MFB + 1);
 #pragma unroll 2
-    for (int k = 0; k < MFB; k++) {
-      double a[8], u[2 * NQ];
+      for (int k = 0; k < MFB; k++) {
+        double a[8], u[2 * NQ];
 #pragma unroll
-      for (int p = 0; p < 4; p++) { a[2 * p] = sLb[(2 * ty + 2 * TG * p) * (MFB + 1) + k]; a[2 * p + 1] = sLb[(2 * ty + 2 * TG * p + 1) * (MFB + 1) + k]; }
+        for (int pp = 0; pp < 4; pp++) { a[2 * pp] = sLb[(2 * ty + 2 * TG * pp) * (MFB + 1) + k]; a[2 * pp + 1] = sLb[(2 * ty + 2 * TG * pp + 1) * (MFB + 1) + k]; }
 #pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        const double2 v = *reinterpret_cast<const double2 *>(sUb + k * TC + 2 * tx + 2 * TG * q);
-        u[2 * q] = v.x; u[2 * q + 1] = v.y;
+        for (int q = 0; q < NQ; q++) {
+          const double2 v = *reinterpret_cast<const double2 *>(sUb + k * TC + 2 * tx + 2 * TG * q);
+          u[2 * q] = v.x; u[2 * q + 1] = v.y;
+        }
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++)
+#pragma unroll
+          for (int q = 0; q < 2 * NQ; q++) acc[pp][q] += a[pp] * u[q];
       }
-#pragma unroll
-      for (int p = 0; p < 8; p++)
-#pragma unroll
-        for (int q = 0; q < 2 * NQ; q++) acc[p][q] += a[p] * u[q];
     }
   }
 #pragma unroll
   for (int pp = 0; pp < 4; pp++) {                   // two rows (2 NQ x 16 bytes) per batch
     double2 v[2][NQ];
+    bool on[2][NQ];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int i = i0 + 2 * ty + 2 * TG * pp + h;
 #pragma unroll
       for (int q = 0; q < NQ; q++) {
         const int j = j0 + 2 * tx + 2 * TG * q;
-        v[h][q] = (i < G && j < G) ? *reinterpret_cast<const double2 *>(A + (size_t)i * ld + j) : make_double2(0.0, 0.0);
+        on[h][q] = i < G && j < G && !(mode == 1 && i >= p && j >= p);
+        v[h][q] = on[h][q] ? *reinterpret_cast<const double2 *>(A + (size_t)i * ld + j) : make_double2(0.0, 0.0);
       }
     }
 #pragma unroll
@@ -482,12 +504,113 @@ k_mf_update(int first, int b, int nkb, const int *__restrict__ G_, const int *__
 #pragma unroll
       for (int q = 0; q < NQ; q++) {
         const int j = j0 + 2 * tx + 2 * TG * q;
-        if (i < G && j < G) {
+        if (on[h][q]) {
           double2 w = v[h][q];
           w.x -= acc[2 * pp + h][2 * q]; w.y -= acc[2 * pp + h][2 * q + 1];
           *reinterpret_cast<double2 *>(A + (size_t)i * ld + j) = w;
         }
       }
+    }
+  }
+}
+
+// The same update on the fp64 TENSOR cores for large trailing matrices: mma.sync.m8n8k4.f64 (DMMA; tcgen05 has no fp64
+// path, so this is the tensor-core instruction for this precision -- measured 37.0 TFLOP/s on the B200 against 33.7 for
+// DFMA, tools/micro/).  One DMMA is 256 FMA per warp instruction: 8 x fewer issue slots and 6 x fewer shared-memory
+// operand loads per flop than the 8 x 4 SIMT micro-tile, whose limiter is the shared-memory pipe (ncu: "Shared is the
+// highest-utilized pipeline").  128 x 128 tile, 8 warps as 2 x 4, warp tile 64 x 32 = 8 x 4 m8n8 tiles (128 accumulator
+// registers); operand strides 36 / 132 doubles make the fragment loads of a half-warp hit 16 distinct bank pairs.
+#define MMA_LS 36
+#define MMA_US 132
+#define MF_MMA_SMEM (2 * (128 * MMA_LS + MFB * MMA_US) * sizeof(double))
+__device__ __forceinline__ void mf_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_mf_update_mma(int first, int b, int nkb, int mode, const int *__restrict__ p_, const int *__restrict__ G_, const int *__restrict__ ld_,
+                const long long *__restrict__ foff, double *__restrict__ F) {
+  constexpr int T = 128, NT = 256, BUFA = T * MMA_LS + MFB * MMA_US;
+  const int f = first + blockIdx.z;
+  const int G = G_[f], ld = ld_[f];
+  const int p = mode ? p_[f] : 0;
+  const int kb_begin = mode == 2 ? 0 : b, kb_end = mode == 2 ? p / MFB : b + nkb;
+  const int r0 = mode == 2 ? p : (b + nkb) * MFB;
+  const int i0 = r0 + blockIdx.y * T, j0 = r0 + blockIdx.x * T;
+  if (i0 >= G || j0 >= G) return;
+  if (mode == 1 && i0 >= p && j0 >= p) return;       // a tile of F22: left to the final pass
+  double *A = F + foff[f];
+  extern __shared__ __align__(16) double mf_sm[];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int wrow = 64 * (w >> 2), wcol = 32 * (w & 3), g = lane >> 2, tg = lane & 3;
+  auto fetch = [&](int kb0, int nk) {
+    for (int kk = 0; kk < nk; kk++) {
+      const int kb = kb0 + kk;
+      double *sLb = mf_sm + kk * BUFA;                 // [128][MMA_LS]
+      double *sUb = sLb + T * MMA_LS;                  // [32][MMA_US]
+#pragma unroll 4
+      for (int q = t; q < T * (MFB / 2); q += NT) {
+        const int row = q / (MFB / 2), c = 2 * (q % (MFB / 2));
+        const bool ok = i0 + row < G;
+        mf_cp_async16(sLb + row * MMA_LS + c, ok ? A + (size_t)(i0 + row) * ld + kb * MFB + c : A, ok);
+      }
+#pragma unroll 4
+      for (int q = t; q < MFB * (T / 2); q += NT) {
+        const int k = q / (T / 2), c = 2 * (q % (T / 2));
+        const bool ok = j0 + c < G;
+        mf_cp_async16(sUb + k * MMA_US + c, ok ? A + (size_t)(kb * MFB + k) * ld + j0 + c : A, ok);
+      }
+      asm volatile("cp.async.commit_group;");
+    }
+  };
+  fetch(kb_begin, min(2, kb_end - kb_begin));
+  for (int q = t; q < T * (T / 16); q += NT) {        // L2 prefetch of the A tile
+    const int row = q / (T / 16), c = 16 * (q % (T / 16));
+    if (i0 + row < G && j0 + c < G) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(i0 + row) * ld + j0 + c));
+  }
+  double acc[8][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+  for (int kb0 = kb_begin; kb0 < kb_end; kb0 += 2) {
+    const int nk = min(2, kb_end - kb0);
+    if (kb0 > kb_begin) { __syncthreads(); fetch(kb0, nk); }     // the buffers are free again
+    for (int kk = 0; kk < nk; kk++) {
+      if (kk == 0 && nk == 2) asm volatile("cp.async.wait_group 1;"); else asm volatile("cp.async.wait_group 0;");
+      __syncthreads();
+      const double *sLb = mf_sm + kk * BUFA + (wrow + g) * MMA_LS + tg;
+      const double *sUb = mf_sm + kk * BUFA + T * MMA_LS + tg * MMA_US + wcol + g;
+#pragma unroll 2
+      for (int k0 = 0; k0 < MFB; k0 += 4) {
+        double a[8], u[4];
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++) a[mt] = sLb[mt * 8 * MMA_LS + k0];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) u[nt] = sUb[k0 * MMA_US + 8 * nt];
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) mf_dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], u[nt]);
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 8; mt++) {
+    const int i = i0 + wrow + 8 * mt + g;
+    double2 v[4];
+    bool on[4];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const int j = j0 + wcol + 8 * nt + 2 * tg;
+      on[nt] = i < G && j < G && !(mode == 1 && i >= p && j >= p);
+      v[nt] = on[nt] ? *reinterpret_cast<const double2 *>(A + (size_t)i * ld + j) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      if (!on[nt]) continue;
+      const int j = j0 + wcol + 8 * nt + 2 * tg;
+      *reinterpret_cast<double2 *>(A + (size_t)i * ld + j) = make_double2(v[nt].x - acc[mt][nt][0], v[nt].y - acc[mt][nt][1]);
     }
   }
 }
@@ -811,6 +934,9 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
   if (const char *e = getenv("UFE_ND_CLUSTER_MING")) S->cl_min_g = atoi(e);
   if (const char *e = getenv("UFE_ND_UPD_BIG")) S->upd_big = atoi(e);
   if (const char *e = getenv("UFE_ND_UPD_NQ")) S->upd_nq = atoi(e);
+  if (const char *e = getenv("UFE_ND_SCHUR_MIN_P")) S->schur_min_p = atoi(e);
+  if (const char *e = getenv("UFE_ND_UPD_MMA")) S->upd_mma = atoi(e);
+  if (const char *e = getenv("UFE_ND_UPD_MMA_MIN_MODE")) S->upd_mma_min_mode = atoi(e);
   if (nranks > 1) S->use_graphs = 0;
   S->lev.resize(nl);
   // local fronts, level-major, p descending inside a level
@@ -908,8 +1034,10 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
     for (int z = 0; z < Lv.n; z++) {
       const int f = Lv.first + z;
       Lv.steps = std::max(Lv.steps, p[f] / MFB); Lv.maxG = std::max(Lv.maxG, G[f]); Lv.max_nb = std::max(Lv.max_nb, nb[f]);
+      Lv.pmax = std::max(Lv.pmax, p[f]);
       if (cf[0][f] >= 0 || cf[1][f] >= 0) Lv.n_internal++;
     }
+    Lv.late_schur = S->schur_min_p > 0 && Lv.pmax >= S->schur_min_p && Lv.max_nb > 0;
     Lv.step.resize(Lv.steps);
     for (int b = 0; b < Lv.steps; b++) {
       MfStep st{0, 0};
@@ -978,10 +1106,15 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
       cudaEventCreate(&S->e1) != cudaSuccess) { ufe_set_error("ufe_nd_solver_create: stream / event creation failed"); return fail(UFE_ERR_CUDA); }
   static bool attr_set = false;
   if (!attr_set) {
-    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(128, 128))));
-    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(128, 64))));
-    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(64, 64))));
-    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(64, 32))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(128, 128))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(128, 128))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(128, 64))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(128, 64))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(64, 64))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(64, 64))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(64, 32))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_UPD_SMEM(64, 32))));
+    UFE_CUDA(cudaFuncSetAttribute(k_mf_update_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MF_MMA_SMEM));
     UFE_CUDA(cudaFuncSetAttribute(k_mf_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     UFE_CUDA(cudaFuncSetAttribute(k_mf_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     UFE_CUDA(cudaFuncSetAttribute(k_mf_fwd_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1007,6 +1140,31 @@ extern "C" int ufe_nd_solver_create(const ufe_nd_tree *T, int32_t N, const int32
 // ------------------------------------------------------------------------------------------------------------------
 // launch sequences
 // ------------------------------------------------------------------------------------------------------------------
+// trailing-update launch: extent = largest trailing (mode 0, 1) or boundary (mode 2) extent of the n fronts
+static int mf_launch_update(ufe_nd_solver *S, cudaStream_t st, const MfLevel &L, bool big, int nq, int extent, int n, int b, int nkb, int mode) {
+  // large trailing matrices: 128 x 64 tiles, 8 x 4 per thread, two CTAs (16 warps) per SM -- 6 % faster at 1 M vertices
+  // than 128 x 128 / 8 x 8 with one CTA per SM; small ones: 64 x 64 tiles of 64 threads (8 x 8 per thread)
+  if (big && S->upd_mma && mode >= S->upd_mma_min_mode) {      // fp64 tensor cores, 128 x 128 tiles
+    k_mf_update_mma<<<dim3((extent + 127) / 128, (extent + 127) / 128, n), 256, MF_MMA_SMEM, st>>>(L.first, b, nkb, mode, S->p, S->G, S->ld, S->foff, S->F);
+    UFE_LAUNCH_CHECK();
+    return UFE_OK;
+  }
+  const int TR = big ? 128 : 64, TC = (big ? 128 : 64) / (nq == 2 ? 2 : 1);
+  const dim3 grid((extent + TC - 1) / TC, (extent + TR - 1) / TR, n);
+#define MF_UPD_LAUNCH(TG_, NQ_, NT_, TR_, TC_)                                                                                      \
+  do {                                                                                                                             \
+    if (mode) k_mf_update<TG_, NQ_, true><<<grid, NT_, MF_UPD_SMEM(TR_, TC_), st>>>(L.first, b, nkb, mode, S->p, S->G, S->ld, S->foff, S->F); \
+    else k_mf_update<TG_, NQ_, false><<<grid, NT_, MF_UPD_SMEM(TR_, TC_), st>>>(L.first, b, nkb, 0, S->p, S->G, S->ld, S->foff, S->F);       \
+  } while (0)
+  if (big && nq == 2) MF_UPD_LAUNCH(16, 2, 256, 128, 64);
+  else if (big) MF_UPD_LAUNCH(16, 4, 256, 128, 128);
+  else if (nq == 2) MF_UPD_LAUNCH(8, 2, 64, 64, 32);
+  else MF_UPD_LAUNCH(8, 4, 64, 64, 64);
+#undef MF_UPD_LAUNCH
+  UFE_LAUNCH_CHECK();
+  return UFE_OK;
+}
+
 static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *dval) {
   const int N = S->N, tb = 256, nf = S->n_fronts;
   k_mf_scale<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dself, S->dpair); UFE_LAUNCH_CHECK();
@@ -1068,13 +1226,12 @@ static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *d
       // large trailing matrices: 128 x 64 tiles, 8 x 4 per thread, two CTAs (16 warps) per SM -- 6 % faster at 1 M vertices
       // than 128 x 128 / 8 x 8 with one CTA per SM; small ones: 64 x 64 tiles of 64 threads (8 x 8 per thread)
       const int nq = S->upd_nq ? S->upd_nq : (big ? 2 : 4);
-      const int TR = big ? 128 : 64, TC = (big ? 128 : 64) / (nq == 2 ? 2 : 1);
-      const dim3 grid((trail + TC - 1) / TC, (trail + TR - 1) / TR, n_upd);
-      if (big && nq == 2) k_mf_update<16, 2><<<grid, 256, MF_UPD_SMEM(128, 64), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
-      else if (big) k_mf_update<16, 4><<<grid, 256, MF_UPD_SMEM(128, 128), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
-      else if (nq == 2) k_mf_update<8, 2><<<grid, 64, MF_UPD_SMEM(64, 32), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
-      else k_mf_update<8, 4><<<grid, 64, MF_UPD_SMEM(64, 64), st>>>(L.first, b - nkb, nkb, S->G, S->ld, S->foff, S->F);
-      UFE_LAUNCH_CHECK();
+      UFE_TRY(mf_launch_update(S, st, L, big, nq, trail, n_upd, b - nkb, nkb, L.late_schur ? 1 : 0));
+    }
+    if (L.late_schur) {        // F22 -= L21 U12, one pass with K = p
+      const long long big_ctas = (long long)((L.max_nb + 127) / 128) * ((L.max_nb + 127) / 128) * L.n;
+      const bool big = S->upd_big && L.max_nb >= 192 && big_ctas >= 120;
+      UFE_TRY(mf_launch_update(S, st, L, big, S->upd_nq ? S->upd_nq : (big ? 2 : 4), L.max_nb, L.n, 0, 0, 2));
     }
   }
   return UFE_OK;
