@@ -629,6 +629,39 @@ def test_nd_multifrontal_solver_matches_sparse_LU(workload, leaf):
         sol.close()
 
 
+@pytest.mark.parametrize("late_schur_from, tensor_cores", [("256", "1"), ("64", "1"), ("64", "0"), ("0", "1")])
+def test_nd_factorisation_variants_agree(monkeypatch, late_schur_from, tensor_cores):
+    """The organisation of the trailing updates is a performance choice, not a numerical one: right-looking K = 64 passes,
+    the late Schur-complement pass with K = p (UFE_ND_SCHUR_MIN_P), fp64 SIMT or fp64 tensor cores (UFE_ND_UPD_MMA) give
+    the sparse-LU solution of a wide-mesh stiffness system (fronts of up to ~900 unknowns, pivot counts above 256)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from ufemism2_0_b200 import nd
+    mesh, C, ice = experiments.antarctic(20000)
+    C.visc_it_nit, C.b200_krylov_pc = 1, "nd_lu"
+    S = diva.initialise_DIVA_solver(mesh, C)
+    try:
+        S.solve_DIVA(ice)
+        A, bb = S.get_stiffness_matrix()
+    finally:
+        S.close()
+    N = 2 * mesh.nTri
+    M = sp.csr_matrix((A.val, (A.ind - 1).astype(np.int32), (A.ptr - 1).astype(np.int32)), shape=(N, N))
+    xr = spla.splu(M.tocsc()).solve(bb)
+    monkeypatch.setenv("UFE_ND_SCHUR_MIN_P", late_schur_from)
+    monkeypatch.setenv("UFE_ND_UPD_MMA", tensor_cores)
+    sol = nd.Solver(np.asarray(mesh.TriGC), A.ptr, A.ind, 64)
+    try:
+        assert sol.info()["max_front"] > 512
+        sol.factor(A.val)
+        x0, r0 = sol.solve(bb, n_refine=0)
+        x1, r1 = sol.solve(bb, n_refine=2)
+        assert r0 < 1e-10 and r1 < 1e-13, (r0, r1)
+        assert np.abs(x1 - xr).max() <= 1e-9 * np.abs(xr).max()
+    finally:
+        sol.close()
+
+
 @pytest.mark.parametrize("workload, method, lag", [("mismipplus_8km", "bicgstab", 0), ("mismipplus_8km", "gmres", 20),
                                                    ("ismip_hom_c", "bicgstab", 0)])
 def test_DIVA_with_nd_lu_preconditioner(oracle, workload, method, lag):
