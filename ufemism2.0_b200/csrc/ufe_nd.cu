@@ -14,9 +14,14 @@
 #include "ufe_internal.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <future>
 #include <numeric>
 
 #include "ufe_nd.cuh"
+
+using ufe_nd_host::host_threads;
+using ufe_nd_host::parallel_for;
 
 namespace {
 
@@ -33,13 +38,18 @@ Graph symmetrise(int nT, const int *bptr, const int *bind) {
     for (int k = bptr[i]; k < bptr[i + 1]; k++) { const int j = bind[k]; if (j != i) { ind[fill[i]++] = j; ind[fill[j]++] = i; } }
   Graph G;
   G.ptr.assign(nT + 1, 0);
-  for (int i = 0; i < nT; i++) {
-    std::sort(ind.begin() + ptr[i], ind.begin() + ptr[i + 1]);
-    const int n = (int)(std::unique(ind.begin() + ptr[i], ind.begin() + ptr[i + 1]) - (ind.begin() + ptr[i]));
-    G.ptr[i + 1] = G.ptr[i] + n;
-  }
+  std::vector<int> len(nT);
+  parallel_for(nT, [&](int i0, int i1) {
+    for (int i = i0; i < i1; i++) {
+      std::sort(ind.begin() + ptr[i], ind.begin() + ptr[i + 1]);
+      len[i] = (int)(std::unique(ind.begin() + ptr[i], ind.begin() + ptr[i + 1]) - (ind.begin() + ptr[i]));
+    }
+  });
+  for (int i = 0; i < nT; i++) G.ptr[i + 1] = G.ptr[i] + len[i];
   G.ind.resize(G.ptr[nT]);
-  for (int i = 0; i < nT; i++) std::copy(ind.begin() + ptr[i], ind.begin() + ptr[i] + (G.ptr[i + 1] - G.ptr[i]), G.ind.begin() + G.ptr[i]);
+  parallel_for(nT, [&](int i0, int i1) {
+    for (int i = i0; i < i1; i++) std::copy(ind.begin() + ptr[i], ind.begin() + ptr[i] + len[i], G.ind.begin() + G.ptr[i]);
+  });
   return G;
 }
 
@@ -48,9 +58,10 @@ struct Builder {
   const Graph &G;
   int leaf;
   std::vector<NdNode> &nodes;
-  std::vector<char> mark;             // scratch flags (nT)
+  std::vector<char> &mark;            // scratch flags (nT), shared: the recursion touches the flags of its own triangles only
+  int par_levels;                     // the two halves of a cut run concurrently above this level
 
-  // returns the index of the created node (children are created first => post-order)
+  // appends the sub-tree of `idx` to `nodes` in post-order and returns the index of its root
   int dissect(std::vector<int> &idx, int level) {
     const int n = (int)idx.size();
     auto make_leaf = [&]() {
@@ -78,8 +89,24 @@ struct Builder {
     for (int t : left) { if (mark[t] == 1) rest.push_back(t); mark[t] = 0; }
     std::sort(sep.begin(), sep.end());
     idx.clear(); idx.shrink_to_fit();
-    const int c0 = dissect(rest, level + 1);
-    const int c1 = dissect(right, level + 1);
+    int c0, c1;
+    if (level < par_levels && n > 8 * leaf) {
+      // child 1 is built into a private vector by another thread and appended behind child 0's sub-tree
+      std::vector<NdNode> other;
+      Builder B1{x, y, G, leaf, other, mark, par_levels};
+      auto fut = std::async(std::launch::async, [&] { return B1.dissect(right, level + 1); });
+      c0 = dissect(rest, level + 1);
+      const int r1 = fut.get(), off = (int)nodes.size();
+      for (NdNode &o : other) {
+        if (o.parent >= 0) o.parent += off;
+        for (int &c : o.child) if (c >= 0) c += off;
+        nodes.push_back(std::move(o));
+      }
+      c1 = r1 + off;
+    } else {
+      c0 = dissect(rest, level + 1);
+      c1 = dissect(right, level + 1);
+    }
     NdNode nd; nd.level = level; nd.sep = std::move(sep); nd.child[0] = c0; nd.child[1] = c1;
     nodes.push_back(std::move(nd));
     const int me = (int)nodes.size() - 1;
@@ -105,7 +132,9 @@ extern "C" int ufe_nd_analyse(int32_t nT, const double *centroid_x, const double
   const Graph G = symmetrise(nT, bptr, bind);
   {
     std::vector<char> mark(nT, 0);
-    Builder B{centroid_x, centroid_y, G, leaf_triangles, T->nodes, std::move(mark)};
+    int par_levels = 0;
+    while ((1 << par_levels) < host_threads()) par_levels++;
+    Builder B{centroid_x, centroid_y, G, leaf_triangles, T->nodes, mark, par_levels};
     std::vector<int> all(nT);
     std::iota(all.begin(), all.end(), 0);
     B.dissect(all, 0);
@@ -153,7 +182,9 @@ extern "C" int ufe_nd_analyse(int32_t nT, const double *centroid_x, const double
   // assembly map: block entry (i,j) belongs to the front of whichever of i, j is eliminated first
   const int nnzb = bptr[nT];
   T->entry_node.resize(nnzb); T->entry_row.resize(nnzb); T->entry_col.resize(nnzb);
-  for (int i = 0; i < nT; i++) {
+  std::atomic<int> bad_i{-1}, bad_j{-1};
+  parallel_for(nT, [&](int i0, int i1) {
+  for (int i = i0; i < i1; i++) {
     for (int k = bptr[i]; k < bptr[i + 1]; k++) {
       const int j = bind[k];
       const int q = std::min(T->node_of[i], T->node_of[j]);      // post-order index: smaller = eliminated earlier
@@ -165,10 +196,12 @@ extern "C" int ufe_nd_analyse(int32_t nT, const double *centroid_x, const double
         return (it != nd.bnd.end() && *it == t) ? ns + (int)(it - nd.bnd.begin()) : -1;
       };
       const int r = where(i), c = where(j);
-      if (r < 0 || c < 0) { ufe_set_error("ufe_nd_analyse: entry (%d,%d) outside its front", i, j); delete T; return UFE_ERR_INVALID; }
+      if (r < 0 || c < 0) { bad_i = i; bad_j = j; return; }
       T->entry_node[k] = q; T->entry_row[k] = r; T->entry_col[k] = c;
     }
   }
+  });
+  if (bad_i >= 0) { ufe_set_error("ufe_nd_analyse: entry (%d,%d) outside its front", bad_i.load(), bad_j.load()); delete T; return UFE_ERR_INVALID; }
   *out = T;
   return UFE_OK;
 }

@@ -1,5 +1,8 @@
 // Elimination tree of the nested-dissection analysis (ufe_nd.cu), shared with the numeric phase (ufe_nd_numeric.cu).
 #pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 struct NdNode {
@@ -20,3 +23,21 @@ struct ufe_nd_tree {
 
 // owner rank / number of ranks below every node for a factorisation distributed over nranks ranks (ufe_nd.cu)
 int ufe_nd_owner_map(const ufe_nd_tree *T, int nranks, std::vector<int> &owner, std::vector<int> &span);
+
+// host threads for the once-per-mesh analysis (4 M unknowns: seconds of sorting and searching otherwise)
+namespace ufe_nd_host {
+inline int host_threads() {
+  static const int n = [] {
+    if (const char *e = getenv("UFE_ND_HOST_THREADS")) return std::max(1, atoi(e));
+    return (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  }();
+  return n;
+}
+template <class Fn> void parallel_for(int n, Fn fn) {           // fn(begin, end) on contiguous chunks
+  const int nt = std::min(host_threads(), std::max(1, n / 4096));
+  if (nt <= 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  for (int q = 0; q < nt; q++) th.emplace_back([=] { fn((int)((long long)n * q / nt), (int)((long long)n * (q + 1) / nt)); });
+  for (auto &t : th) t.join();
+}
+}  // namespace ufe_nd_host

@@ -32,6 +32,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <atomic>
 #include <numeric>
 
 #define MFB 32    // pivot block width
@@ -1058,7 +1059,9 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
   }
   // destination of every scalar entry: its block entry's front and position there (-1: a front of another rank)
   std::vector<long long> dst(S->nnz);
-  for (int i = 0; i < N; i++) {
+  std::atomic<int> bad_i{-1}, bad_j{-1};
+  ufe_nd_host::parallel_for(N, [&](int ia, int ib) {
+  for (int i = ia; i < ib; i++) {
     const int bi = i >> 1;
     for (int k = ptr[i] - 1; k < ptr[i + 1] - 1; k++) {
       const int j = ind[k] - 1, bj = j >> 1;
@@ -1069,7 +1072,7 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
         if (it != hi && *it == bj) e = (int)(it - T->bind.data());
         else for (int t = T->bptr[bi]; t < T->bptr[bi + 1]; t++) if (T->bind[t] == bj) { e = t; break; }   // unsorted block rows
       }
-      if (e < 0) { ufe_set_error("ufe_nd_solver_create: entry (%d,%d) is not in the analysed block pattern", i + 1, j + 1); delete S; return UFE_ERR_INVALID; }
+      if (e < 0) { bad_i = i; bad_j = j; return; }
       const int q = T->entry_node[e];
       if (owner[q] != rank) { dst[k] = -1; continue; }
       const int f = lid[q];
@@ -1079,6 +1082,8 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
       dst[k] = foff[f] + (long long)row * ld[f] + col;
     }
   }
+  });
+  if (bad_i >= 0) { ufe_set_error("ufe_nd_solver_create: entry (%d,%d) is not in the analysed block pattern", bad_i + 1, bad_j + 1); delete S; return UFE_ERR_INVALID; }
   int rc = UFE_OK;
   auto fail = [&](int c) { ufe_nd_solver_free(S); return c; };
   if ((rc = mf_upload(&S->ns, ns)) || (rc = mf_upload(&S->p, p)) || (rc = mf_upload(&S->nb, nb)) || (rc = mf_upload(&S->G, G)) ||
