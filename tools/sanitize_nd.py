@@ -20,4 +20,17 @@ for name, (mesh, C, ice), nit in (("MISMIP+ 8km", experiments.MISMIPplus(8e3), 2
         print(name, meth, lag, info.n_visc_its, info.n_Axb_its, info.flags, info.krylov_pc_used, "L0", its, fl, used,
               float(np.abs(S.u_vav_b).max()), flush=True)
         S.close()
+# the large-front kernels on a small mesh: late Schur pass from 64 pivots, 128-wide tiles (SIMT and tensor cores) for every level
+os.environ["UFE_ND_SCHUR_MIN_P"] = "64"
+os.environ["UFE_ND_BIG_MIN_CTAS"] = "1"
+for mma, min_mode in (("1", "0"), ("0", "2")):
+    os.environ["UFE_ND_UPD_MMA"], os.environ["UFE_ND_UPD_MMA_MIN_MODE"] = mma, min_mode
+    mesh, C, ice = experiments.antarctic(6000)
+    C2 = copy.copy(C)
+    C2.visc_it_nit, C2.b200_krylov_pc = 2, "nd_lu"
+    S = diva.initialise_DIVA_solver(mesh, C2)
+    info = S.solve_DIVA(ice)
+    print("Antarctic 6e3 large-front kernels, tensor cores", mma, info.n_visc_its, info.n_Axb_its, info.flags, info.krylov_pc_used,
+          float(np.abs(S.u_vav_b).max()), flush=True)
+    S.close()
 print("SANITIZE_RUN_DONE")

@@ -92,7 +92,7 @@ struct ufe_nd_solver {
   double flops = 0.0;
   bool factored = false;
   int premul_pair = 1;                       // preconditioner mode: the right-hand side is multiplied by the 2x2 (1) or 1x1 (0) diagonal blocks
-  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384, upd_big = 1, upd_nq = 0, schur_min_p = 256, upd_mma = 1, upd_mma_min_mode = 2;      // levels with at most this many (large) fronts use the cluster sweeps
+  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384, upd_big = 1, upd_nq = 0, schur_min_p = 256, upd_mma = 1, upd_mma_min_mode = 2, big_min_ctas = 120;      // levels with at most this many (large) fronts use the cluster sweeps
   MfGraph g_factor, g_apply[6];
 };
 
@@ -938,6 +938,7 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
   if (const char *e = getenv("UFE_ND_SCHUR_MIN_P")) S->schur_min_p = atoi(e);
   if (const char *e = getenv("UFE_ND_UPD_MMA")) S->upd_mma = atoi(e);
   if (const char *e = getenv("UFE_ND_UPD_MMA_MIN_MODE")) S->upd_mma_min_mode = atoi(e);
+  if (const char *e = getenv("UFE_ND_BIG_MIN_CTAS")) S->big_min_ctas = atoi(e);      // tests: large-tile kernels on small meshes
   if (nranks > 1) S->use_graphs = 0;
   S->lev.resize(nl);
   // local fronts, level-major, p descending inside a level
@@ -1227,7 +1228,7 @@ static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *d
       b += nkb;
       if (trail <= 0) continue;
       const long long big_ctas = (long long)((trail + 127) / 128) * ((trail + 127) / 128) * n_upd;
-      const bool big = S->upd_big && trail >= 192 && big_ctas >= 120;
+      const bool big = S->upd_big && trail >= 192 && big_ctas >= S->big_min_ctas;
       // large trailing matrices: 128 x 64 tiles, 8 x 4 per thread, two CTAs (16 warps) per SM -- 6 % faster at 1 M vertices
       // than 128 x 128 / 8 x 8 with one CTA per SM; small ones: 64 x 64 tiles of 64 threads (8 x 8 per thread)
       const int nq = S->upd_nq ? S->upd_nq : (big ? 2 : 4);
@@ -1235,7 +1236,7 @@ static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *d
     }
     if (L.late_schur) {        // F22 -= L21 U12, one pass with K = p
       const long long big_ctas = (long long)((L.max_nb + 127) / 128) * ((L.max_nb + 127) / 128) * L.n;
-      const bool big = S->upd_big && L.max_nb >= 192 && big_ctas >= 120;
+      const bool big = S->upd_big && L.max_nb >= 192 && big_ctas >= S->big_min_ctas;
       UFE_TRY(mf_launch_update(S, st, L, big, S->upd_nq ? S->upd_nq : (big ? 2 : 4), L.max_nb, L.n, 0, 0, 2));
     }
   }
