@@ -629,10 +629,11 @@ def test_nd_multifrontal_solver_matches_sparse_LU(workload, leaf):
         sol.close()
 
 
-@pytest.mark.parametrize("late_schur_from, tensor_cores", [("256", "1"), ("64", "1"), ("64", "0"), ("0", "1")])
-def test_nd_factorisation_variants_agree(monkeypatch, late_schur_from, tensor_cores):
+@pytest.mark.parametrize("late_schur_from, tensor_cores, lazy_zero", [("256", "1", "1"), ("64", "1", "0"), ("64", "0", "1"), ("0", "1", "0")])
+def test_nd_factorisation_variants_agree(monkeypatch, late_schur_from, tensor_cores, lazy_zero):
     """The organisation of the trailing updates is a performance choice, not a numerical one: right-looking K = 64 passes,
-    the late Schur-complement pass with K = p (UFE_ND_SCHUR_MIN_P), fp64 SIMT or fp64 tensor cores (UFE_ND_UPD_MMA) give
+    the late Schur-complement pass with K = p (UFE_ND_SCHUR_MIN_P), fp64 SIMT or fp64 tensor cores (UFE_ND_UPD_MMA), one memset
+    of all fronts or level-by-level zeroing through a write-only extend-add (UFE_ND_LAZY_ZERO) give
     the sparse-LU solution of a wide-mesh stiffness system (fronts of up to ~900 unknowns, pivot counts above 256)."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
@@ -650,10 +651,12 @@ def test_nd_factorisation_variants_agree(monkeypatch, late_schur_from, tensor_co
     xr = spla.splu(M.tocsc()).solve(bb)
     monkeypatch.setenv("UFE_ND_SCHUR_MIN_P", late_schur_from)
     monkeypatch.setenv("UFE_ND_UPD_MMA", tensor_cores)
+    monkeypatch.setenv("UFE_ND_LAZY_ZERO", lazy_zero)
     sol = nd.Solver(np.asarray(mesh.TriGC), A.ptr, A.ind, 64)
     try:
         assert sol.info()["max_front"] > 512
         sol.factor(A.val)
+        sol.factor(A.val)                 # a second factorisation over the used fronts (nothing may survive from the first)
         x0, r0 = sol.solve(bb, n_refine=0)
         x1, r1 = sol.solve(bb, n_refine=2)
         assert r0 < 1e-10 and r1 < 1e-13, (r0, r1)

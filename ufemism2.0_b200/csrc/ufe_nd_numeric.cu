@@ -66,6 +66,7 @@ struct ufe_nd_solver {
   int rank = 0, nranks = 1;
   ncclComm_t nccl = nullptr;
   std::vector<MfLevel> lev;
+  std::vector<long long> lev_lo, lev_hi;      // range of F that holds the fronts of a level (level-major storage)
   std::vector<MfLink> links;
   // per local front (level-major order, p descending inside a level)
   int *ns = nullptr, *p = nullptr, *nb = nullptr, *G = nullptr, *ld = nullptr, *woff = nullptr, *dioff = nullptr,
@@ -92,7 +93,7 @@ struct ufe_nd_solver {
   double flops = 0.0;
   bool factored = false;
   int premul_pair = 1;                       // preconditioner mode: the right-hand side is multiplied by the 2x2 (1) or 1x1 (0) diagonal blocks
-  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384, upd_big = 1, upd_nq = 0, schur_min_p = 256, upd_mma = 1, upd_mma_min_mode = 2, big_min_ctas = 120;      // levels with at most this many (large) fronts use the cluster sweeps
+  int use_graphs = 1, k64 = 1, cl_max_fronts = 32, cl_min_g = 384, upd_big = 1, upd_nq = 0, schur_min_p = 256, upd_mma = 1, upd_mma_min_mode = 2, big_min_ctas = 120, lazy_zero = -1;     // lazy_zero: fronts zeroed level by level (-1: when they exceed 1 GB)      // levels with at most this many (large) fronts use the cluster sweeps
   MfGraph g_factor, g_apply[6];
 };
 
@@ -112,27 +113,34 @@ __global__ void k_mf_scale(int N, const int *__restrict__ ptr, const int *__rest
 }
 
 // one thread per matrix row: every (row, column) has its own destination, so plain adds are race-free
+// (only the destinations in [lo, hi): the fronts of one level, when the fronts are zeroed level by level)
 __global__ void k_mf_assemble(int N, const int *__restrict__ ptr, const int *__restrict__ ind, const double *__restrict__ val,
-                              const double *__restrict__ scale, const long long *__restrict__ dst, double *__restrict__ F) {
+                              const double *__restrict__ scale, const long long *__restrict__ dst, double *__restrict__ F,
+                              long long lo, long long hi) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const double si = scale[i];
   for (int k = ptr[i] - 1; k < ptr[i + 1] - 1; k++) {
     const long long d = dst[k];
-    if (d >= 0) F[d] += si * val[k] * scale[ind[k] - 1];
+    if (d >= lo && d < hi) F[d] += si * val[k] * scale[ind[k] - 1];
   }
 }
 
 // identity on the padded pivot rows [ns, p) of every front
-__global__ void k_mf_pad(int nf, const int *__restrict__ ns, const int *__restrict__ p, const int *__restrict__ ld,
+__global__ void k_mf_pad(int first, int nf, const int *__restrict__ ns, const int *__restrict__ p, const int *__restrict__ ld,
                          const long long *__restrict__ foff, double *__restrict__ F) {
-  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (f >= nf) return;
+  f += first;
   const int r = ns[f] + lane;
   if (r < p[f]) F[foff[f] + (size_t)r * ld[f] + r] = 1.0;
 }
 
 // parent front += Schur complements of its children (pull through the inverse maps; child 0 first, then child 1)
+// STORE: the parent has NOT been zeroed -- every entry of the front is written (sum of the children's contributions, or 0),
+// so a level costs one write pass instead of a memset and a read-modify-write; the matrix entries are added afterwards
+template <bool STORE>
 __global__ void __launch_bounds__(256)
 k_mf_extend(int first, const int *__restrict__ G_, const int *__restrict__ ld_, const long long *__restrict__ foff,
             const int *__restrict__ woff, const long long *__restrict__ cf0, const long long *__restrict__ cf1,
@@ -140,13 +148,13 @@ k_mf_extend(int first, const int *__restrict__ G_, const int *__restrict__ ld_, 
             const int *__restrict__ pinv1, double *__restrict__ F) {
   const int f = first + blockIdx.z;
   const long long o0 = cf0[f], o1 = cf1[f];
-  if (o0 < 0 && o1 < 0) return;
+  if (!STORE && o0 < 0 && o1 < 0) return;
   const int G = G_[f], ld = ld_[f];
   const int i0 = blockIdx.y * 32, j = blockIdx.x * 32 + threadIdx.x;
   if (i0 >= G || j >= G) return;
   const int *q0 = pinv0 + woff[f], *q1 = pinv1 + woff[f];
   const int b0 = o0 >= 0 ? q0[j] : -1, b1 = o1 >= 0 ? q1[j] : -1;
-  if (b0 < 0 && b1 < 0) return;
+  if (!STORE && b0 < 0 && b1 < 0) return;
   const int l0 = cld0[f], l1 = cld1[f];
   double *A = F + foff[f];
   for (int ii = threadIdx.y; ii < 32; ii += 8) {
@@ -156,7 +164,8 @@ k_mf_extend(int first, const int *__restrict__ G_, const int *__restrict__ ld_, 
     bool any = false;
     if (b0 >= 0) { const int a0 = q0[i]; if (a0 >= 0) { v += F[o0 + (size_t)a0 * l0 + b0]; any = true; } }
     if (b1 >= 0) { const int a1 = q1[i]; if (a1 >= 0) { v += F[o1 + (size_t)a1 * l1 + b1]; any = true; } }
-    if (any) A[(size_t)i * ld + j] += v;
+    if (STORE) A[(size_t)i * ld + j] = v;
+    else if (any) A[(size_t)i * ld + j] += v;
   }
 }
 
@@ -938,6 +947,7 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
   if (const char *e = getenv("UFE_ND_SCHUR_MIN_P")) S->schur_min_p = atoi(e);
   if (const char *e = getenv("UFE_ND_UPD_MMA")) S->upd_mma = atoi(e);
   if (const char *e = getenv("UFE_ND_UPD_MMA_MIN_MODE")) S->upd_mma_min_mode = atoi(e);
+  if (const char *e = getenv("UFE_ND_LAZY_ZERO")) S->lazy_zero = atoi(e);
   if (const char *e = getenv("UFE_ND_BIG_MIN_CTAS")) S->big_min_ctas = atoi(e);      // tests: large-tile kernels on small meshes
   if (nranks > 1) S->use_graphs = 0;
   S->lev.resize(nl);
@@ -1029,6 +1039,13 @@ static int mf_create(const ufe_nd_tree *T, int N, const int *ptr, const int *ind
       pwoff[c] = L.w_buf;
       L.child_schur = foff[c] + (long long)p[c] * ld[c] + p[c]; L.child_ld = ld[c]; L.child_wb = woff[c] + p[c];
     }
+  }
+  S->lev_lo.assign(nl, 0); S->lev_hi.assign(nl, 0);
+  for (int l = 0; l < nl; l++) {
+    const MfLevel &Lv = S->lev[l];
+    if (Lv.n == 0) continue;
+    const int fl = Lv.first + Lv.n - 1;
+    S->lev_lo[l] = foff[Lv.first]; S->lev_hi[l] = foff[fl] + (long long)ld[fl] * ld[fl];
   }
   // per-level / per-step launch shapes
   for (int l = 0; l < nl; l++) {
@@ -1174,9 +1191,15 @@ static int mf_launch_update(ufe_nd_solver *S, cudaStream_t st, const MfLevel &L,
 static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *dval) {
   const int N = S->N, tb = 256, nf = S->n_fronts;
   k_mf_scale<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dself, S->dpair); UFE_LAUNCH_CHECK();
-  UFE_CUDA(cudaMemsetAsync(S->F, 0, S->f_doubles * sizeof(double), st));
-  k_mf_assemble<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dst, S->F); UFE_LAUNCH_CHECK();
-  if (nf > 0) { k_mf_pad<<<(nf + 7) / 8, 256, 0, st>>>(nf, S->ns, S->p, S->ld, S->foff, S->F); UFE_LAUNCH_CHECK(); }
+  // Large problems: the fronts are zeroed level by level -- an internal level is WRITTEN by the extend-add (children's
+  // contributions or 0), then the matrix entries of that level are added -- instead of one memset of everything, one
+  // scatter and a read-modify-write extend-add per level (1 M vertices: 44 GB of fronts, 7 ms per avoided pass).
+  const bool lazy = S->lazy_zero >= 0 ? S->lazy_zero != 0 : S->f_doubles * sizeof(double) > ((size_t)1 << 30);
+  if (!lazy) {
+    UFE_CUDA(cudaMemsetAsync(S->F, 0, S->f_doubles * sizeof(double), st));
+    k_mf_assemble<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dst, S->F, 0LL, (long long)S->f_doubles); UFE_LAUNCH_CHECK();
+    if (nf > 0) { k_mf_pad<<<(nf + 7) / 8, 256, 0, st>>>(0, nf, S->ns, S->p, S->ld, S->foff, S->F); UFE_LAUNCH_CHECK(); }
+  }
   for (int l = (int)S->lev.size() - 1; l >= 0; l--) {
     const MfLevel &L = S->lev[l];
     // Schur complements of children on other ranks arrive first (the level below is complete on every rank)
@@ -1193,10 +1216,20 @@ static int mf_factor_launches(ufe_nd_solver *S, cudaStream_t st, const double *d
       g_launch_count++;
     }
     if (L.n == 0) continue;
-    if (L.n_internal > 0) {
+    if (lazy) {
+      const long long lo = S->lev_lo[l], hi = S->lev_hi[l];
+      if (L.n_internal > 0) {
+        const int t = (L.maxG + 31) / 32;
+        k_mf_extend<true><<<dim3(t, t, L.n), dim3(32, 8), 0, st>>>(L.first, S->G, S->ld, S->foff, S->woff, S->c_f[0], S->c_f[1], S->c_ld[0],
+                                                                    S->c_ld[1], S->pinv[0], S->pinv[1], S->F);
+        UFE_LAUNCH_CHECK();
+      } else UFE_CUDA(cudaMemsetAsync(S->F + lo, 0, (size_t)(hi - lo) * sizeof(double), st));
+      k_mf_pad<<<(L.n + 7) / 8, 256, 0, st>>>(L.first, L.n, S->ns, S->p, S->ld, S->foff, S->F); UFE_LAUNCH_CHECK();
+      k_mf_assemble<<<(N + tb - 1) / tb, tb, 0, st>>>(N, S->ptr, S->ind, dval, S->scale, S->dst, S->F, lo, hi); UFE_LAUNCH_CHECK();
+    } else if (L.n_internal > 0) {
       const int t = (L.maxG + 31) / 32;
-      k_mf_extend<<<dim3(t, t, L.n), dim3(32, 8), 0, st>>>(L.first, S->G, S->ld, S->foff, S->woff, S->c_f[0], S->c_f[1], S->c_ld[0],
-                                                            S->c_ld[1], S->pinv[0], S->pinv[1], S->F);
+      k_mf_extend<false><<<dim3(t, t, L.n), dim3(32, 8), 0, st>>>(L.first, S->G, S->ld, S->foff, S->woff, S->c_f[0], S->c_f[1], S->c_ld[0],
+                                                                   S->c_ld[1], S->pinv[0], S->pinv[1], S->F);
       UFE_LAUNCH_CHECK();
     }
     for (int b = 0; b < L.steps;) {
