@@ -98,9 +98,14 @@ enum { UFE_KRYLOV_BICGSTAB = 0, UFE_KRYLOV_GMRES = 1 };
 /* UFE_PC_BJACOBI_LU: block Jacobi over contiguous row ranges (like PETSc's per-rank blocks) with an
  * exact block-tridiagonal LU solve inside each block (the reference uses ILU(0) there). */
 enum { UFE_PC_JACOBI = 0, UFE_PC_BJACOBI2 = 1, UFE_PC_BJACOBI_LU = 2,
-       UFE_PC_AUTO = 3 /* BJACOBI_LU when its dense blocks fit the memory budget, else (one GPU) ND_LU when its fronts fit, else BJACOBI2 */,
-       UFE_PC_ND_LU = 4 /* exact: multifrontal nested-dissection factorisation of the whole matrix (csrc/ufe_nd_numeric.cu);
-                           for wide meshes whose banded blocks do not fit BJACOBI_LU; one GPU; krylov_pc_lag applies */ };
+       UFE_PC_AUTO = 3 /* ND_LU when the number of ranks is 1, 2, 4 or 8 and its fronts fit the device memory (env UFE_AUTO_ND=0
+                          skips it), else BJACOBI_LU when its dense blocks fit the memory budget, else BJACOBI2;
+                          ufe_solve_info.krylov_pc_used reports the choice */,
+       UFE_PC_ND_LU = 4 /* exact: multifrontal nested-dissection LU of the whole matrix (csrc/ufe_nd_numeric.cu), factorised
+                           once per Picard iteration (krylov_pc_lag applies), sub-trees distributed over 1, 2, 4 or 8 ranks.
+                           With fresh factors the linear solve is one Richardson step x = M^-1 b checked with the
+                           reference's stopping rule on the true scaled residual (n_Axb_its = 1); the Krylov method only
+                           continues from that x if the check fails */ };
 
 typedef struct ufe_config {
   int32_t do_include_SSADIVA_crossterms;           /* :276 */
