@@ -1,4 +1,4 @@
-// Numeric phase of the multifrontal nested-dissection solver (device code).
+// Numeric phase of the multifrontal nested-dissection solver (device code; DESIGN.md section 3, profiles/r2_notes.md).
 //
 // Exact solve of the DIVA / SSA stiffness system  A x = b  (solve_linearised_SSA_DIVA.f90:159 hands exactly this
 // system to PETSc, petsc_basic.f90:32-141).  The symbolic analysis (ufe_nd.cu) gives a binary elimination tree; every
@@ -10,11 +10,15 @@
 // back, sorted by p (descending) so that the fronts still active at pivot step b form a prefix of the level.
 //
 // Factorisation, deepest level first: right-looking block LU of the first p rows / columns, 32-wide pivot blocks,
-//      D_b^-1 (32 x 32 inverse, partial pivoting inside the block; kept in a side buffer),
-//      L_ib = A_ib D_b^-1  (i > b: later pivot rows AND the boundary rows),        [k_mf_panel]
-//      A_ij -= L_ib A_bj   (i, j > b; 128 x 128 tiles, 8 x 8 per thread, K = 32)   [k_mf_update]
-// which leaves L, U in place and the Schur complement in the boundary block; the parent PULLS the Schur complements of
-// its two children through inverse index maps (child 0 then child 1: fixed summation order, bit-reproducible). [k_mf_extend]
+//      D_b^-1 (32 x 32 inverse in registers, partial pivoting inside the block; kept in a side buffer),
+//      L_ib = A_ib D_b^-1  (i > b: later pivot rows AND the boundary rows),        [k_mf_panel, k_mf_panel2: two blocks per outer step]
+//      A_ij -= L_ib A_bj   (i, j > b; K = 64 per pass, 8 x 8 / 8 x 4 register tiles) [k_mf_update]
+// which leaves L, U in place and the Schur complement in the boundary block.  Fronts with many pivots: the steps leave
+// the boundary block F22 alone and it is updated once, F22 -= L21 U12 with K = p, on the fp64 tensor cores
+// (mma.sync.m8n8k4.f64)                                                              [k_mf_update_mma]
+// The parent PULLS the Schur complements of its two children through inverse index maps (child 0 then child 1: fixed
+// summation order, bit-reproducible); for large problems it WRITES the parent (contributions or 0) so that the fronts
+// need no memset, and the matrix entries of the level are added afterwards.          [k_mf_extend<STORE>, k_mf_assemble]
 // Solve: one CTA per front and one launch per level and direction: forward  y = L^-1 w  (boundary rows collect the
 // update for the parent, which pulls them), backward  x_s = U11^-1 (y - U12 x_b)  with x_b read from the parent.
 //
