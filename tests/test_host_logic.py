@@ -444,3 +444,35 @@ def test_nd_tree_distribution_over_ranks():
         assert tri_per_rank.max() < 1.35 * nT / P, tri_per_rank      # coordinate bisection balances the sub-trees
     with pytest.raises(capi.UfeError, match="power of two"):
         nd.analyse(np.asarray(mesh.TriGC), B.indptr.astype(np.int32), B.indices.astype(np.int32), 48, nranks=(3,))
+
+
+def test_nd_analysis_is_independent_of_the_host_thread_count(tmp_path):
+    """The once-per-mesh symbolic analysis runs the two halves of the top cuts on different host threads and appends their
+    sub-trees in post-order: the tree, the extend-add maps and the entry map must be exactly the single-threaded ones."""
+    script = tmp_path / "nd_sum.py"
+    script.write_text(textwrap.dedent("""
+        import hashlib, sys
+        sys.path.insert(0, %r)
+        import ufe_pkg; ufe_pkg.load()
+        import numpy as np, scipy.sparse as sp
+        from ufemism2_0_b200 import experiments, nd
+        mesh, C, ice = experiments.antarctic(30000)
+        nT = mesh.nTri
+        Tri = np.asarray(mesh.Tri) - 1
+        P = sp.csr_matrix((np.ones(3 * nT), (np.repeat(np.arange(nT), 3), Tri.ravel())), shape=(nT, mesh.nV))
+        B = (P @ P.T).tocsr(); B.sort_indices()
+        T = nd.analyse(np.asarray(mesh.TriGC), B.indptr.astype(np.int32), B.indices.astype(np.int32), 32, nranks=(4,))
+        h = hashlib.sha256()
+        for q in T.nodes:
+            h.update(np.int32([q.level, q.parent]).tobytes()); h.update(q.sep.tobytes()); h.update(q.bnd.tobytes()); h.update(q.up.tobytes())
+        for a in (T.entry_node, T.entry_row, T.entry_col, T.owners[4]):
+            h.update(np.ascontiguousarray(a).tobytes())
+        print(len(T.nodes), T.n_levels, T.max_front, h.hexdigest())
+        """ % ROOT))
+    out = []
+    for threads in ("1", "8"):
+        env = dict(os.environ, UFE_ND_HOST_THREADS=threads)
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(r.stdout.strip().splitlines()[-1])
+    assert out[0] == out[1], out
