@@ -476,3 +476,60 @@ def test_nd_analysis_is_independent_of_the_host_thread_count(tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         out.append(r.stdout.strip().splitlines()[-1])
     assert out[0] == out[1], out
+
+
+def test_pivot_block_inversion_scheme():
+    """numpy restatement of mf_inv32_cta (csrc/ufe_nd_numeric.cu): in-place Gauss-Jordan where column p is replaced by the
+    inverse's column of the pivot row, implicit threshold pivoting as a row permutation, lazy row scaling, the columns
+    processed in groups of four (the owner group runs its four steps first, the other groups apply them afterwards), and
+    the final scatter Ip[pinv[i]][perm[q]] = a_i[q] s_i.  Checks the scheme itself on well- and badly-pivoted blocks."""
+    rng = np.random.default_rng(7)
+
+    def invert(A, thresh=0.05):
+        n = A.shape[0]
+        W = A.copy()
+        perm = list(range(n))
+        s = np.ones(n)
+        for g in range(n // 4):
+            cols = list(range(4 * g, 4 * g + 4))
+            steps = []
+            for t, p in enumerate(cols):                    # the owner of the four columns, on its own columns only
+                c = W[:, p].copy()
+                if abs(c[perm[p]]) < thresh:
+                    cand = [(abs(c[perm[k]]), -k) for k in range(p, n)]
+                    k = -max(cand)[1]
+                    perm[p], perm[k] = perm[k], perm[p]
+                P = perm[p]
+                piv = c[P]
+                if abs(piv) < 1e-13:
+                    piv = -1e-13 if piv < 0 else 1e-13
+                d = 1.0 / piv
+                m = c * d
+                m[P] = 0.0
+                s[P] = d
+                steps.append((m, P))
+                for q in cols:
+                    W[:, q] -= m * W[P, q]
+                W[:, p] = -m
+                W[P, p] = 1.0
+            for m, P in steps:                              # every other group applies the four steps to its columns
+                for q in range(n):
+                    if q not in cols:
+                        W[:, q] -= m * W[P, q]
+        pinv = [0] * n
+        for p in range(n):
+            pinv[perm[p]] = p
+        out = np.zeros_like(A)
+        for i in range(n):
+            for q in range(n):
+                out[pinv[i], perm[q]] = W[i, q] * s[i]
+        return out
+
+    for case in range(6):
+        A = rng.standard_normal((32, 32)) * 0.3
+        if case < 2:
+            A += np.eye(32)                                  # Jacobi-scaled fronts: unit diagonal, no pivot search
+        if case == 5:
+            A[:, 3] *= 1e-3; A[7, 7] = 0.0                   # small pivots force the search
+        X = invert(A)
+        assert np.abs(X @ A - np.eye(32)).max() < 1e-9 * max(1.0, np.abs(X).max()), case
